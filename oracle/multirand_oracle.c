@@ -1,0 +1,232 @@
+/*
+ * oracle/multirand_oracle.c -- CPU restatement of the reference RNG module (src/multirand.F90).
+ * TEST INFRASTRUCTURE ONLY (see pic1dp_oracle.h).  Pinned by the reference's own known-answer
+ * vectors (src/multirand.F90:396-425), checked in tests/test_oracle_multirand.py.
+ *
+ * Fortran signed 64-bit wrap-around arithmetic is restated on uint64_t; ishft(x,-k) is a logical
+ * right shift, ishft(x,k) a logical left shift.
+ */
+#include "pic1dp_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NSEED 20635 /* multirand_nseed, src/multirand.F90:83 */
+
+struct orc_multirand {
+  uint64_t seeds[NSEED];
+  int iseed;
+  int al_int;
+  int gauss_filled;
+  double gauss_buf;
+};
+
+orc_multirand *orc_multirand_new(void) { return (orc_multirand *)calloc(1, sizeof(orc_multirand)); }
+void orc_multirand_free(orc_multirand *g) { free(g); }
+
+static inline uint64_t xorshl(uint64_t x, int k) { return x ^ (x << k); }
+static inline uint64_t xorshr(uint64_t x, int k) { return x ^ (x >> k); }
+
+/* George Marsaglia's 64-bit KISS: src/multirand.F90:921-945 */
+static uint64_t kiss64(orc_multirand *g) {
+  uint64_t *s = g->seeds;
+  uint64_t t = (s[0] << 58) + s[3];
+  if ((s[0] >> 63) == (t >> 63))
+    s[3] = (s[0] >> 6) + (s[0] >> 63);
+  else
+    s[3] = (s[0] >> 6) - ((s[0] + t) >> 63) + 1;
+  s[0] = s[0] + t;
+  s[1] = xorshl(s[1], 13);
+  s[1] = xorshr(s[1], 17);
+  s[1] = xorshl(s[1], 43);
+  s[2] = 6906969069ULL * s[2] + 1234567ULL;
+  return s[0] + s[1] + s[2];
+}
+
+/* 64-bit Mersenne Twister 19937: src/multirand.F90:952-997 */
+static uint64_t mt19937_64(orc_multirand *g) {
+  enum { nn = 312, mm = 156 };
+  const uint64_t um = 0xFFFFFFFF80000000ULL, lm = 0x000000007FFFFFFFULL;
+  const uint64_t mag01[2] = {0ULL, 0xB5026F5AA96619E9ULL};
+  uint64_t *s = g->seeds, x;
+  if (g->iseed >= nn) {
+    int i;
+    for (i = 0; i < nn - mm; i++) {
+      x = (s[i] & um) | (s[i + 1] & lm);
+      s[i] = s[i + mm] ^ (x >> 1) ^ mag01[x & 1ULL];
+    }
+    for (; i < nn - 1; i++) {
+      x = (s[i] & um) | (s[i + 1] & lm);
+      s[i] = s[i + (mm - nn)] ^ (x >> 1) ^ mag01[x & 1ULL];
+    }
+    x = (s[nn - 1] & um) | (s[0] & lm);
+    s[nn - 1] = s[mm - 1] ^ (x >> 1) ^ mag01[x & 1ULL];
+    g->iseed = 0;
+  }
+  x = s[g->iseed];
+  x ^= (x >> 29) & 0x5555555555555555ULL;
+  x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+  x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+  x ^= (x >> 43);
+  g->iseed++;
+  return x;
+}
+
+/* George Marsaglia's 64-bit SuperKISS: src/multirand.F90:1004-1039 */
+static uint64_t superkiss64(orc_multirand *g) {
+  enum { nn = 20632, icarry = nn, ixcng = nn + 1, ixs = nn + 2 };
+  uint64_t *s = g->seeds;
+  if (g->iseed >= nn) {
+    for (int i = 0; i < nn; i++) {
+      uint64_t h = s[icarry] & 1ULL;
+      uint64_t z = ((s[i] << 41) >> 1) + ((s[i] << 39) >> 1) + (s[icarry] >> 1);
+      s[icarry] = (s[i] >> 23) + (s[i] >> 25) + (z >> 63);
+      s[i] = ~((z << 1) + h);
+    }
+    g->iseed = 0;
+  }
+  s[ixcng] = s[ixcng] * 6906969069ULL + 123ULL;
+  s[ixs] = xorshl(s[ixs], 13);
+  s[ixs] = xorshr(s[ixs], 17);
+  s[ixs] = xorshl(s[ixs], 43);
+  uint64_t r = s[g->iseed] + s[ixcng] + s[ixs];
+  g->iseed++;
+  return r;
+}
+
+int64_t orc_multirand_int64(orc_multirand *g) {
+  uint64_t r;
+  if (g->al_int == 2)
+    r = mt19937_64(g);
+  else if (g->al_int == 3)
+    r = superkiss64(g);
+  else
+    r = kiss64(g);
+  return (int64_t)r;
+}
+
+/* INT2REAL64: src/multirand.F90:49 -- signed int64 -> real64, / (2^64-1), + 0.5; [0,1] inclusive */
+double orc_multirand_real64(orc_multirand *g) {
+  return (double)orc_multirand_int64(g) / 18446744073709551615.0 + 0.5;
+}
+
+/* default seeds used by multirand_selftest: src/multirand.F90:476-518 */
+void orc_multirand_seed_default(orc_multirand *g, int al_int) {
+  uint64_t *s = g->seeds;
+  memset(g, 0, sizeof(*g));
+  g->al_int = al_int;
+  if (al_int == 2) {
+    s[0] = 5489ULL;
+    for (int i = 1; i < 312; i++) s[i] = 6364136223846793005ULL * xorshr(s[i - 1], 62) + (uint64_t)i;
+    g->iseed = 312;
+  } else if (al_int == 3) {
+    s[20632] = 36243678541ULL;
+    s[20633] = 12367890123456ULL;
+    s[20634] = 521288629546311ULL;
+    for (int i = 0; i < 20632; i++) {
+      s[20633] = s[20633] * 6906969069ULL + 123ULL;
+      s[20634] = xorshl(s[20634], 13);
+      s[20634] = xorshr(s[20634], 17);
+      s[20634] = xorshl(s[20634], 43);
+      s[i] = s[20633] + s[20634];
+    }
+    g->iseed = 20632;
+  } else {
+    s[0] = 1234567890987654321ULL;
+    s[1] = 362436362436362436ULL;
+    s[2] = 1066149217761810ULL;
+    s[3] = 123456123456123456ULL;
+  }
+}
+
+static const int64_t primes1[100] = {
+    15484219, 15484223, 15484243, 15484247, 15484279, 15484333, 15484363, 15484387, 15484393, 15484409,
+    15484421, 15484453, 15484457, 15484459, 15484471, 15484489, 15484517, 15484519, 15484549, 15484559,
+    15484591, 15484627, 15484631, 15484643, 15484661, 15484697, 15484709, 15484723, 15484769, 15484771,
+    15484783, 15484817, 15484823, 15484873, 15484877, 15484879, 15484901, 15484919, 15484939, 15484951,
+    15484961, 15484999, 15485039, 15485053, 15485059, 15485077, 15485083, 15485143, 15485161, 15485179,
+    15485191, 15485221, 15485243, 15485251, 15485257, 15485273, 15485287, 15485291, 15485293, 15485299,
+    15485311, 15485321, 15485339, 15485341, 15485357, 15485363, 15485383, 15485389, 15485401, 15485411,
+    15485429, 15485441, 15485447, 15485471, 15485473, 15485497, 15485537, 15485539, 15485543, 15485549,
+    15485557, 15485567, 15485581, 15485609, 15485611, 15485621, 15485651, 15485653, 15485669, 15485677,
+    15485689, 15485711, 15485737, 15485747, 15485761, 15485773, 15485783, 15485801, 15485807, 15485837};
+static const int64_t primes2[100] = {
+    7001, 7013, 7019, 7027, 7039, 7043, 7057, 7069, 7079, 7103, 7109, 7121, 7127, 7129, 7151, 7159, 7177,
+    7187, 7193, 7207, 7211, 7213, 7219, 7229, 7237, 7243, 7247, 7253, 7283, 7297, 7307, 7309, 7321, 7331,
+    7333, 7349, 7351, 7369, 7393, 7411, 7417, 7433, 7451, 7457, 7459, 7477, 7481, 7487, 7489, 7499, 7507,
+    7517, 7523, 7529, 7537, 7541, 7547, 7549, 7559, 7561, 7573, 7577, 7583, 7589, 7591, 7603, 7607, 7621,
+    7639, 7643, 7649, 7669, 7673, 7681, 7687, 7691, 7699, 7703, 7717, 7723, 7727, 7741, 7753, 7757, 7759,
+    7789, 7793, 7817, 7823, 7829, 7841, 7853, 7867, 7873, 7877, 7879, 7883, 7901, 7907, 7919};
+
+static inline int64_t i64abs(int64_t a) { return a < 0 ? -a : a; }
+
+/* seed_type == 1 (constant seeds, rank dependent) + warm-up: src/multirand.F90:301-381.
+ * The SuperKISS fix-up loop at :346 tests the wrong array (reference defect, SURVEY App.A-7); with the
+ * default self test enabled it never iterates, and this restatement skips it. */
+void orc_multirand_init_const(orc_multirand *g, int al_int, int mype, int warmup) {
+  int64_t nseed = (al_int == 2) ? 312 : (al_int == 3) ? 20635 : 4;
+  memset(g, 0, sizeof(*g));
+  g->al_int = al_int;
+  int64_t clock = primes1[1]; /* :305 */
+  int64_t s4[4];
+  for (int i = 0; i < 4; i++) s4[i] = clock; /* :307 */
+  {                                          /* :308-313, mype is always present in pic1dp */
+    int64_t idx = i64abs(clock + primes2[i64abs(clock) % 100] * (int64_t)mype) % 100;
+    for (int i = 0; i < 4; i++) s4[i] += primes1[idx] * (int64_t)mype;
+  }
+  for (int i = 0; i < 4; i++) { /* :314-320 */
+    int64_t idx = i64abs(s4[i] + primes1[i64abs(clock) % 100] * (int64_t)i) % 100;
+    s4[i] += primes2[idx] * (int64_t)i;
+  }
+  for (int i = 0; i < 4; i++) g->seeds[i] = (uint64_t)s4[i];
+
+  uint64_t *tmp = (uint64_t *)calloc(NSEED, sizeof(uint64_t));
+  for (int i = 1; i <= 20; i++) tmp[0] = kiss64(g);        /* :322-324 */
+  for (int64_t i = 1; i < nseed; i++) tmp[i] = kiss64(g);  /* :325-327 */
+  if (al_int == 1) {                                       /* :332-340 */
+    while (tmp[1] == 0) tmp[1] = kiss64(g);
+    while (tmp[0] == 0 && tmp[3] == 0) {
+      tmp[0] = kiss64(g);
+      tmp[3] = kiss64(g);
+    }
+  }
+  memcpy(g->seeds, tmp, NSEED * sizeof(uint64_t)); /* :350 */
+  free(tmp);
+  if (al_int == 2)
+    g->iseed = 312; /* :359 */
+  else if (al_int == 3)
+    g->iseed = 20632; /* :365 */
+  for (int64_t i = 1; i <= (int64_t)warmup * nseed; i++) (void)orc_multirand_int64(g); /* :379-381 */
+}
+
+/* src/multirand.F90:664-690 (no exclusions, as called from particle_load) */
+void orc_multirand_real_array(orc_multirand *g, double *a, int64_t n) {
+  for (int64_t i = 0; i < n; i++) a[i] = orc_multirand_real64(g);
+}
+
+/* Marsaglia polar method, array form: src/multirand.F90:838-872 */
+void orc_multirand_gaussian_array(orc_multirand *g, double *a, int64_t n) {
+  const double max64 = 9223372036854775807.0;
+  int64_t lo = 0;
+  if (g->gauss_filled && n > 0) {
+    a[lo++] = g->gauss_buf;
+    g->gauss_filled = 0;
+  }
+  for (int64_t i = lo; i < n; i += 2) {
+    double x, y, w;
+    do {
+      x = (double)orc_multirand_int64(g) / max64;
+      y = (double)orc_multirand_int64(g) / max64;
+      w = x * x + y * y;
+    } while (!(w > 0.0 && w < 1.0));
+    w = sqrt((-2.0 * log(w)) / w);
+    a[i] = x * w;
+    if (i < n - 1) {
+      a[i + 1] = y * w;
+    } else {
+      g->gauss_buf = y * w;
+      g->gauss_filled = 1;
+    }
+  }
+}
