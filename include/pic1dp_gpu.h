@@ -1,0 +1,239 @@
+/*
+ * include/pic1dp_gpu.h -- C ABI of the B200-native PIC1D hot path (libpic1dp_b200.so).
+ *
+ * This is the drop-in boundary for the per-timestep vector-matrix PIC cycle of PIC1D-PETSc
+ * (wenjundeng/pic1dp).  The reference has no plugin registry: the path sits behind argument-less Fortran
+ * module procedures over module-global PETSc Vec/Mat state.  Each entry point below cites the reference
+ * interface it replaces (file:line into the reference tree); fortran/pic1dp_gpu_shim.F90 shows the
+ * ISO_C_BINDING side a maintainer adds inside pic1dp_particle / pic1dp_field / pic1dp_interaction
+ * (INTEGRATION.md walks through it).
+ *
+ * Conventions
+ *  - Plain C: pointers, sizes, POD structs.  No torch / CUDA types in any signature.
+ *  - Every call returns int: 0 = PIC1DP_OK, otherwise a PIC1DP_E* code; the Fortran shim stores it into
+ *    global_ierr and applies CHKERRQ exactly as it does after PETSc calls (src/pic1dp_global.F90:59).
+ *    pic1dp_gpu_strerror() maps a code to text; pic1dp_gpu_last_error() returns the detailed message of
+ *    the last failure on that handle.
+ *  - The library owns all device memory from create to destroy.  Host pointers are borrowed for the
+ *    duration of one call.  Marker arrays held by the host go stale between get_markers calls.
+ *  - One host thread <-> one handle <-> one GPU <-> one CUDA stream.  Calls are asynchronous on that stream
+ *    and ordered; calls that return data to the host synchronise.  Not thread-safe per handle (neither is the
+ *    reference: module save state, src/multirand.F90:43-44).
+ *  - All marker and grid data are fp64 (PetscScalar real double, src/pic1dp_global.F90:28-30); cell indices
+ *    int32 (PetscInt).
+ */
+#ifndef PIC1DP_GPU_H
+#define PIC1DP_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIC1DP_ABI_VERSION 1
+#define PIC1DP_MAX_SPECIES 4
+#define PIC1DP_MAX_MODES 64
+#define PIC1DP_UNIQUE_ID_BYTES 128
+
+/* error codes */
+enum {
+  PIC1DP_OK = 0,
+  PIC1DP_EINVAL = 1,      /* bad argument / parameter combination (input_init checks, src/pic1dp_input.F90:292-307) */
+  PIC1DP_ECUDA = 2,       /* CUDA runtime error (message in last_error) */
+  PIC1DP_ENCCL = 3,       /* NCCL error or NCCL library not loadable */
+  PIC1DP_ENOMEM = 4,      /* device/host allocation failed */
+  PIC1DP_ESTATE = 5,      /* call sequence error (e.g. push before markers were set) */
+  PIC1DP_ECAPACITY = 6,   /* marker count exceeds the capacity given at create */
+  PIC1DP_ENODEVICE = 7,   /* no CUDA device: this library has no CPU fallback */
+  PIC1DP_EUNSUPPORTED = 8 /* requested mode not available for these parameters (e.g. smem grid too large) */
+};
+
+/* deposit (S^T w) strategies; all give the same sum up to fp64 summation order */
+enum {
+  PIC1DP_DEPOSIT_AUTO = 0,       /* pick by nx */
+  PIC1DP_DEPOSIT_SMEM_ATOMIC = 1,/* per-CTA shared-memory grid, fp64 atomicAdd; CTA partials reduced in fixed order */
+  PIC1DP_DEPOSIT_GLOBAL_RED = 2, /* RED.ADD.F64 into an L2-resident per-CTA private grid */
+  PIC1DP_DEPOSIT_WARP_PRIVATE = 3/* per-warp private shared-memory grid, lane-ordered duplicate merge: bitwise
+                                    run-to-run deterministic ("deterministic deposition") */
+};
+
+/* field-solve summation order for the partial-DFT projections */
+enum {
+  PIC1DP_FIELD_TREE = 0,      /* fixed-shape block tree reduction (deterministic, fast) */
+  PIC1DP_FIELD_SEQUENTIAL = 1 /* j = 0..nx-1 in order: bit-identical to sequential-AIJ MatMultTranspose on one rank */
+};
+
+/*
+ * Run-time copy of the reference's compile-time parameters that the hot path reads
+ * (src/pic1dp_input.F90:32-256), plus placement.  Fill with pic1dp_gpu_params_default() first.
+ */
+typedef struct pic1dp_params {
+  int32_t abi_version;                      /* PIC1DP_ABI_VERSION */
+  int32_t struct_bytes;                     /* sizeof(pic1dp_params) */
+  /* grid and field (src/pic1dp_input.F90:47, :75-80, :128) */
+  int32_t nx;                               /* input_nx */
+  int32_t nmode;                            /* input_nmode */
+  int32_t modes[PIC1DP_MAX_MODES];          /* input_modes */
+  double lx;                                /* input_lx */
+  double dt;                                /* input_dt (:109) */
+  /* species (:57-72) */
+  int32_t nspecies;                         /* input_nspecies */
+  double charge[PIC1DP_MAX_SPECIES];        /* input_species_charge */
+  double mass[PIC1DP_MAX_SPECIES];          /* input_species_mass */
+  double temperature[PIC1DP_MAX_SPECIES];   /* input_species_temperature */
+  double temperature2[PIC1DP_MAX_SPECIES];  /* input_species_temperature2 */
+  double density[PIC1DP_MAX_SPECIES];       /* input_species_density */
+  double v0[PIC1DP_MAX_SPECIES];            /* input_species_v0 */
+  /* model switches */
+  int32_t iptcldist;                        /* input_iptcldist (:54) 0 Maxwellian 1 two-stream1 2 two-stream2 3 bump-on-tail */
+  int32_t deltaf;                           /* input_deltaf (:106) */
+  int32_t linear;                           /* input_linear (:43) */
+  int32_t iptclshape;                       /* input_iptclshape (:138): 1,2 -> right weight `frac` and matrix-path
+                                               scaling (src/pic1dp_particle.F90:322-323, interaction.F90:46-78);
+                                               3,4 -> right weight 1-(1-frac), array-path scaling (:79-151) */
+  /* placement */
+  int64_t capacity;                         /* local marker capacity per species (this rank's share of input_nparticle_max) */
+  int32_t device;                           /* CUDA device ordinal */
+  int32_t rank;                             /* global_mype */
+  int32_t nranks;                           /* global_npe */
+  /* implementation choices */
+  int32_t deposit_mode;                     /* PIC1DP_DEPOSIT_* */
+  int32_t field_mode;                       /* PIC1DP_FIELD_* */
+  int32_t fuse;                             /* 1: push also wraps x and deposits (collect_charge then only reduces);
+                                               0: each call has exactly the reference's side effects */
+  int32_t reserved[8];
+} pic1dp_params;
+
+typedef struct pic1dp_gpu pic1dp_gpu_t; /* opaque handle: the module-global state of the three Fortran modules */
+
+/* defaults of src/pic1dp_input.F90 (electron bump-on-tail, nx=192, 1 mode, dt=0.05, delta-f nonlinear, shape 4) */
+void pic1dp_gpu_params_default(pic1dp_params *p);
+
+/* library / ABI identification */
+int pic1dp_gpu_abi_version(void);
+const char *pic1dp_gpu_strerror(int code);
+const char *pic1dp_gpu_last_error(const pic1dp_gpu_t *h); /* h may be NULL: last create() failure */
+
+/*
+ * create: replaces particle_init (src/pic1dp_particle.F90:66-139: VecCreate/VecDuplicate of x,v,p,w,*_bak) and
+ * field_init (src/pic1dp_field.F90:55-212: field Vecs, 1/k operator :158-174, partial-DFT matrices :176-210).
+ * Validates parameters like input_init (src/pic1dp_input.F90:287-308).  Fails with PIC1DP_ENODEVICE when no
+ * GPU is present -- there is no CPU fallback.
+ */
+int pic1dp_gpu_create(const pic1dp_params *p, pic1dp_gpu_t **out);
+
+/* destroy: replaces particle_final (src/pic1dp_particle.F90:819-858) and field_final (src/pic1dp_field.F90:315-348) */
+int pic1dp_gpu_destroy(pic1dp_gpu_t *h);
+
+/*
+ * Multi-GPU: replaces MPI_COMM_WORLD as used by MPI_Allreduce at src/pic1dp_interaction.F90:132-133.
+ * Rank 0 calls comm_unique_id, the host broadcasts the 128 bytes (MPI_Bcast in the Fortran host,
+ * torch.distributed in bench.py), every rank calls comm_init.  With nranks == 1 neither call is needed and
+ * NCCL is never loaded.
+ */
+int pic1dp_gpu_comm_unique_id(uint8_t id[PIC1DP_UNIQUE_ID_BYTES]);
+int pic1dp_gpu_comm_init(pic1dp_gpu_t *h, const uint8_t id[PIC1DP_UNIQUE_ID_BYTES]);
+
+/*
+ * set_markers: H2D of one species after particle_load (src/pic1dp_particle.F90:145-269 fills x,v,p,w through
+ * VecGetArrayF90).  np = particle_np(ispecies) (:248).  isp is 0-based.
+ */
+int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const double *x, const double *v,
+                           const double *p, const double *w);
+
+/*
+ * get_markers: D2H refresh of the host Vecs before pic1dp_output reads them (src/pic1dp_output.F90:128-150,
+ * :228-237) or before particle_optimize.  Any of x,v,p,w may be NULL.  *np receives particle_np.
+ */
+int pic1dp_gpu_get_markers(pic1dp_gpu_t *h, int32_t isp, double *x, double *v, double *p, double *w, int64_t *np);
+
+/*
+ * compute_shape_x: replaces particle_compute_shape_x (src/pic1dp_particle.F90:275-350) for iptclshape 1-3:
+ * wraps x in place (:308-310).  No matrix or (index, weight) array is materialised -- weights are recomputed
+ * on the fly with the rounding that iptclshape selects.  No-op for iptclshape 4, as in the reference driver
+ * (src/pic1dp.F90:65, :86).
+ */
+int pic1dp_gpu_compute_shape_x(pic1dp_gpu_t *h);
+
+/*
+ * get_shape_x: the (index, weight) arrays that particle_compute_shape_x stores for iptclshape 3
+ * (particle_shape_x_indexes / particle_shape_x_values, src/pic1dp_particle.F90:47-48, :331-332) and the two
+ * matrix values of a row for iptclshape 1,2 (:320-323), computed from the current x without modifying it:
+ * indexes[i] = left cell ix1, values_left[i] = 1-frac, values_right[i] = frac (shape 1,2) or 1-(1-frac) (3,4).
+ * Debug / parity interface: the hot path never stores these.  Any output pointer may be NULL.
+ */
+int pic1dp_gpu_get_shape_x(pic1dp_gpu_t *h, int32_t isp, int32_t *indexes, double *values_left,
+                           double *values_right);
+
+/*
+ * collect_charge: replaces interaction_collect_charge (src/pic1dp_interaction.F90:33-155): wrap x (:102-104),
+ * deposit S^T w (:96-114), species charge (:126-127), all-reduce over ranks (:132-133), scale to density
+ * (:140-148).  Result: field_chargeden on every rank.
+ */
+int pic1dp_gpu_collect_charge(pic1dp_gpu_t *h);
+
+/*
+ * solve_field: replaces field_solve_electric (src/pic1dp_field.F90:218-270): partial DFT of rho onto the kept
+ * modes, 1/k, inverse.  Results: field_electric, field_mode_re, field_mode_im.  Solved redundantly on every rank
+ * (replaces the E all-gather VecScatter at src/pic1dp_interaction.F90:197-206).
+ */
+int pic1dp_gpu_solve_field(pic1dp_gpu_t *h);
+
+/*
+ * push: replaces interaction_push_particle (src/pic1dp_interaction.F90:161-370) for global_irk = irk (1 or 2):
+ * backup (:178-189, done by buffer rotation, no copy), gather S.E (:243-257), push x (:261), w (:266-331),
+ * v (:335-338).  With params.fuse == 1 the wrap + deposit of the following collect_charge is folded in.
+ */
+int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk);
+
+/*
+ * step: nsteps iterations of the reference time loop body (src/pic1dp.F90:79-93):
+ * do irk = 1,2 { push; [compute_shape_x]; collect_charge; solve_field }.  Same results as the individual calls.
+ */
+int pic1dp_gpu_step(pic1dp_gpu_t *h, int32_t nsteps);
+
+/* field access: field_electric, field_chargeden, field_mode_re, field_mode_im (src/pic1dp_field.F90:27-31);
+ * any pointer may be NULL.  get synchronises. */
+int pic1dp_gpu_get_field(pic1dp_gpu_t *h, double *electric, double *chargeden, double *mode_re, double *mode_im);
+/* set field_chargeden / field_electric from the host (what field_test does with VecSetValues,
+ * src/pic1dp_field.F90:286-297); either may be NULL */
+int pic1dp_gpu_set_field(pic1dp_gpu_t *h, const double *electric, const double *chargeden);
+
+/* the partial-DFT operators built at create (src/pic1dp_field.F90:158-210): F_re, F_im row-major [j*nmode+m],
+ * grad_inv[nmode]; any may be NULL */
+int pic1dp_gpu_get_operators(pic1dp_gpu_t *h, double *F_re, double *F_im, double *grad_inv);
+
+/* field energy |E|_2^2 * lx / nx (src/pic1dp_output.F90:120-123), reduced on the device */
+int pic1dp_gpu_field_energy(pic1dp_gpu_t *h, double *energy);
+
+/* block until all queued work of this handle is done; surfaces asynchronous CUDA errors */
+int pic1dp_gpu_sync(pic1dp_gpu_t *h);
+
+/* ---- instrumentation (replaces the wtimer slots global_iwt_push_particle / _collect_charge / _mpiallredu /
+ * _field_electric, src/pic1dp_global.F90:38-50, with CUDA events on the handle's stream) ---- */
+int pic1dp_gpu_timer_start(pic1dp_gpu_t *h);
+int pic1dp_gpu_timer_stop(pic1dp_gpu_t *h, float *milliseconds); /* synchronises */
+
+typedef struct pic1dp_counters {
+  int64_t kernel_launches;   /* kernels of this library launched on this handle so far */
+  int64_t nccl_calls;        /* ncclAllReduce calls issued */
+  int64_t oob_markers;       /* markers whose wrapped x was exactly lx (ix == nx; the reference writes out of
+                                bounds there, src/pic1dp_interaction.F90:104-113); deposited as ix=0, s=1 */
+  int64_t h2d_bytes;         /* bytes copied host->device by this handle */
+  int64_t d2h_bytes;         /* bytes copied device->host */
+  int32_t deposit_mode;      /* resolved PIC1DP_DEPOSIT_* */
+  int32_t grid_ctas;         /* CTAs of the particle kernels */
+  int32_t cta_threads;
+  int32_t smem_bytes;        /* dynamic shared memory of the fused kernel */
+} pic1dp_counters;
+int pic1dp_gpu_get_counters(pic1dp_gpu_t *h, pic1dp_counters *c);
+
+/* per-kernel device time of one profiled timestep (each launch bracketed by events; slower than step()):
+ * ms[0] push+deposit irk=1, ms[1] reduce+allreduce irk=1, ms[2] field irk=1, ms[3..5] same for irk=2 */
+int pic1dp_gpu_profile_step(pic1dp_gpu_t *h, float ms[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIC1DP_GPU_H */

@@ -1,0 +1,151 @@
+// field_kernels.cuh -- grid-side kernels of the PIC1D hot path for sm_100a.
+//
+//  k_reduce_charge : fixed-order sum of the per-CTA private grids + species charge
+//                    (/root/reference/src/pic1dp_interaction.F90:81, :126-127; matrix path :52-59)
+//  k_finalize_rho  : scale to charge density + full-f offset after the all-reduce (:140-148; matrix path :64-78)
+//  k_field_solve   : mode-filtered partial DFT, 1/k, inverse (/root/reference/src/pic1dp_field.F90:231-256).
+//                    There is no KSP / tridiagonal solve in the reference: only the kept modes survive.
+//  k_field_energy  : |E|_2^2 * lx / nx (/root/reference/src/pic1dp_output.F90:120-123)
+//
+// The grid is tiny (nx <= a few thousand): these are single- or few-CTA kernels, latency- not bandwidth-bound.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "particle_kernels.cuh"
+
+namespace pic1dp {
+
+struct GridArgs {
+  int nx, nmode, nspecies, ngrids;  // ngrids = CTAs of the particle kernel (private grids per species)
+  int deltaf, matrix_path, zero_partials;
+  double lx, rnx;
+  double Z[4], n[4];
+  double *partial;        // [nspecies][ngrids][nx]
+  double *red;            // [nred][nx], nred = matrix_path ? nspecies : 1
+  double *rho, *E, *mode_re, *mode_im;
+  const double *F_re, *F_im, *ginv;  // [nx*nmode] row-major, [nmode]
+  double a_im, a_re;      // -1.0/nx, 1.0/nx  (src/pic1dp_field.F90:234, :239)
+  double nx_over_lx;      // input_nx / input_lx (src/pic1dp_interaction.F90:77)
+  double *energy;
+};
+
+// one thread per cell; CTA partials summed in ascending CTA order (deterministic)
+__global__ void __launch_bounds__(128) k_reduce_charge(const GridArgs g) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.nx) return;
+  double c2 = 0.0;
+  for (int s = 0; s < g.nspecies; s++) {
+    double *ps = g.partial + (size_t)s * g.ngrids * g.nx + j;
+    double c1 = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < g.ngrids; k++) {
+      const double t = ps[(size_t)k * g.nx];
+      c1 = (k == 0) ? t : dadd(c1, t);
+    }
+    if (g.zero_partials)
+      for (int k = 0; k < g.ngrids; k++) ps[(size_t)k * g.nx] = 0.0;
+    if (g.matrix_path)
+      g.red[(size_t)s * g.nx + j] = c1;  // field_tmp = S^T w per species (:52-59)
+    else
+      c2 = dadd(c2, dmul(c1, g.Z[s]));   // charge2 += charge1 * Z (:126-127)
+  }
+  if (!g.matrix_path) g.red[j] = c2;
+}
+
+__global__ void __launch_bounds__(128) k_finalize_rho(const GridArgs g) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.nx) return;
+  double rho;
+  if (!g.matrix_path) {
+    rho = ddiv(dmul(g.red[j], g.rnx), g.lx);  // charge1 * nx / lx (:140-141)
+    if (!g.deltaf)
+      for (int s = 0; s < g.nspecies; s++) rho = dsub(rho, dmul(g.Z[s], g.n[s]));  // :142-148
+  } else {
+    rho = 0.0;  // :47
+    for (int s = 0; s < g.nspecies; s++) {
+      double t = g.red[(size_t)s * g.nx + j];
+      if (!g.deltaf) t = dsub(t, ddiv(dmul(g.n[s], g.lx), g.rnx));  // :67
+      rho = dadd(rho, dmul(g.Z[s], t));                              // VecAXPY :71
+    }
+    rho = dmul(rho, g.nx_over_lx);  // VecScale :77
+  }
+  g.rho[j] = rho;
+}
+
+// Single CTA, 1024 threads.  smem: rho[nx] + 2*nmode mode values.
+// SEQ=true : thread m walks j = 0..nx-1 in order (bit-identical to sequential-AIJ MatMultTranspose).
+// SEQ=false: warp per mode, lanes stride j, fixed shuffle tree (deterministic).
+template <bool SEQ>
+__global__ void __launch_bounds__(1024) k_field_solve(const GridArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  double *s_rho = smem;
+  double *s_re = smem + g.nx;
+  double *s_im = s_re + g.nmode;
+  const int M = g.nmode, nx = g.nx;
+  for (int j = threadIdx.x; j < nx; j += blockDim.x) s_rho[j] = g.rho[j];
+  __syncthreads();
+  if (SEQ) {
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+      double sim = 0.0, sre = 0.0;
+      for (int j = 0; j < nx; j++) {
+        sim = dadd(sim, dmul(g.F_re[(size_t)j * M + m], s_rho[j]));  // MatMultTranspose(F_re, rho) :231
+        sre = dadd(sre, dmul(g.F_im[(size_t)j * M + m], s_rho[j]));  // MatMultTranspose(F_im, rho) :236
+      }
+      s_im[m] = dmul(dmul(sim, g.a_im), g.ginv[m]);  // :234, :246
+      s_re[m] = dmul(dmul(sre, g.a_re), g.ginv[m]);  // :239, :243
+    }
+  } else {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int m = wid; m < M; m += nw) {
+      double sim = 0.0, sre = 0.0;
+      for (int j = lane; j < nx; j += 32) {
+        sim = dadd(sim, dmul(g.F_re[(size_t)j * M + m], s_rho[j]));
+        sre = dadd(sre, dmul(g.F_im[(size_t)j * M + m], s_rho[j]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sim = dadd(sim, __shfl_xor_sync(0xffffffffu, sim, o));
+        sre = dadd(sre, __shfl_xor_sync(0xffffffffu, sre, o));
+      }
+      if (lane == 0) {
+        s_im[m] = dmul(dmul(sim, g.a_im), g.ginv[m]);
+        s_re[m] = dmul(dmul(sre, g.a_re), g.ginv[m]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    g.mode_re[m] = s_re[m];
+    g.mode_im[m] = s_im[m];
+  }
+  // E = 2 * (F_re . mode_re + F_im . mode_im): MatMult then MatMultAdd, row sums left to right (:251-256)
+  for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+    double sum = 0.0;
+    for (int m = 0; m < M; m++) sum = dadd(sum, dmul(g.F_re[(size_t)j * M + m], s_re[m]));
+    for (int m = 0; m < M; m++) sum = dadd(sum, dmul(g.F_im[(size_t)j * M + m], s_im[m]));
+    g.E[j] = dmul(sum, 2.0);
+  }
+}
+
+// single CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_field_energy(const GridArgs g) {
+  __shared__ double s_part[32];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < g.nx; j += blockDim.x) s = dadd(s, dmul(g.E[j], g.E[j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s = dadd(s, __shfl_xor_sync(0xffffffffu, s, o));
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? s_part[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = dadd(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (threadIdx.x == 0) {
+      const double nrm = sqrt(s);  // VecNorm(NORM_2)
+      *g.energy = ddiv(dmul(dmul(nrm, nrm), g.lx), g.rnx);
+    }
+  }
+}
+
+}  // namespace pic1dp

@@ -1,0 +1,402 @@
+// particle_kernels.cuh -- marker-side kernels of the PIC1D hot path for sm_100a.
+//
+// One fused kernel per RK substep does, per marker: weights (index + linear weights, never stored), field
+// gather S.E from a shared-memory copy of E, RK2 push of x, w, v, periodic wrap, and charge deposition S^T w
+// into an on-chip grid.  Replaces interaction_push_particle (/root/reference/src/pic1dp_interaction.F90:161-370)
+// followed by the marker loop of interaction_collect_charge (:96-114).  Unfused variants (push only, deposit
+// only) keep the reference's call-by-call side effects.
+//
+// Arithmetic is "strict": every fp64 operation is an explicit round-to-nearest intrinsic in the reference's
+// left-to-right order, so nvcc cannot contract to FMA.  Given identical inputs the cell index, weights, x and v
+// are bit-identical to the x86-64 reference build; w differs only through exp() (<= 1 ulp vs glibc).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pic1dp {
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// Per-species constants, all evaluated on the host in IEEE double exactly as the Fortran compiler folds them.
+struct SpeciesConst {
+  double Z, m, T;           // charge, mass, temperature
+  double n, omn, v0;        // density, 1-density, v0
+  double Tm, T2m;           // T/m, T2/m
+  double twoTm, twoT2m;     // 2*T/m, 2*T2/m
+  double sqTm, sqT2m;       // sqrt(T/m), sqrt(T2/m)
+  // exact reciprocals, used only when every divisor above is a power of two (x/c == x*(1/c) bit for bit)
+  double i_m, i_T, i_Tm, i_T2m, i_twoTm, i_twoT2m, i_sqTm, i_sqT2m;
+  int pow2;
+};
+
+struct ParticleArgs {
+  // current state (midpoint state at irk == 2)
+  const double *x_cur, *v_cur, *w_cur, *p;
+  // start-of-step state (x_bak ...; equal to *_cur at irk == 1 and then not read)
+  const double *x_bak, *v_bak, *w_bak;
+  // outputs (at irk == 2 these alias *_bak: each thread reads its own element before writing it)
+  double *x_out, *v_out, *w_out;
+  const double *dep_src;   // deposit-only kernel: w (delta-f) or p (full-f)
+  const double *E;         // field_electric, nx
+  double *partial;         // per-CTA private grids of this species, [gridDim.x][nx]
+  unsigned long long *noob;
+  int64_t np;
+  int nx;
+  double lx, rnx, dt;      // dt is already halved at irk == 1 (src/pic1dp_interaction.F90:179)
+  SpeciesConst c;
+  int deltaf, linear, right_frac;
+};
+
+// ---- periodic wrap: px = mod(px, lx); if (px < 0) px = px + lx  (src/pic1dp_interaction.F90:102-104) ----
+// fmod is exact; for lx <= x < 2 lx it equals x - lx (exact by Sterbenz), for -lx < x < 0 it returns x.
+__device__ __forceinline__ double wrap_x(double x, double lx) {
+  if (x >= 0.0 && x < lx) return x;
+  if (x >= lx && x < dadd(lx, lx)) return dsub(x, lx);
+  if (x < 0.0 && x > -lx) return dadd(x, lx);
+  double r = fmod(x, lx);
+  if (r < 0.0) r = dadd(r, lx);
+  return r;
+}
+
+struct Shape {
+  int ix, ixr;
+  double sl, sr;
+};
+
+// ---- weights: sx = x/lx*nx; ix = floor(sx); s = 1-(sx-ix)  (src/pic1dp_interaction.F90:106-108, :250-252;
+// matrix modes src/pic1dp_particle.F90:312-323 use `frac` as the right weight) ----
+__device__ __forceinline__ Shape shape_of(double x, double lx, double rnx, int nx, int right_frac, bool &oob) {
+  Shape s;
+  const double sx = dmul(ddiv(x, lx), rnx);
+  int ix = __double2int_rd(sx);
+  double frac = dsub(sx, (double)ix);
+  double sl = dsub(1.0, frac);
+  if ((unsigned)ix >= (unsigned)nx) {  // x wrapped to exactly lx (reference writes out of bounds here)
+    oob = true;
+    ix = 0;
+    sl = 1.0;
+    frac = 0.0;
+  }
+  s.ix = ix;
+  s.sl = sl;
+  s.sr = right_frac ? frac : dsub(1.0, sl);
+  int ixr = ix + 1;
+  if (ixr > nx - 1) ixr = 0;
+  s.ixr = ixr;
+  return s;
+}
+
+// ---- -d f0/dv / f0  (src/pic1dp_interaction.F90:275-326) ----
+template <int DIST, bool POW2>
+__device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
+#define DIVC(x, name) (POW2 ? dmul((x), c.i_##name) : ddiv((x), c.name))
+  if (DIST == 1) {  // two-stream1 :276
+    return dsub(v, ddiv(2.0, v));
+  } else if (DIST == 2) {  // two-stream2 :278-292
+    const double vp = dadd(v, c.v0), vm = dsub(v, c.v0);
+    const double ep = exp(-DIVC(dmul(vp, vp), twoTm));
+    const double em = exp(-DIVC(dmul(vm, vm), twoTm));
+    const double num = dadd(dmul(vp, ep), dmul(vm, em));
+    const double den = dadd(ep, em);
+    double r = ddiv(num, den);
+    r = dmul(r, c.m);
+    return DIVC(r, T);
+  } else if (DIST == 3) {  // bump-on-tail :294-321
+    const double vm = dsub(v, c.v0);
+    const double e1 = exp(-DIVC(dmul(v, v), twoTm));
+    const double e2 = exp(-DIVC(dmul(vm, vm), twoT2m));
+    const double a = DIVC(dmul(DIVC(dmul(c.n, v), Tm), e1), sqTm);
+    const double b = DIVC(dmul(DIVC(dmul(c.omn, vm), T2m), e2), sqT2m);
+    const double num = dadd(a, b);
+    const double den = dadd(DIVC(dmul(c.n, e1), sqTm), DIVC(dmul(c.omn, e2), sqT2m));
+    return ddiv(num, den);
+  } else {  // (shifted) Maxwellian :323-325
+    return DIVC(dsub(v, c.v0), Tm);
+  }
+#undef DIVC
+}
+
+template <int DIST>
+__device__ __forceinline__ double dlnf0(const SpeciesConst &c, double v) {
+  return c.pow2 ? dlnf0_impl<DIST, true>(c, v) : dlnf0_impl<DIST, false>(c, v);
+}
+
+// ---- gather + push of one marker (src/pic1dp_interaction.F90:250-338) ----
+template <int DIST>
+__device__ __forceinline__ void push_one(const ParticleArgs &a, const double *sE, double x, double v, double w,
+                                         double p, double xb, double vb, double wb, double &xo, double &vo,
+                                         double &wo) {
+  bool oob = false;  // x == lx exactly was already counted by the deposit that produced this x
+  const Shape s = shape_of(x, a.lx, a.rnx, a.nx, a.right_frac, oob);
+  const double electric = dadd(dmul(sE[s.ix], s.sl), dmul(sE[s.ixr], s.sr));  // :254-257
+  xo = dadd(xb, dmul(a.dt, v));                                              // :261
+  wo = w;
+  if (a.deltaf) {
+    const double tmp1 = a.linear ? dmul(p, electric) : dmul(dsub(p, w), electric);  // :268-272
+    const double tmp2 = dlnf0<DIST>(a.c, v);
+    double t = dmul(dmul(dmul(a.dt, tmp1), tmp2), a.c.Z);  // :329
+    t = a.c.pow2 ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);       // :330
+    wo = dadd(wb, t);
+  }
+  vo = v;
+  if (!a.linear) {
+    double t = dmul(dmul(a.dt, electric), a.c.Z);  // :336
+    t = a.c.pow2 ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);
+    vo = dadd(vb, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Deposit strategies.  Each adds (sl*w) to cell ix and (sr*w) to cell ixr of an on-chip grid.
+// ------------------------------------------------------------------------------------------------------------
+enum { DEP_SMEM_ATOMIC = 1, DEP_GLOBAL_RED = 2, DEP_WARP_PRIVATE = 3 };
+
+template <int DEP>
+struct Depositor;
+
+// per-CTA shared grid, fp64 atomicAdd (lowers to an ATOMS.CAS loop on sm_100a)
+template <>
+struct Depositor<DEP_SMEM_ATOMIC> {
+  double *g;
+  __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
+    if (valid) {
+      atomicAdd(&g[ix], a);
+      atomicAdd(&g[ixr], b);
+    }
+  }
+};
+
+// fire-and-forget RED.ADD.F64 into this CTA's private global (L2-resident) grid
+template <>
+struct Depositor<DEP_GLOBAL_RED> {
+  double *g;
+  __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
+    if (valid) {
+      atomicAdd(&g[ix], a);  // result unused -> REDG.E.ADD.F64
+      atomicAdd(&g[ixr], b);
+    }
+  }
+};
+
+// per-warp private shared grid, no atomics.  Lanes of one instruction that hit the same cell are merged with
+// MATCH.ANY: every lane sums its peers' contributions in ascending lane order, the lowest lane does the
+// read-modify-write.  Fixed marker->lane mapping + fixed order => bitwise run-to-run deterministic.
+// Must be called by all 32 lanes (invalid lanes pass valid=false).
+template <>
+struct Depositor<DEP_WARP_PRIVATE> {
+  double *g;  // this warp's grid
+  __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    if (!valid) {  // joins the ix == 0 group with zero contributions; ixr must agree with that group's (nx >= 2)
+      ix = 0;
+      ixr = 1;
+      a = 0.0;
+      b = 0.0;
+    }
+    const unsigned peers = __match_any_sync(full, ix);
+    const bool leader = (__ffs(peers) - 1) == lane;
+    double A = a, B = b;
+    if (__any_sync(full, peers != (1u << lane))) {
+      const int maxc = __reduce_max_sync(full, (unsigned)__popc(peers));
+      unsigned rem = peers;
+      A = 0.0;
+      B = 0.0;
+      for (int k = 0; k < maxc; k++) {
+        const int src = rem ? (__ffs(rem) - 1) : lane;
+        const double ta = __shfl_sync(full, a, src);
+        const double tb = __shfl_sync(full, b, src);
+        if (rem) {
+          A = (k == 0) ? ta : dadd(A, ta);
+          B = (k == 0) ? tb : dadd(B, tb);
+          rem &= rem - 1;
+        }
+      }
+    }
+    if (leader) g[ix] = dadd(g[ix], A);
+    __syncwarp();
+    if (leader) g[ixr] = dadd(g[ixr], B);
+    __syncwarp();
+  }
+};
+
+// streaming (evict-first) global accesses: marker arrays are touched once per substep
+__device__ __forceinline__ double2 ld2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ double ld1(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
+__device__ __forceinline__ void st1(double *p, double v) { __stcs(p, v); }
+
+// Shared-memory layout of the particle kernels: [E : nx] [deposit grid(s) : nx * ngrids]
+template <int DEP>
+__device__ __forceinline__ double *dep_setup(double *smem_after_E, int nx, double *my_partial) {
+  if (DEP == DEP_SMEM_ATOMIC) {
+    for (int j = threadIdx.x; j < nx; j += blockDim.x) smem_after_E[j] = 0.0;
+    return smem_after_E;
+  } else if (DEP == DEP_WARP_PRIVATE) {
+    const int nw = blockDim.x >> 5;
+    for (int j = threadIdx.x; j < nx * nw; j += blockDim.x) smem_after_E[j] = 0.0;
+    return smem_after_E + (size_t)(threadIdx.x >> 5) * nx;
+  } else {
+    return my_partial;  // zeroed by the reduce kernel of the previous substep
+  }
+}
+
+template <int DEP>
+__device__ __forceinline__ void dep_flush(double *smem_after_E, int nx, double *my_partial) {
+  if (DEP == DEP_SMEM_ATOMIC) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < nx; j += blockDim.x) my_partial[j] = smem_after_E[j];
+  } else if (DEP == DEP_WARP_PRIVATE) {
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+      double t = smem_after_E[j];
+      for (int wq = 1; wq < nw; wq++) t = dadd(t, smem_after_E[(size_t)wq * nx + j]);  // fixed warp order
+      my_partial[j] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused substep kernel: gather + push + wrap + deposit.  Persistent grid, 2 markers per thread per iteration
+// through 128-bit loads/stores.  IRK2 selects the second RK substep (reads midpoint + start-of-step state).
+// FUSED=false gives the reference's push-only side effects (x left unwrapped, no deposit).
+// ------------------------------------------------------------------------------------------------------------
+template <int DIST, bool IRK2, int DEP, bool FUSED>
+__global__ void __launch_bounds__(512) k_push(const ParticleArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double *sE = smem;
+  for (int j = threadIdx.x; j < a.nx; j += blockDim.x) sE[j] = a.E[j];
+  double *my_partial = FUSED ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
+  Depositor<DEP> dep;
+  dep.g = FUSED ? dep_setup<DEP>(smem + a.nx, a.nx, my_partial) : nullptr;
+  __syncthreads();
+
+  const int64_t tile = (int64_t)blockDim.x * 2;
+  const bool need_p = a.deltaf || FUSED;  // full-f deposits p (src/pic1dp_interaction.F90:88-90)
+  unsigned long long noob = 0;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
+    const int64_t i = base + (int64_t)threadIdx.x * 2;
+    const bool v0ok = i < a.np, v1ok = i + 1 < a.np;
+    double2 x = {0.0, 0.0}, v = {0.0, 0.0}, w = {0.0, 0.0}, p = {0.0, 0.0};
+    double2 xb = {0.0, 0.0}, vb = {0.0, 0.0}, wb = {0.0, 0.0};
+    if (v1ok) {
+      x = ld2(a.x_cur + i);
+      v = ld2(a.v_cur + i);
+      if (a.deltaf) w = ld2(a.w_cur + i);
+      if (need_p) p = ld2(a.p + i);
+      if (IRK2) {
+        xb = ld2(a.x_bak + i);
+        vb = ld2(a.v_bak + i);
+        if (a.deltaf) wb = ld2(a.w_bak + i);
+      }
+    } else if (v0ok) {
+      x.x = ld1(a.x_cur + i);
+      v.x = ld1(a.v_cur + i);
+      if (a.deltaf) w.x = ld1(a.w_cur + i);
+      if (need_p) p.x = ld1(a.p + i);
+      if (IRK2) {
+        xb.x = ld1(a.x_bak + i);
+        vb.x = ld1(a.v_bak + i);
+        if (a.deltaf) wb.x = ld1(a.w_bak + i);
+      }
+    }
+    if (!IRK2) {
+      xb = x;
+      vb = v;
+      wb = w;
+    } else if (!a.deltaf) {
+      wb = w;
+    }
+    double2 xo = {0.0, 0.0}, vo = {0.0, 0.0}, wo = {0.0, 0.0};
+    if (v0ok) push_one<DIST>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
+    if (v1ok) push_one<DIST>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
+    if (FUSED) {
+      if (v0ok) xo.x = wrap_x(xo.x, a.lx);
+      if (v1ok) xo.y = wrap_x(xo.y, a.lx);
+    }
+    if (v1ok) {
+      st2(a.x_out + i, xo);
+      if (!a.linear) st2(a.v_out + i, vo);
+      if (a.deltaf) st2(a.w_out + i, wo);
+    } else if (v0ok) {
+      st1(a.x_out + i, xo.x);
+      if (!a.linear) st1(a.v_out + i, vo.x);
+      if (a.deltaf) st1(a.w_out + i, wo.x);
+    }
+    if (FUSED) {
+      // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
+      const double q0 = a.deltaf ? wo.x : p.x, q1 = a.deltaf ? wo.y : p.y;
+      bool o0 = false, o1 = false;
+      const Shape s0 = shape_of(xo.x, a.lx, a.rnx, a.nx, a.right_frac, o0);
+      dep.add(s0.ix, s0.ixr, dmul(s0.sl, q0), dmul(s0.sr, q0), v0ok);  // :110, :113
+      const Shape s1 = shape_of(xo.y, a.lx, a.rnx, a.nx, a.right_frac, o1);
+      dep.add(s1.ix, s1.ixr, dmul(s1.sl, q1), dmul(s1.sr, q1), v1ok);
+      noob += (v0ok && o0) + (v1ok && o1);
+    }
+  }
+  if (FUSED) dep_flush<DEP>(smem + a.nx, a.nx, my_partial);
+  if (FUSED && noob) atomicAdd(a.noob, noob);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Deposit-only kernel: the marker loop of interaction_collect_charge (src/pic1dp_interaction.F90:96-114) /
+// particle_compute_shape_x (src/pic1dp_particle.F90:306-334): wrap x in place, deposit dep_src.
+// DEPOSIT=false: wrap only (compute_shape_x for iptclshape 1-3).
+// ------------------------------------------------------------------------------------------------------------
+template <int DEP, bool DEPOSIT>
+__global__ void __launch_bounds__(512) k_deposit(const ParticleArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  double *my_partial = DEPOSIT ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
+  Depositor<DEP> dep;
+  dep.g = DEPOSIT ? dep_setup<DEP>(smem, a.nx, my_partial) : nullptr;
+  __syncthreads();
+  const int64_t tile = (int64_t)blockDim.x * 2;
+  unsigned long long noob = 0;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
+    const int64_t i = base + (int64_t)threadIdx.x * 2;
+    const bool v0ok = i < a.np, v1ok = i + 1 < a.np;
+    double2 x = {0.0, 0.0}, q = {0.0, 0.0};
+    if (v1ok) {
+      x = ld2(a.x_cur + i);
+      if (DEPOSIT) q = ld2(a.dep_src + i);
+    } else if (v0ok) {
+      x.x = ld1(a.x_cur + i);
+      if (DEPOSIT) q.x = ld1(a.dep_src + i);
+    }
+    const double2 xw = {wrap_x(x.x, a.lx), wrap_x(x.y, a.lx)};
+    // the reference always stores the wrapped value (:102); skip the store when it is bit-identical
+    if (v1ok) {
+      if (xw.x != x.x || xw.y != x.y) st2(a.x_out + i, xw);
+    } else if (v0ok) {
+      if (xw.x != x.x) st1(a.x_out + i, xw.x);
+    }
+    if (DEPOSIT) {
+      bool o0 = false, o1 = false;
+      const Shape s0 = shape_of(xw.x, a.lx, a.rnx, a.nx, a.right_frac, o0);
+      dep.add(s0.ix, s0.ixr, dmul(s0.sl, q.x), dmul(s0.sr, q.x), v0ok);
+      const Shape s1 = shape_of(xw.y, a.lx, a.rnx, a.nx, a.right_frac, o1);
+      dep.add(s1.ix, s1.ixr, dmul(s1.sl, q.y), dmul(s1.sr, q.y), v1ok);
+      noob += (v0ok && o0) + (v1ok && o1);
+    }
+  }
+  if (DEPOSIT) dep_flush<DEP>(smem, a.nx, my_partial);
+  if (DEPOSIT && noob) atomicAdd(a.noob, noob);
+}
+
+// weights of the current x, exported for parity checks (particle_shape_x_indexes / _values of iptclshape 3,
+// src/pic1dp_particle.F90:331-332)
+__global__ void __launch_bounds__(256) k_shape_x(const ParticleArgs a, int *ix, double *sl, double *sr) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.np; i += (int64_t)gridDim.x * blockDim.x) {
+    bool oob = false;
+    const Shape s = shape_of(a.x_cur[i], a.lx, a.rnx, a.nx, a.right_frac, oob);
+    ix[i] = s.ix;
+    sl[i] = s.sl;
+    sr[i] = s.sr;
+  }
+}
+
+}  // namespace pic1dp

@@ -1,0 +1,829 @@
+// pic1dp_gpu.cu -- C ABI (include/pic1dp_gpu.h) and device-resident state of the B200-native PIC1D hot path.
+//
+// The handle plays the role of the module-global PETSc state of pic1dp_particle / pic1dp_field
+// (/root/reference/src/pic1dp_particle.F90:26-58, /root/reference/src/pic1dp_field.F90:27-48):
+//   markers : SoA fp64 x, v, w in two buffer sets (A/B) + p.  The RK2 "backup" (VecCopy x3,
+//             src/pic1dp_interaction.F90:181-187) is a buffer rotation: substep 1 reads A and writes B,
+//             substep 2 reads A (start-of-step) and B (midpoint) and overwrites A.
+//   grid    : E, rho, mode_re, mode_im, cos / -sin partial-DFT tables, 1/k -- replicated on every GPU.
+//   deposit : per-CTA private grids, reduced in fixed order; one ncclAllReduce(nx doubles) per substep.
+// No matrix is ever materialised; no CPU fallback exists.
+#include "../../include/pic1dp_gpu.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "field_kernels.cuh"
+#include "particle_kernels.cuh"
+
+using namespace pic1dp;
+
+// ------------------------------------------------------------------------------------------------------------
+// NCCL is bound at run time (dlopen) and only when nranks > 1, so a single-GPU process never needs it and a
+// process that already loaded torch's bundled libnccl.so.2 reuses that copy.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  void *so = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) =
+      nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+  bool load() {
+    if (so) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      so = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (so) break;
+    }
+    if (!so) {
+      err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+      return false;
+    }
+#define BIND(field, sym)                                           \
+  *(void **)(&field) = dlsym(so, sym);                             \
+  if (!field) {                                                    \
+    err = std::string("dlsym failed: ") + sym;                     \
+    return false;                                                  \
+  }
+    BIND(GetUniqueId, "ncclGetUniqueId");
+    BIND(CommInitRank, "ncclCommInitRank");
+    BIND(AllReduce, "ncclAllReduce");
+    BIND(CommDestroy, "ncclCommDestroy");
+    BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+    return true;
+  }
+};
+NcclApi g_nccl;
+std::string g_create_err;
+}  // namespace
+
+struct Species {
+  double *x[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr}, *w[2] = {nullptr, nullptr};
+  double *p = nullptr;
+  int cur = 0;       // buffer set holding the current state
+  int bak = 0;       // buffer set holding the start-of-step state (valid between irk=1 and irk=2)
+  int64_t np = 0;
+  bool loaded = false;
+  SpeciesConst c;
+};
+
+struct pic1dp_gpu {
+  pic1dp_params p;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t pev[7] = {};
+  Species sp[PIC1DP_MAX_SPECIES];
+  double *d_E = nullptr, *d_rho = nullptr, *d_mre = nullptr, *d_mim = nullptr;
+  double *d_Fre = nullptr, *d_Fim = nullptr, *d_ginv = nullptr;
+  double *d_partial = nullptr, *d_red = nullptr, *d_energy = nullptr;
+  unsigned long long *d_noob = nullptr;
+  std::vector<double> h_Fre, h_Fim, h_ginv;
+  int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0;
+  bool partial_valid = false;  // a fused push has already deposited into d_partial
+  int nred = 1;
+  ncclComm_t comm = nullptr;
+  int64_t launches = 0, nccl_calls = 0, h2d = 0, d2h = 0;
+  std::string err;
+};
+
+static const char *kErrText[] = {"ok",
+                                 "invalid argument or parameter combination",
+                                 "CUDA runtime error",
+                                 "NCCL error",
+                                 "out of memory",
+                                 "invalid call sequence",
+                                 "marker count exceeds capacity",
+                                 "no CUDA device (this library has no CPU fallback)",
+                                 "mode not supported for these parameters"};
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                     \
+      return (e_ == cudaErrorMemoryAllocation) ? PIC1DP_ENOMEM : PIC1DP_ECUDA;                         \
+    }                                                                                                  \
+  } while (0)
+
+#define CKL(h)                                                                                         \
+  do {                                                                                                 \
+    cudaError_t e_ = cudaGetLastError();                                                               \
+    if (e_ != cudaSuccess) {                                                                           \
+      (h)->err = std::string("kernel launch: ") + cudaGetErrorString(e_);                              \
+      return PIC1DP_ECUDA;                                                                             \
+    }                                                                                                  \
+    (h)->launches++;                                                                                   \
+  } while (0)
+
+static bool is_pow2(double c) {
+  if (!(c > 0.0) || !isfinite(c)) return false;
+  int e;
+  return frexp(c, &e) == 0.5;
+}
+
+static void species_const(const pic1dp_params &p, int s, SpeciesConst &c) {
+  const double T = p.temperature[s], T2 = p.temperature2[s], m = p.mass[s];
+  c.Z = p.charge[s];
+  c.m = m;
+  c.T = T;
+  c.n = p.density[s];
+  c.omn = 1.0 - p.density[s];
+  c.v0 = p.v0[s];
+  c.Tm = T / m;
+  c.T2m = T2 / m;
+  c.twoTm = 2.0 * T / m;
+  c.twoT2m = 2.0 * T2 / m;
+  c.sqTm = sqrt(T / m);
+  c.sqT2m = sqrt(T2 / m);
+  const double divs[8] = {c.m, c.T, c.Tm, c.T2m, c.twoTm, c.twoT2m, c.sqTm, c.sqT2m};
+  bool all = true;
+  for (double d : divs) all = all && is_pow2(d);
+  c.pow2 = all ? 1 : 0;
+  c.i_m = 1.0 / c.m;
+  c.i_T = 1.0 / c.T;
+  c.i_Tm = 1.0 / c.Tm;
+  c.i_T2m = 1.0 / c.T2m;
+  c.i_twoTm = 1.0 / c.twoTm;
+  c.i_twoT2m = 1.0 / c.twoT2m;
+  c.i_sqTm = 1.0 / c.sqTm;
+  c.i_sqT2m = 1.0 / c.sqT2m;
+}
+
+// ---- kernel dispatch tables -----------------------------------------------------------------------------
+typedef void (*PushKernel)(const ParticleArgs);
+
+template <int DIST, bool IRK2, bool FUSED>
+static PushKernel pick_dep(int dep) {
+  switch (dep) {
+    case DEP_SMEM_ATOMIC: return k_push<DIST, IRK2, DEP_SMEM_ATOMIC, FUSED>;
+    case DEP_GLOBAL_RED: return k_push<DIST, IRK2, DEP_GLOBAL_RED, FUSED>;
+    default: return k_push<DIST, IRK2, DEP_WARP_PRIVATE, FUSED>;
+  }
+}
+template <int DIST>
+static PushKernel pick_irk(int dep, bool irk2, bool fused) {
+  if (!fused) return irk2 ? k_push<DIST, true, DEP_SMEM_ATOMIC, false> : k_push<DIST, false, DEP_SMEM_ATOMIC, false>;
+  return irk2 ? pick_dep<DIST, true, true>(dep) : pick_dep<DIST, false, true>(dep);
+}
+static PushKernel pick_push(int dist, int dep, bool irk2, bool fused) {
+  switch (dist) {
+    case 1: return pick_irk<1>(dep, irk2, fused);
+    case 2: return pick_irk<2>(dep, irk2, fused);
+    case 3: return pick_irk<3>(dep, irk2, fused);
+    default: return pick_irk<0>(dep, irk2, fused);
+  }
+}
+static PushKernel pick_deposit(int dep, bool deposit) {
+  if (!deposit) return k_deposit<DEP_SMEM_ATOMIC, false>;
+  switch (dep) {
+    case DEP_SMEM_ATOMIC: return k_deposit<DEP_SMEM_ATOMIC, true>;
+    case DEP_GLOBAL_RED: return k_deposit<DEP_GLOBAL_RED, true>;
+    default: return k_deposit<DEP_WARP_PRIVATE, true>;
+  }
+}
+
+static int dep_grids(int dep, int threads) { return dep == DEP_WARP_PRIVATE ? threads / 32 : (dep == DEP_SMEM_ATOMIC ? 1 : 0); }
+
+// ---- public API -----------------------------------------------------------------------------------------
+extern "C" {
+
+int pic1dp_gpu_abi_version(void) { return PIC1DP_ABI_VERSION; }
+
+const char *pic1dp_gpu_strerror(int code) {
+  if (code < 0 || code > PIC1DP_EUNSUPPORTED) return "unknown error";
+  return kErrText[code];
+}
+
+const char *pic1dp_gpu_last_error(const pic1dp_gpu_t *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+void pic1dp_gpu_params_default(pic1dp_params *p) {
+  memset(p, 0, sizeof(*p));
+  p->abi_version = PIC1DP_ABI_VERSION;
+  p->struct_bytes = (int32_t)sizeof(pic1dp_params);
+  p->nx = 192;
+  p->nmode = 1;
+  p->modes[0] = 1;
+  p->lx = 2.0 * 3.1415926535897932384626 / 0.36;
+  p->dt = 0.05;
+  p->nspecies = 1;
+  p->charge[0] = -1.0;
+  p->mass[0] = 1.0;
+  p->temperature[0] = 1.0;
+  p->temperature2[0] = 1.0;
+  p->density[0] = 0.9;
+  p->v0[0] = 5.0;
+  p->iptcldist = 3;
+  p->deltaf = 1;
+  p->linear = 0;
+  p->iptclshape = 4;
+  p->capacity = 6400000;
+  p->device = 0;
+  p->rank = 0;
+  p->nranks = 1;
+  p->deposit_mode = PIC1DP_DEPOSIT_AUTO;
+  p->field_mode = PIC1DP_FIELD_TREE;
+  p->fuse = 1;
+}
+
+static int validate(const pic1dp_params *p, std::string &err) {
+  if (!p) { err = "params is NULL"; return PIC1DP_EINVAL; }
+  if (p->abi_version != PIC1DP_ABI_VERSION || p->struct_bytes != (int32_t)sizeof(pic1dp_params)) {
+    err = "ABI mismatch: fill params with pic1dp_gpu_params_default() of this library";
+    return PIC1DP_EINVAL;
+  }
+  if (p->nx < 2 || p->nx > (1 << 20)) { err = "nx out of range"; return PIC1DP_EINVAL; }
+  if (p->nmode < 1 || p->nmode > PIC1DP_MAX_MODES) { err = "nmode out of range"; return PIC1DP_EINVAL; }
+  for (int m = 0; m < p->nmode; m++)
+    if (p->modes[m] == 0) { err = "mode number 0 has no 1/k"; return PIC1DP_EINVAL; }
+  if (p->nspecies < 1 || p->nspecies > PIC1DP_MAX_SPECIES) { err = "nspecies out of range"; return PIC1DP_EINVAL; }
+  if (!(p->lx > 0.0) || !(p->dt > 0.0)) { err = "lx and dt must be positive"; return PIC1DP_EINVAL; }
+  if (p->iptcldist < 0 || p->iptcldist > 3) { err = "iptcldist must be 0..3"; return PIC1DP_EINVAL; }
+  if (p->iptclshape < 1 || p->iptclshape > 4) { err = "iptclshape must be 1..4"; return PIC1DP_EINVAL; }
+  if ((p->deltaf != 0 && p->deltaf != 1) || (p->linear != 0 && p->linear != 1)) {
+    err = "deltaf and linear must be 0 or 1";
+    return PIC1DP_EINVAL;
+  }
+  // src/pic1dp_input.F90:301-307
+  if (p->linear == 1 && p->deltaf == 0) { err = "case of input_linear = 1 and input_deltaf = 0 not implemented"; return PIC1DP_EINVAL; }
+  if (p->capacity < 1) { err = "capacity must be >= 1"; return PIC1DP_EINVAL; }
+  if (p->nranks < 1 || p->rank < 0 || p->rank >= p->nranks) { err = "bad rank/nranks"; return PIC1DP_EINVAL; }
+  for (int s = 0; s < p->nspecies; s++)
+    if (!(p->mass[s] > 0.0) || !(p->temperature[s] > 0.0) || !(p->temperature2[s] > 0.0)) {
+      err = "mass and temperatures must be positive";
+      return PIC1DP_EINVAL;
+    }
+  if (p->deposit_mode < 0 || p->deposit_mode > 3 || p->field_mode < 0 || p->field_mode > 1) {
+    err = "bad deposit_mode / field_mode";
+    return PIC1DP_EINVAL;
+  }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
+  if (!h) return PIC1DP_OK;
+  cudaSetDevice(h->p.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (int s = 0; s < PIC1DP_MAX_SPECIES; s++) {
+    Species &S = h->sp[s];
+    for (int b = 0; b < 2; b++) {
+      if (S.x[b]) cudaFree(S.x[b]);
+      if (S.v[b] && (b == 0 || S.v[1] != S.v[0])) cudaFree(S.v[b]);
+      if (S.w[b] && (b == 0 || S.w[1] != S.w[0])) cudaFree(S.w[b]);
+    }
+    if (S.p) cudaFree(S.p);
+  }
+  double *bufs[] = {h->d_E, h->d_rho, h->d_mre, h->d_mim, h->d_Fre, h->d_Fim, h->d_ginv, h->d_partial, h->d_red, h->d_energy};
+  for (double *b : bufs)
+    if (b) cudaFree(b);
+  if (h->d_noob) cudaFree(h->d_noob);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (cudaEvent_t e : h->pev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return PIC1DP_OK;
+}
+
+static int create_impl(pic1dp_gpu_t *h) {
+  const pic1dp_params &p = h->p;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    h->err = "no CUDA device visible";
+    return PIC1DP_ENODEVICE;
+  }
+  if (p.device < 0 || p.device >= ndev) {
+    h->err = "device ordinal out of range";
+    return PIC1DP_EINVAL;
+  }
+  CK(cudaSetDevice(p.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, p.device));
+  h->nsm = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  for (int i = 0; i < 7; i++) CK(cudaEventCreate(&h->pev[i]));
+
+  const int nx = p.nx, M = p.nmode;
+  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  // ---- deposit strategy and launch geometry ----
+  h->threads = 512;
+  int dep = p.deposit_mode;
+  auto smem_need = [&](int d, int thr) { return (size_t)nx * 8 * (1 + dep_grids(d, thr)); };
+  if (dep == PIC1DP_DEPOSIT_AUTO) {
+    if (smem_need(DEP_WARP_PRIVATE, 512) <= max_smem)
+      dep = DEP_WARP_PRIVATE;
+    else if (smem_need(DEP_SMEM_ATOMIC, 512) <= max_smem)
+      dep = DEP_SMEM_ATOMIC;
+    else
+      dep = DEP_GLOBAL_RED;
+  }
+  if (dep == DEP_WARP_PRIVATE && smem_need(dep, h->threads) > max_smem) {
+    // fewer warps per CTA so that one private grid per warp still fits
+    while (h->threads > 64 && smem_need(dep, h->threads) > max_smem) h->threads /= 2;
+  }
+  if (smem_need(dep, h->threads) > max_smem) {
+    h->err = "shared-memory grid does not fit for this nx with the requested deposit_mode";
+    return PIC1DP_EUNSUPPORTED;
+  }
+  h->dep = dep;
+  h->smem_push = (int)smem_need(dep, h->threads);
+  h->smem_dep = (int)((size_t)nx * 8 * dep_grids(dep, h->threads));
+  {
+    // occupancy: as many CTAs per SM as registers / smem allow, persistent grid = SMs x that
+    PushKernel kmax = pick_push(p.iptcldist, dep, true, true);
+    CK(cudaFuncSetAttribute(kmax, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_push));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmax, h->threads, h->smem_push));
+    if (per_sm < 1) per_sm = 1;
+    h->grid = h->nsm * per_sm;
+  }
+  for (int dist_irk = 0; dist_irk < 2; dist_irk++)
+    for (int fused = 0; fused < 2; fused++) {
+      PushKernel k = pick_push(p.iptcldist, dep, dist_irk == 1, fused == 1);
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_push));
+    }
+  CK(cudaFuncSetAttribute(pick_deposit(dep, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          h->smem_dep > 0 ? h->smem_dep : 8));
+  CK(cudaFuncSetAttribute(k_field_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
+  CK(cudaFuncSetAttribute(k_field_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
+
+  // ---- markers ----
+  const size_t cap = ((size_t)p.capacity + 1) & ~(size_t)1;  // even, for 128-bit accesses
+  for (int s = 0; s < p.nspecies; s++) {
+    Species &S = h->sp[s];
+    species_const(p, s, S.c);
+    CK(cudaMalloc(&S.x[0], cap * 8));
+    CK(cudaMalloc(&S.x[1], cap * 8));
+    CK(cudaMalloc(&S.v[0], cap * 8));
+    if (p.linear) S.v[1] = S.v[0]; else CK(cudaMalloc(&S.v[1], cap * 8));  // linear: v is never written (:335)
+    CK(cudaMalloc(&S.w[0], cap * 8));
+    if (!p.deltaf) S.w[1] = S.w[0]; else CK(cudaMalloc(&S.w[1], cap * 8));  // full-f: w is never written (:266)
+    CK(cudaMalloc(&S.p, cap * 8));
+  }
+  // ---- grid ----
+  h->nred = (p.iptclshape <= 2) ? p.nspecies : 1;
+  CK(cudaMalloc(&h->d_E, (size_t)nx * 8));
+  CK(cudaMalloc(&h->d_rho, (size_t)nx * 8));
+  CK(cudaMalloc(&h->d_mre, (size_t)M * 8));
+  CK(cudaMalloc(&h->d_mim, (size_t)M * 8));
+  CK(cudaMalloc(&h->d_Fre, (size_t)nx * M * 8));
+  CK(cudaMalloc(&h->d_Fim, (size_t)nx * M * 8));
+  CK(cudaMalloc(&h->d_ginv, (size_t)M * 8));
+  CK(cudaMalloc(&h->d_partial, (size_t)p.nspecies * h->grid * nx * 8));
+  CK(cudaMalloc(&h->d_red, (size_t)h->nred * nx * 8));
+  CK(cudaMalloc(&h->d_energy, 8));
+  CK(cudaMalloc(&h->d_noob, 8));
+  CK(cudaMemsetAsync(h->d_E, 0, (size_t)nx * 8, h->stream));
+  CK(cudaMemsetAsync(h->d_rho, 0, (size_t)nx * 8, h->stream));
+  CK(cudaMemsetAsync(h->d_mre, 0, (size_t)M * 8, h->stream));
+  CK(cudaMemsetAsync(h->d_mim, 0, (size_t)M * 8, h->stream));
+  CK(cudaMemsetAsync(h->d_partial, 0, (size_t)p.nspecies * h->grid * nx * 8, h->stream));
+  CK(cudaMemsetAsync(h->d_red, 0, (size_t)h->nred * nx * 8, h->stream));
+  CK(cudaMemsetAsync(h->d_noob, 0, 8, h->stream));
+
+  // ---- field operators (src/pic1dp_field.F90:158-210), evaluated on the host with libm exactly as written ----
+  const double PETSC_PI = 3.14159265358979323846264338327950288419716939937510582;
+  h->h_Fre.resize((size_t)nx * M);
+  h->h_Fim.resize((size_t)nx * M);
+  h->h_ginv.resize(M);
+  for (int m = 0; m < M; m++) h->h_ginv[m] = 1.0 / (2.0 * PETSC_PI / p.lx * (double)p.modes[m]);  // :166
+  for (int j = 0; j < nx; j++)
+    for (int m = 0; m < M; m++) {
+      const double arg = 2.0 * PETSC_PI / (double)nx * (double)p.modes[m] * (double)j;  // :188, :196
+      h->h_Fre[(size_t)j * M + m] = cos(arg);
+      h->h_Fim[(size_t)j * M + m] = -sin(arg);
+    }
+  CK(cudaMemcpyAsync(h->d_Fre, h->h_Fre.data(), (size_t)nx * M * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_Fim, h->h_Fim.data(), (size_t)nx * M * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_ginv, h->h_ginv.data(), (size_t)M * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_create(const pic1dp_params *p, pic1dp_gpu_t **out) {
+  if (!out) { g_create_err = "out is NULL"; return PIC1DP_EINVAL; }
+  *out = nullptr;
+  int rc = validate(p, g_create_err);
+  if (rc) return rc;
+  pic1dp_gpu_t *h = new pic1dp_gpu();
+  h->p = *p;
+  rc = create_impl(h);
+  if (rc) {
+    g_create_err = h->err;
+    pic1dp_gpu_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_comm_unique_id(uint8_t id[PIC1DP_UNIQUE_ID_BYTES]) {
+  if (!id) return PIC1DP_EINVAL;
+  if (!g_nccl.load()) { g_create_err = g_nccl.err; return PIC1DP_ENCCL; }
+  ncclUniqueId u;
+  static_assert(sizeof(ncclUniqueId) == PIC1DP_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclResult_t r = g_nccl.GetUniqueId(&u);
+  if (r != ncclSuccess) { g_create_err = g_nccl.GetErrorString(r); return PIC1DP_ENCCL; }
+  memcpy(id, &u, sizeof(u));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_comm_init(pic1dp_gpu_t *h, const uint8_t id[PIC1DP_UNIQUE_ID_BYTES]) {
+  if (!h || !id) return PIC1DP_EINVAL;
+  if (h->p.nranks == 1) return PIC1DP_OK;
+  if (!g_nccl.load()) { h->err = g_nccl.err; return PIC1DP_ENCCL; }
+  CK(cudaSetDevice(h->p.device));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  ncclResult_t r = g_nccl.CommInitRank(&h->comm, h->p.nranks, u, h->p.rank);
+  if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return PIC1DP_ENCCL; }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const double *x, const double *v,
+                           const double *p, const double *w) {
+  if (!h || isp < 0 || isp >= h->p.nspecies || np < 0 || !x || !v || !p || !w) {
+    if (h) h->err = "set_markers: bad argument";
+    return PIC1DP_EINVAL;
+  }
+  if (np > h->p.capacity) { h->err = "set_markers: np exceeds capacity"; return PIC1DP_ECAPACITY; }
+  CK(cudaSetDevice(h->p.device));
+  Species &S = h->sp[isp];
+  S.cur = 0;
+  S.bak = 0;
+  S.np = np;
+  const size_t b = (size_t)np * 8;
+  CK(cudaMemcpyAsync(S.x[0], x, b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(S.v[0], v, b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(S.p, p, b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(S.w[0], w, b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // host buffers are only borrowed for the call
+  h->h2d += 4 * (int64_t)b;
+  S.loaded = true;
+  h->partial_valid = false;
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_get_markers(pic1dp_gpu_t *h, int32_t isp, double *x, double *v, double *p, double *w, int64_t *np) {
+  if (!h || isp < 0 || isp >= h->p.nspecies) return PIC1DP_EINVAL;
+  Species &S = h->sp[isp];
+  if (!S.loaded) { h->err = "get_markers before set_markers"; return PIC1DP_ESTATE; }
+  CK(cudaSetDevice(h->p.device));
+  const size_t b = (size_t)S.np * 8;
+  if (x) { CK(cudaMemcpyAsync(x, S.x[S.cur], b, cudaMemcpyDeviceToHost, h->stream)); h->d2h += b; }
+  if (v) { CK(cudaMemcpyAsync(v, S.v[S.cur], b, cudaMemcpyDeviceToHost, h->stream)); h->d2h += b; }
+  if (p) { CK(cudaMemcpyAsync(p, S.p, b, cudaMemcpyDeviceToHost, h->stream)); h->d2h += b; }
+  if (w) { CK(cudaMemcpyAsync(w, S.w[S.cur], b, cudaMemcpyDeviceToHost, h->stream)); h->d2h += b; }
+  CK(cudaStreamSynchronize(h->stream));
+  if (np) *np = S.np;
+  return PIC1DP_OK;
+}
+
+static void fill_grid_args(pic1dp_gpu_t *h, GridArgs &g) {
+  const pic1dp_params &p = h->p;
+  memset(&g, 0, sizeof(g));
+  g.nx = p.nx;
+  g.nmode = p.nmode;
+  g.nspecies = p.nspecies;
+  g.ngrids = h->grid;
+  g.deltaf = p.deltaf;
+  g.matrix_path = p.iptclshape <= 2;
+  g.zero_partials = h->dep == DEP_GLOBAL_RED;
+  g.lx = p.lx;
+  g.rnx = (double)p.nx;
+  for (int s = 0; s < p.nspecies; s++) {
+    g.Z[s] = p.charge[s];
+    g.n[s] = p.density[s];
+  }
+  g.partial = h->d_partial;
+  g.red = h->d_red;
+  g.rho = h->d_rho;
+  g.E = h->d_E;
+  g.mode_re = h->d_mre;
+  g.mode_im = h->d_mim;
+  g.F_re = h->d_Fre;
+  g.F_im = h->d_Fim;
+  g.ginv = h->d_ginv;
+  g.a_im = -1.0 / (double)p.nx;
+  g.a_re = 1.0 / (double)p.nx;
+  g.nx_over_lx = (double)p.nx / p.lx;
+  g.energy = h->d_energy;
+}
+
+static void fill_particle_args(pic1dp_gpu_t *h, int s, ParticleArgs &a) {
+  const pic1dp_params &p = h->p;
+  Species &S = h->sp[s];
+  memset(&a, 0, sizeof(a));
+  a.p = S.p;
+  a.E = h->d_E;
+  a.partial = h->d_partial + (size_t)s * h->grid * p.nx;
+  a.noob = h->d_noob;
+  a.np = S.np;
+  a.nx = p.nx;
+  a.lx = p.lx;
+  a.rnx = (double)p.nx;
+  a.c = S.c;
+  a.deltaf = p.deltaf;
+  a.linear = p.linear;
+  a.right_frac = p.iptclshape <= 2;
+}
+
+static int check_loaded(pic1dp_gpu_t *h, const char *who) {
+  for (int s = 0; s < h->p.nspecies; s++)
+    if (!h->sp[s].loaded) {
+      h->err = std::string(who) + ": markers of every species must be set first";
+      return PIC1DP_ESTATE;
+    }
+  return PIC1DP_OK;
+}
+
+// wrap (+ deposit) pass over all species
+static int run_deposit_pass(pic1dp_gpu_t *h, bool deposit) {
+  PushKernel k = pick_deposit(h->dep, deposit);
+  for (int s = 0; s < h->p.nspecies; s++) {
+    Species &S = h->sp[s];
+    ParticleArgs a;
+    fill_particle_args(h, s, a);
+    a.x_cur = S.x[S.cur];
+    a.x_out = S.x[S.cur];
+    a.dep_src = h->p.deltaf ? S.w[S.cur] : S.p;
+    k<<<h->grid, h->threads, deposit ? h->smem_dep : 0, h->stream>>>(a);
+    CKL(h);
+  }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_compute_shape_x(pic1dp_gpu_t *h) {
+  if (!h) return PIC1DP_EINVAL;
+  int rc = check_loaded(h, "compute_shape_x");
+  if (rc) return rc;
+  if (h->p.iptclshape == 4) return PIC1DP_OK;  // src/pic1dp.F90:65, :86
+  if (h->partial_valid) return PIC1DP_OK;      // fused push already wrapped x
+  CK(cudaSetDevice(h->p.device));
+  return run_deposit_pass(h, false);
+}
+
+int pic1dp_gpu_get_shape_x(pic1dp_gpu_t *h, int32_t isp, int32_t *indexes, double *values_left,
+                           double *values_right) {
+  if (!h || isp < 0 || isp >= h->p.nspecies) return PIC1DP_EINVAL;
+  Species &S = h->sp[isp];
+  if (!S.loaded) { h->err = "get_shape_x before set_markers"; return PIC1DP_ESTATE; }
+  if (S.np == 0) return PIC1DP_OK;
+  CK(cudaSetDevice(h->p.device));
+  int *d_ix = nullptr;
+  double *d_sl = nullptr, *d_sr = nullptr;
+  const size_t n = (size_t)S.np;
+  CK(cudaMalloc(&d_ix, n * 4));
+  CK(cudaMalloc(&d_sl, n * 8));
+  CK(cudaMalloc(&d_sr, n * 8));
+  ParticleArgs a;
+  fill_particle_args(h, isp, a);
+  a.x_cur = S.x[S.cur];
+  k_shape_x<<<h->nsm * 4, 256, 0, h->stream>>>(a, d_ix, d_sl, d_sr);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    h->launches++;
+    if (indexes) e = cudaMemcpyAsync(indexes, d_ix, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && values_left) e = cudaMemcpyAsync(values_left, d_sl, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && values_right) e = cudaMemcpyAsync(values_right, d_sr, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d_ix);
+  cudaFree(d_sl);
+  cudaFree(d_sr);
+  if (e != cudaSuccess) { h->err = std::string("get_shape_x: ") + cudaGetErrorString(e); return PIC1DP_ECUDA; }
+  return PIC1DP_OK;
+}
+
+static int reduce_and_finalize(pic1dp_gpu_t *h, cudaEvent_t mid) {
+  GridArgs g;
+  fill_grid_args(h, g);
+  const int nb = (h->p.nx + 127) / 128;
+  k_reduce_charge<<<nb, 128, 0, h->stream>>>(g);
+  CKL(h);
+  (void)mid;
+  if (h->p.nranks > 1) {
+    if (!h->comm) { h->err = "collect_charge: nranks > 1 but comm_init was not called"; return PIC1DP_ESTATE; }
+    ncclResult_t r = g_nccl.AllReduce(h->d_red, h->d_red, (size_t)h->nred * h->p.nx, ncclDouble, ncclSum, h->comm,
+                                      h->stream);  // MPI_Allreduce, src/pic1dp_interaction.F90:132-133
+    if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return PIC1DP_ENCCL; }
+    h->nccl_calls++;
+  }
+  k_finalize_rho<<<nb, 128, 0, h->stream>>>(g);
+  CKL(h);
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_collect_charge(pic1dp_gpu_t *h) {
+  if (!h) return PIC1DP_EINVAL;
+  int rc = check_loaded(h, "collect_charge");
+  if (rc) return rc;
+  CK(cudaSetDevice(h->p.device));
+  if (!h->partial_valid) {
+    rc = run_deposit_pass(h, true);
+    if (rc) return rc;
+  }
+  h->partial_valid = false;
+  return reduce_and_finalize(h, nullptr);
+}
+
+int pic1dp_gpu_solve_field(pic1dp_gpu_t *h) {
+  if (!h) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  GridArgs g;
+  fill_grid_args(h, g);
+  const int smem = (h->p.nx + 2 * h->p.nmode) * 8;
+  if (h->p.field_mode == PIC1DP_FIELD_SEQUENTIAL)
+    k_field_solve<true><<<1, 1024, smem, h->stream>>>(g);
+  else
+    k_field_solve<false><<<1, 1024, smem, h->stream>>>(g);
+  CKL(h);
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
+  if (!h || (irk != 1 && irk != 2)) { if (h) h->err = "push: irk must be 1 or 2"; return PIC1DP_EINVAL; }
+  int rc = check_loaded(h, "push");
+  if (rc) return rc;
+  CK(cudaSetDevice(h->p.device));
+  const pic1dp_params &p = h->p;
+  const bool fused = p.fuse != 0;
+  PushKernel k = pick_push(p.iptcldist, h->dep, irk == 2, fused);
+  if (fused && h->partial_valid && h->dep == DEP_GLOBAL_RED)  // a previous fused deposit was never collected
+    CK(cudaMemsetAsync(h->d_partial, 0, (size_t)p.nspecies * h->grid * p.nx * 8, h->stream));
+  for (int s = 0; s < p.nspecies; s++) {
+    Species &S = h->sp[s];
+    ParticleArgs a;
+    fill_particle_args(h, s, a);
+    int out;
+    if (irk == 1) {
+      S.bak = S.cur;       // VecCopy x,v,w -> *_bak (:181-187) without moving a byte
+      out = S.cur ^ 1;
+      a.dt = 0.5 * p.dt;   // :179
+    } else {
+      out = S.bak;         // overwrite the start-of-step set
+      a.dt = p.dt;         // :192
+    }
+    a.x_cur = S.x[S.cur];
+    a.v_cur = S.v[S.cur];
+    a.w_cur = S.w[S.cur];
+    a.x_bak = S.x[S.bak];
+    a.v_bak = S.v[S.bak];
+    a.w_bak = S.w[S.bak];
+    a.x_out = S.x[out];
+    a.v_out = S.v[out];
+    a.w_out = S.w[out];
+    k<<<h->grid, h->threads, h->smem_push, h->stream>>>(a);
+    CKL(h);
+    S.cur = out;
+  }
+  h->partial_valid = fused;
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_step(pic1dp_gpu_t *h, int32_t nsteps) {
+  if (!h || nsteps < 0) return PIC1DP_EINVAL;
+  for (int it = 0; it < nsteps; it++)
+    for (int irk = 1; irk <= 2; irk++) {  // src/pic1dp.F90:79-90
+      int rc = pic1dp_gpu_push(h, irk);
+      if (rc) return rc;
+      if (h->p.iptclshape < 4) {
+        rc = pic1dp_gpu_compute_shape_x(h);
+        if (rc) return rc;
+      }
+      rc = pic1dp_gpu_collect_charge(h);
+      if (rc) return rc;
+      rc = pic1dp_gpu_solve_field(h);
+      if (rc) return rc;
+    }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_profile_step(pic1dp_gpu_t *h, float ms[6]) {
+  if (!h || !ms) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  int e = 0;
+  CK(cudaEventRecord(h->pev[e++], h->stream));
+  for (int irk = 1; irk <= 2; irk++) {
+    int rc = pic1dp_gpu_push(h, irk);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->pev[e++], h->stream));
+    if (h->p.iptclshape < 4) {
+      rc = pic1dp_gpu_compute_shape_x(h);
+      if (rc) return rc;
+    }
+    rc = pic1dp_gpu_collect_charge(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->pev[e++], h->stream));
+    rc = pic1dp_gpu_solve_field(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->pev[e++], h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 6; i++) CK(cudaEventElapsedTime(&ms[i], h->pev[i], h->pev[i + 1]));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_get_field(pic1dp_gpu_t *h, double *electric, double *chargeden, double *mode_re, double *mode_im) {
+  if (!h) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  const size_t nb = (size_t)h->p.nx * 8, mb = (size_t)h->p.nmode * 8;
+  if (electric) { CK(cudaMemcpyAsync(electric, h->d_E, nb, cudaMemcpyDeviceToHost, h->stream)); h->d2h += nb; }
+  if (chargeden) { CK(cudaMemcpyAsync(chargeden, h->d_rho, nb, cudaMemcpyDeviceToHost, h->stream)); h->d2h += nb; }
+  if (mode_re) { CK(cudaMemcpyAsync(mode_re, h->d_mre, mb, cudaMemcpyDeviceToHost, h->stream)); h->d2h += mb; }
+  if (mode_im) { CK(cudaMemcpyAsync(mode_im, h->d_mim, mb, cudaMemcpyDeviceToHost, h->stream)); h->d2h += mb; }
+  CK(cudaStreamSynchronize(h->stream));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_set_field(pic1dp_gpu_t *h, const double *electric, const double *chargeden) {
+  if (!h) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  const size_t nb = (size_t)h->p.nx * 8;
+  if (electric) { CK(cudaMemcpyAsync(h->d_E, electric, nb, cudaMemcpyHostToDevice, h->stream)); h->h2d += nb; }
+  if (chargeden) { CK(cudaMemcpyAsync(h->d_rho, chargeden, nb, cudaMemcpyHostToDevice, h->stream)); h->h2d += nb; }
+  CK(cudaStreamSynchronize(h->stream));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_get_operators(pic1dp_gpu_t *h, double *F_re, double *F_im, double *grad_inv) {
+  if (!h) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  const size_t fb = (size_t)h->p.nx * h->p.nmode * 8;
+  if (F_re) CK(cudaMemcpy(F_re, h->d_Fre, fb, cudaMemcpyDeviceToHost));
+  if (F_im) CK(cudaMemcpy(F_im, h->d_Fim, fb, cudaMemcpyDeviceToHost));
+  if (grad_inv) CK(cudaMemcpy(grad_inv, h->d_ginv, (size_t)h->p.nmode * 8, cudaMemcpyDeviceToHost));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_field_energy(pic1dp_gpu_t *h, double *energy) {
+  if (!h || !energy) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  GridArgs g;
+  fill_grid_args(h, g);
+  k_field_energy<<<1, 1024, 0, h->stream>>>(g);
+  CKL(h);
+  CK(cudaMemcpyAsync(energy, h->d_energy, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->d2h += 8;
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_sync(pic1dp_gpu_t *h) {
+  if (!h) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaStreamSynchronize(h->stream));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_timer_start(pic1dp_gpu_t *h) {
+  if (!h) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_timer_stop(pic1dp_gpu_t *h, float *milliseconds) {
+  if (!h || !milliseconds) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(milliseconds, h->ev0, h->ev1));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_get_counters(pic1dp_gpu_t *h, pic1dp_counters *c) {
+  if (!h || !c) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  unsigned long long noob = 0;
+  CK(cudaMemcpyAsync(&noob, h->d_noob, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  c->kernel_launches = h->launches;
+  c->nccl_calls = h->nccl_calls;
+  c->oob_markers = (int64_t)noob;
+  c->h2d_bytes = h->h2d;
+  c->d2h_bytes = h->d2h;
+  c->deposit_mode = h->dep;
+  c->grid_ctas = h->grid;
+  c->cta_threads = h->threads;
+  c->smem_bytes = h->smem_push;
+  return PIC1DP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+"""Host-side mirror of the reference's module interface for the hot path, over the C ABI.
+
+The reference exposes the path as argument-less Fortran module procedures over module-global state
+(/root/reference/src/pic1dp_interaction.F90:33,161; src/pic1dp_particle.F90:66,275,819;
+src/pic1dp_field.F90:55,218,315) driven by `program pic1dp` (src/pic1dp.F90:63-109).  `Pic1dpModules` keeps
+the same procedure names, the same implicit inputs (`global_irk`, the `input_*` parameters) and the same
+error behaviour (every call leaves its status in `global_ierr`; non-zero raises, like CHKERRQ aborts), so a
+test can replay the reference driver line by line.  The Fortran ISO_C_BINDING shim with the identical
+structure is fortran/pic1dp_gpu_shim.F90.
+
+Everything here is plumbing: the work happens in libpic1dp_b200.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import Counters, Params
+
+
+class Pic1dpError(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str):
+        self.code = code
+        super().__init__(f"{where}: error {code} ({_capi.load().pic1dp_gpu_strerror(code).decode()}): {detail}")
+
+
+def default_params(**over) -> Params:
+    """Defaults of src/pic1dp_input.F90.  Keyword overrides: scalars, or sequences for per-species/per-mode fields."""
+    p = Params()
+    _capi.load().pic1dp_gpu_params_default(C.byref(p))
+    for k, v in over.items():
+        cur = getattr(p, k)
+        if hasattr(cur, "__len__"):
+            for i, vi in enumerate(v):
+                cur[i] = vi
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def _dp(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "fp64 C-contiguous arrays only"
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ptr(addr: int):
+    return C.cast(C.c_void_p(addr), C.POINTER(C.c_double))
+
+
+class Pic1dGpu:
+    """RAII wrapper of one pic1dp_gpu_t handle (one GPU, one stream)."""
+
+    def __init__(self, params: Params):
+        self.L = _capi.load()
+        self.params = params
+        self._h = C.c_void_p()
+        rc = self.L.pic1dp_gpu_create(C.byref(params), C.byref(self._h))
+        if rc:
+            self._h = C.c_void_p()
+            raise Pic1dpError(rc, "pic1dp_gpu_create", self.L.pic1dp_gpu_last_error(None).decode())
+
+    def _ck(self, rc: int, where: str):
+        if rc:
+            raise Pic1dpError(rc, where, self.L.pic1dp_gpu_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.L.pic1dp_gpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- communicator ----
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * _capi.UNIQUE_ID_BYTES)()
+        rc = self.L.pic1dp_gpu_comm_unique_id(buf)
+        if rc:
+            raise Pic1dpError(rc, "pic1dp_gpu_comm_unique_id", self.L.pic1dp_gpu_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes):
+        buf = (C.c_uint8 * _capi.UNIQUE_ID_BYTES).from_buffer_copy(uid)
+        self._ck(self.L.pic1dp_gpu_comm_init(self._h, buf), "pic1dp_gpu_comm_init")
+
+    # ---- markers ----
+    def set_markers(self, isp: int, x, v, p, w):
+        n = x.size
+        assert v.size == n and p.size == n and w.size == n
+        self._ck(self.L.pic1dp_gpu_set_markers(self._h, isp, n, _dp(x), _dp(v), _dp(p), _dp(w)), "set_markers")
+
+    def set_markers_ptr(self, isp: int, n: int, x: int, v: int, p: int, w: int):
+        """Raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        self._ck(self.L.pic1dp_gpu_set_markers(self._h, isp, n, _ptr(x), _ptr(v), _ptr(p), _ptr(w)), "set_markers")
+
+    def get_markers(self, isp: int, want=("x", "v", "p", "w")):
+        n = C.c_int64()
+        self._ck(self.L.pic1dp_gpu_get_markers(self._h, isp, None, None, None, None, C.byref(n)), "get_markers")
+        out = {k: np.empty(n.value) for k in want}
+        self._ck(self.L.pic1dp_gpu_get_markers(self._h, isp, _dp(out.get("x")), _dp(out.get("v")), _dp(out.get("p")),
+                                               _dp(out.get("w")), C.byref(n)), "get_markers")
+        return out
+
+    def get_markers_ptr(self, isp: int, x: int = 0, v: int = 0, p: int = 0, w: int = 0) -> int:
+        n = C.c_int64()
+        f = lambda a: _ptr(a) if a else None
+        self._ck(self.L.pic1dp_gpu_get_markers(self._h, isp, f(x), f(v), f(p), f(w), C.byref(n)), "get_markers")
+        return n.value
+
+    def get_shape_x(self, isp: int):
+        """(indexes, values_left, values_right) of the current x -- particle_shape_x_indexes / _values."""
+        n = C.c_int64()
+        self._ck(self.L.pic1dp_gpu_get_markers(self._h, isp, None, None, None, None, C.byref(n)), "get_markers")
+        ix = np.empty(n.value, dtype=np.int32)
+        sl, sr = np.empty(n.value), np.empty(n.value)
+        self._ck(self.L.pic1dp_gpu_get_shape_x(self._h, isp, ix.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sl), _dp(sr)),
+                 "get_shape_x")
+        return ix, sl, sr
+
+    # ---- the hot path ----
+    def compute_shape_x(self):
+        self._ck(self.L.pic1dp_gpu_compute_shape_x(self._h), "compute_shape_x")
+
+    def collect_charge(self):
+        self._ck(self.L.pic1dp_gpu_collect_charge(self._h), "collect_charge")
+
+    def solve_field(self):
+        self._ck(self.L.pic1dp_gpu_solve_field(self._h), "solve_field")
+
+    def push(self, irk: int):
+        self._ck(self.L.pic1dp_gpu_push(self._h, irk), "push")
+
+    def step(self, nsteps: int = 1):
+        self._ck(self.L.pic1dp_gpu_step(self._h, nsteps), "step")
+
+    # ---- fields ----
+    def get_field(self):
+        nx, M = self.params.nx, self.params.nmode
+        E, rho, mre, mim = np.empty(nx), np.empty(nx), np.empty(M), np.empty(M)
+        self._ck(self.L.pic1dp_gpu_get_field(self._h, _dp(E), _dp(rho), _dp(mre), _dp(mim)), "get_field")
+        return dict(electric=E, chargeden=rho, mode_re=mre, mode_im=mim)
+
+    def get_field_ptr(self, E: int = 0, rho: int = 0, mre: int = 0, mim: int = 0):
+        f = lambda a: _ptr(a) if a else None
+        self._ck(self.L.pic1dp_gpu_get_field(self._h, f(E), f(rho), f(mre), f(mim)), "get_field")
+
+    def set_field(self, electric=None, chargeden=None):
+        e = None if electric is None else np.ascontiguousarray(electric, dtype=np.float64)
+        r = None if chargeden is None else np.ascontiguousarray(chargeden, dtype=np.float64)
+        self._ck(self.L.pic1dp_gpu_set_field(self._h, _dp(e), _dp(r)), "set_field")
+
+    def get_operators(self):
+        nx, M = self.params.nx, self.params.nmode
+        Fre, Fim, g = np.empty(nx * M), np.empty(nx * M), np.empty(M)
+        self._ck(self.L.pic1dp_gpu_get_operators(self._h, _dp(Fre), _dp(Fim), _dp(g)), "get_operators")
+        return Fre.reshape(nx, M), Fim.reshape(nx, M), g
+
+    def field_energy(self) -> float:
+        e = C.c_double()
+        self._ck(self.L.pic1dp_gpu_field_energy(self._h, C.byref(e)), "field_energy")
+        return e.value
+
+    # ---- instrumentation ----
+    def sync(self):
+        self._ck(self.L.pic1dp_gpu_sync(self._h), "sync")
+
+    def timer_start(self):
+        self._ck(self.L.pic1dp_gpu_timer_start(self._h), "timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._ck(self.L.pic1dp_gpu_timer_stop(self._h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def counters(self) -> Counters:
+        c = Counters()
+        self._ck(self.L.pic1dp_gpu_get_counters(self._h, C.byref(c)), "get_counters")
+        return c
+
+    def profile_step(self):
+        ms = (C.c_float * 6)()
+        self._ck(self.L.pic1dp_gpu_profile_step(self._h, ms), "profile_step")
+        return list(ms)
+
+
+def petsc_decide(n: int, npe: int, rank: int):
+    """Contiguous block split PETSc makes for VecSetSizes(PETSC_DECIDE, n) (requested at
+    src/pic1dp_particle.F90:91): rank r owns n/npe + (r < n mod npe) entries.  Returns [low, high)."""
+    base, rem = divmod(n, npe)
+    low = base * rank + min(rank, rem)
+    return low, low + base + (1 if rank < rem else 0)
+
+
+class Pic1dpModules:
+    """The three reference modules as one object: same procedure names and implicit state.
+
+    Usage replays src/pic1dp.F90:57-90::
+
+        m = Pic1dpModules(params); m.particle_init(); m.field_init()
+        m.particle_set(0, x, v, p, w)             # stands in for particle_load (host-generated markers)
+        if m.input.iptclshape < 4: m.particle_compute_shape_x()
+        m.interaction_collect_charge(); m.field_solve_electric()
+        for m.global_irk in (1, 2):
+            m.interaction_push_particle()
+            if m.input.iptclshape < 4: m.particle_compute_shape_x()
+            m.interaction_collect_charge(); m.field_solve_electric()
+    """
+
+    def __init__(self, params: Params):
+        self.input = params          # input_* parameters (src/pic1dp_input.F90)
+        self.global_irk = 1          # src/pic1dp_global.F90:64
+        self.global_ierr = 0         # src/pic1dp_global.F90:59
+        self.global_mype = params.rank
+        self.global_npe = params.nranks
+        self.gpu: Optional[Pic1dGpu] = None
+        self.particle_np = [0] * params.nspecies  # src/pic1dp_particle.F90:54
+
+    def _call(self, fn, *a):
+        try:
+            r = fn(*a)
+            self.global_ierr = 0
+            return r
+        except Pic1dpError as e:  # CHKERRQ(global_ierr)
+            self.global_ierr = e.code
+            raise
+
+    # pic1dp_particle
+    def particle_init(self):
+        if self.gpu is None:
+            self.gpu = self._call(Pic1dGpu, self.input)
+
+    def particle_set(self, isp: int, x, v, p, w):
+        self.particle_np[isp] = x.size
+        self._call(self.gpu.set_markers, isp, x, v, p, w)
+
+    def particle_get(self, isp: int):
+        return self._call(self.gpu.get_markers, isp)
+
+    def particle_compute_shape_x(self):
+        self._call(self.gpu.compute_shape_x)
+
+    def particle_final(self):
+        if self.gpu is not None:
+            self.gpu.close()
+            self.gpu = None
+
+    # pic1dp_field
+    def field_init(self):
+        self.particle_init()  # one handle owns both modules' state
+
+    def field_solve_electric(self):
+        self._call(self.gpu.solve_field)
+
+    def field_final(self):
+        self.particle_final()
+
+    @property
+    def field_electric(self):
+        return self._call(self.gpu.get_field)["electric"]
+
+    @property
+    def field_chargeden(self):
+        return self._call(self.gpu.get_field)["chargeden"]
+
+    @property
+    def field_mode_re(self):
+        return self._call(self.gpu.get_field)["mode_re"]
+
+    @property
+    def field_mode_im(self):
+        return self._call(self.gpu.get_field)["mode_im"]
+
+    # pic1dp_interaction
+    def interaction_collect_charge(self):
+        self._call(self.gpu.collect_charge)
+
+    def interaction_push_particle(self):
+        self._call(self.gpu.push, self.global_irk)

@@ -1,0 +1,188 @@
+"""CPU checks of the oracle's hot-path restatement against an independent numpy re-derivation of the same
+reference statements and against analytic answers.  (The reference holds no golden vectors for this path --
+"parity unpinned" -- so the restatement is cross-checked, not pinned.)"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from helpers import OracleRun, copy_state, make_params, synth_markers
+
+
+def np_shape(x, lx, nx):
+    sx = x / lx * nx
+    ix = np.floor(sx).astype(np.int64)
+    s = 1.0 - (sx - ix)
+    return ix, s
+
+
+def test_field_test_analytic():
+    # /root/reference/src/pic1dp_field.F90:276-309 with the default grid: E = sin(theta)/k1, k1 = 0.36
+    o = O.Oracle(O.default_params())
+    j = np.arange(192)
+    E, mre, mim = o.field_solve(np.cos(2.0 * np.pi * j / 192))
+    assert np.max(np.abs(E - np.sin(2.0 * np.pi * j / 192) / 0.36)) < 1e-14
+    # E_k = -i rho_k / k with rho_k = 1/2: re = 0, im = -1/(2k)
+    assert abs(mre[0]) < 1e-15 and abs(mim[0] + 0.5 / 0.36) < 1e-14
+
+
+def test_field_solve_discards_unkept_modes():
+    # F1 of SURVEY.md: only input_modes survive; a mode-2 density gives E == 0 when only mode 1 is kept
+    o = O.Oracle(O.default_params())
+    j = np.arange(192)
+    E, _, _ = o.field_solve(np.cos(2.0 * np.pi * 2 * j / 192))
+    assert np.max(np.abs(E)) < 1e-15
+
+
+def test_field_solve_vs_numpy_formula():
+    p = O.default_params(nx=256, nmode=3, modes=[1, 2, 5])
+    o = O.Oracle(p)
+    rho = np.random.default_rng(0).standard_normal(256)
+    E, mre, mim = o.field_solve(rho)
+    j = np.arange(256)
+    Eref = np.zeros(256)
+    for i, m in enumerate([1, 2, 5]):
+        th = 2.0 * np.pi / 256 * m * j
+        k = 2.0 * np.pi / p.lx * m
+        im = -np.sum(np.cos(th) * rho) / 256 / k
+        re = np.sum(-np.sin(th) * rho) / 256 / k
+        assert abs(im - mim[i]) < 1e-13 and abs(re - mre[i]) < 1e-13
+        Eref += 2.0 * (np.cos(th) * re - np.sin(th) * im)
+    assert np.max(np.abs(E - Eref)) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [4, 2])
+def test_deposit_vs_numpy(shape):
+    op, _ = make_params(nx=128, iptclshape=shape)
+    st = synth_markers(op, 20000, seed=1, spread=1.2)
+    o = O.Oracle(op)
+    x = st["x"].copy()
+    c1, noob = o.deposit_species(x, st["w"])
+    xw = np.fmod(st["x"], op.lx)
+    xw = np.where(xw < 0, xw + op.lx, xw)
+    assert np.array_equal(x, xw)
+    ix, s = np_shape(xw, op.lx, op.nx)
+    assert noob == int(np.sum(ix >= op.nx))
+    right = (1.0 - s) if shape >= 3 else (xw / op.lx * op.nx - ix)
+    ref = np.zeros(op.nx)
+    np.add.at(ref, ix % op.nx, s * st["w"])
+    np.add.at(ref, (ix + 1) % op.nx, right * st["w"])
+    assert np.max(np.abs(c1 - ref)) < 1e-13 * np.sum(np.abs(st["w"])) / op.nx * 50
+
+
+def test_charge_is_conserved():
+    op, _ = make_params(nx=64)
+    st = synth_markers(op, 5000, seed=2)
+    r = OracleRun(op, [[copy_state(st)]])
+    r.collect_charge()
+    assert abs(np.sum(r.rho) * op.lx / op.nx - op.charge[0] * np.sum(st["w"])) < 1e-13 * np.sum(np.abs(st["w"]))
+
+
+@pytest.mark.parametrize("dist", [0, 1, 2, 3])
+def test_dlnf0_is_minus_dlog_f0(dist):
+    """-d f0/dv / f0 against a central difference of log f0 (src/pic1dp_interaction.F90:275-326)."""
+    op, _ = make_params(iptcldist=dist, temperature=[1.3], temperature2=[0.6], mass=[1.7], density=[0.8], v0=[2.5])
+    o = O.Oracle(op)
+    T, T2, m, n, v0 = 1.3, 0.6, 1.7, 0.8, 2.5
+
+    def f0(v):
+        if dist == 1:
+            return v * v * np.exp(-v * v / 2)
+        if dist == 2:
+            return np.exp(-(v + v0) ** 2 / (2 * T / m)) + np.exp(-(v - v0) ** 2 / (2 * T / m))
+        if dist == 3:
+            return n * np.exp(-v * v / (2 * T / m)) / np.sqrt(T / m) + (1 - n) * np.exp(-(v - v0) ** 2 / (2 * T2 / m)) / np.sqrt(T2 / m)
+        return np.exp(-(v - v0) ** 2 / (2 * T / m))
+
+    for v in (-3.1, -0.7, 0.4, 1.9, 2.5, 4.2):
+        h = 1e-6
+        num = -(np.log(f0(v + h)) - np.log(f0(v - h))) / (2 * h)
+        assert abs(o.dlnf0(0, v) - num) < 1e-6 * max(1.0, abs(num))
+
+
+def test_push_vs_numpy_one_substep():
+    op, _ = make_params(nx=128)
+    st = synth_markers(op, 10000, seed=3)
+    E = 1e-3 * np.cos(2 * np.pi * np.arange(128) / 128)
+    r = OracleRun(op, [[copy_state(st)]])
+    r.E = E.copy()
+    r.push(1)
+    ix, s = np_shape(st["x"], op.lx, op.nx)
+    Ep = E[ix] * s + E[(ix + 1) % 128] * (1.0 - s)
+    dt = 0.5 * op.dt
+    v = st["v"]
+    e1, e2 = np.exp(-v * v / 2.0), np.exp(-(v - 5.0) ** 2 / 2.0)
+    tmp2 = (0.9 * v * e1 + 0.1 * (v - 5.0) * e2) / (0.9 * e1 + 0.1 * e2)
+    out = r.st[0][0]
+    assert np.array_equal(out["x"], st["x"] + dt * v)
+    assert np.array_equal(out["v"], st["v"] + dt * Ep * -1.0 / 1.0)
+    wref = st["w"] + dt * ((st["p"] - st["w"]) * Ep) * tmp2 * -1.0
+    assert np.max(np.abs(out["w"] - wref)) < 1e-13 * np.max(np.abs(wref))
+    assert np.array_equal(out["xb"], st["x"]) and np.array_equal(out["wb"], st["w"])  # backup, :181-187
+
+
+def test_rank_emulation_matches_single_rank_to_rounding():
+    """Particle decomposition (PETSC_DECIDE blocks, src/pic1dp_particle.F90:91) changes only summation order."""
+    op, _ = make_params(nx=192)
+    st = synth_markers(op, 40001, seed=4)
+    one = OracleRun(op, [[copy_state(st)]])
+    parts = []
+    for r in range(4):
+        lo, hi = O.petsc_decide(40001, 4, r)
+        parts.append({k: a[lo:hi].copy() for k, a in st.items()})
+    assert sum(p["x"].size for p in parts) == 40001
+    four = OracleRun(op, [parts])
+    for run in (one, four):
+        run.init_field()
+        run.step()
+        run.step()
+    assert np.max(np.abs(one.rho - four.rho)) < 1e-12 * np.max(np.abs(one.rho))
+    assert np.max(np.abs(one.E - four.E)) < 1e-12 * np.max(np.abs(one.E))
+    assert np.allclose(np.concatenate([p["x"] for p in four.st[0]]), one.st[0][0]["x"], rtol=1e-13, atol=0)
+
+
+def test_orc_run_equals_python_replay():
+    """The threaded C driver (used as the timed CPU baseline) gives the same numbers as the call-by-call replay."""
+    op, _ = make_params(nx=192)
+    st = synth_markers(op, 30000, seed=5)
+    parts = [[{k: a[lo:hi].copy() for k, a in st.items()} for lo, hi in (O.petsc_decide(30000, 3, r) for r in range(3))]]
+    replay = OracleRun(op, [[copy_state(p) for p in parts[0]]])
+    replay.init_field()
+    E0 = replay.E.copy()
+    for _ in range(3):
+        replay.step()
+    res = O.Oracle(op).run(parts, 3, E0, nthreads=3)
+    assert np.array_equal(res["E"], replay.E) and np.array_equal(res["rho"], replay.rho)
+    for r in range(3):
+        for k in ("x", "v", "w"):
+            assert np.array_equal(parts[0][r][k], replay.st[0][r][k])
+    assert res["energy"][-1] == O.Oracle(op).field_energy(replay.E)
+
+
+def test_bump_on_tail_grows_at_the_analytic_rate():
+    """Physics known-answer: electron bump-on-tail, k = 0.36 (src/pic1dp_input.F90:47-72): field energy grows at
+    2*gamma with gamma = 0.0838311 (root of the dispersion relation solved by tools/dispersion.py:130-157).
+    Small marker count => loose tolerance; the fit is growthrate_energy_fit of tools/OutputData.py:153-170."""
+    from tools_py3.runinfo import growthrate_energy_fit
+    op, _ = make_params(nx=64)
+    n = 400000
+    st = synth_markers(op, n, seed=6)
+    # quiet start: stratified x and v remove most marker noise
+    rng = np.random.default_rng(6)
+    nxs, nvs = 500, n // 500
+    xs = (np.arange(nxs) + 0.5) / nxs * op.lx
+    vs = ((np.arange(nvs) + 0.5) / nvs - 0.5) * 16.0
+    X, V = np.meshgrid(xs, vs, indexing="ij")
+    st["x"], st["v"] = X.ravel().copy(), V.ravel().copy()
+    v = st["v"]
+    f0 = 0.9 * np.exp(-v * v / 2) / np.sqrt(2 * np.pi) + 0.1 * np.exp(-(v - 5.0) ** 2 / 2) / np.sqrt(2 * np.pi)
+    st["p"] = op.lx * 16.0 / n * f0
+    st["w"] = 1e-5 * np.sin(2 * np.pi / op.lx * st["x"]) * st["p"]
+    st["p"] = st["p"] + st["w"]
+    parts = [[{k: a[lo:hi].copy() for k, a in st.items()} for lo, hi in (O.petsc_decide(n, 8, r) for r in range(8))]]
+    init = OracleRun(op, [[copy_state(p) for p in parts[0]]])
+    init.init_field()
+    nsteps = 1000  # t = 50
+    res = O.Oracle(op).run(parts, nsteps, init.E, nthreads=8)
+    t = op.dt * (np.arange(nsteps) + 1)
+    gamma = growthrate_energy_fit(t, res["energy"], 20.0, 50.0) / 2.0
+    assert abs(gamma - 0.0838311) < 0.004, gamma
