@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the PIC1D hot path in particle-steps/s (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path through the C ABI
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one full timestep input_dt of the reference time loop (src/pic1dp.F90:79-93): 2 RK substeps, each
+= gather + push(x, w, v) + wrap + deposit, plus 2 field solves and 2 density all-reduces.  1 particle-step = 1 marker
+advanced one step.  Workload: BASELINE.json configs[3] -- bump-on-tail delta-f, 1e8 markers per GPU, nx=1024,
+weak scaling; markers are synthetic (numpy PCG64, seed = 1234 + rank) with the loader's distribution.
+
+Keys of the JSON line: see the measurement contract in DESIGN.md.  `value` = device-timed (CUDA events on the
+library's stream), markers resident in HBM; `e2e` = same metric through the C ABI with host (pinned) buffers:
+set_markers H2D inside the timed region, get_field D2H after every step and get_markers D2H at the reference's
+output cadence (every 10 steps, src/pic1dp_input.F90:250 / src/pic1dp.F90:98-108) and at the end.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_IRK1 = 56   # read x,v,w,p; write x',v',w'            (SURVEY.md 8d / DESIGN.md)
+BYTES_IRK2 = 80   # read mid x,v,w + start x,v,w + p; write x,v,w
+BYTES_STEP = BYTES_IRK1 + BYTES_IRK2
+OUTPUT_EVERY = 10  # input_output_interval / input_dt = 0.5 / 0.05
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--markers", type=float, default=1e8, help="markers per GPU")
+    ap.add_argument("--nx", type=int, default=1024)
+    ap.add_argument("--deposit", type=int, default=0, help="PIC1DP_DEPOSIT_* (0 = auto)")
+    ap.add_argument("--cpu-markers", type=float, default=2e7, help="markers of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def fill_markers(x, v, p, w, lx, seed, chunk=1 << 24):
+    """Bump-on-tail markers like particle_load's default branch (src/pic1dp_particle.F90:179-237), in place."""
+    n = x.size
+    rng = np.random.default_rng(seed)
+    c = lx * 16.0 / n
+    s2pi = np.sqrt(2.0 * np.pi)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        xs = rng.random(hi - lo) * lx
+        vs = (rng.random(hi - lo) - 0.5) * 16.0
+        f0 = 0.9 * np.exp(-vs * vs / 2.0) / s2pi + 0.1 * np.exp(-(vs - 5.0) ** 2 / 2.0) / s2pi
+        pp = c * f0
+        ww = 1e-5 * np.sin(2.0 * np.pi / lx * xs) * pp
+        x[lo:hi], v[lo:hi], w[lo:hi], p[lo:hi] = xs, vs, ww, pp + ww
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [t.strip() for t in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except Exception:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_run(nx, n_markers, steps, warmup, nthreads):
+    """The reference's algorithm for this path on host cores: oracle port with the reference's structure
+    (separate push / deposit passes, backup copies, per-rank private grids summed in rank order), one emulated
+    MPI rank per thread.  Returns particle-steps/s."""
+    from oracle import oracle as O
+    op = O.default_params(nx=nx)
+    orc = O.Oracle(op)
+    n = int(n_markers)
+    x, v, p, w = (np.empty(n) for _ in range(4))
+    fill_markers(x, v, p, w, op.lx, seed=999)
+    parts = []
+    for r in range(nthreads):
+        lo, hi = O.petsc_decide(n, nthreads, r)
+        parts.append(dict(x=x[lo:hi].copy(), v=v[lo:hi].copy(), p=p[lo:hi].copy(), w=w[lo:hi].copy()))
+    E0 = np.zeros(nx)
+    if warmup > 0:
+        r = orc.run([parts], warmup, E0, nthreads=nthreads)
+        E0 = r["E"]
+    r = orc.run([parts], steps, E0, nthreads=nthreads)
+    return n * steps / r["seconds"], r["seconds"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = int(args.cpu_markers)
+    value, secs = cpu_reference_run(args.nx, n, args.steps, args.warmup, cores)
+    sample = f"{n} markers x {args.steps} steps, nx={args.nx}, {cores} emulated MPI ranks (one per host thread)"
+    line = {
+        "impl": "reference", "metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of the reference loops (oracle/), not the PETSc binary: no "
+                                 "Fortran/MPI/PETSc toolchain exists in this image"},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    n = int(args.markers)
+    return {"workload": "configs[3]: bump-on-tail delta-f nonlinear, weak scaling 1e8 markers per GPU, nx=1024, "
+                        "1 mode, dt=0.05, iptclshape=4",
+            "markers_per_gpu": n, "markers_total": n * n_gpus, "nx": args.nx, "nmode": 1,
+            "bytes_per_particle_step": BYTES_STEP,
+            "l2": "inputs larger than L2: %.1f GB of marker state streamed per step per GPU" % (n * BYTES_STEP / 1e9),
+            "parallelism": f"particle-decomposition x{n_gpus}, replicated grid, ncclAllReduce(rho) per substep"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py ...")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
+
+    from pic1dp_b200 import build as _build
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    import pic1dp_b200 as P
+
+    n = int(args.markers)
+    gp = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit)
+    g = P.Pic1dGpu(gp)
+    if world > 1:
+        uid = [g.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(uid[0])
+
+    # ---- synthetic markers in pinned host memory ----
+    host = {k: torch.empty(n, dtype=torch.float64, pin_memory=True) for k in ("x", "v", "p", "w")}
+    hv = {k: t.numpy() for k, t in host.items()}
+    fill_markers(hv["x"], hv["v"], hv["p"], hv["w"], gp.lx, seed=1234 + rank)
+    ptr = {k: t.data_ptr() for k, t in host.items()}
+    nx = args.nx
+    hf = {k: torch.empty(m, dtype=torch.float64, pin_memory=True) for k, m in (("E", nx), ("rho", nx), ("re", 1), ("im", 1))}
+
+    def barrier():
+        g.sync()
+        if world > 1:
+            dist.barrier()
+        g.sync()
+
+    def max_over_ranks(val):
+        if world == 1:
+            return val
+        t = torch.tensor([val], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") ----
+    g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])
+    g.collect_charge()
+    g.solve_field()
+    g.step(args.warmup)
+    barrier()
+    c0 = g.counters()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    t0 = time.time()
+    g.timer_start()
+    g.step(args.steps)
+    ms = g.timer_stop()
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    c1 = g.counters()
+    ms = max_over_ranks(ms)
+    value = n * world * args.steps / (ms * 1e-3)
+    energy = g.field_energy()
+
+    # ---- roofline of the dominant kernel, CUDA events around each launch ----
+    prof = np.array([g.profile_step() for _ in range(5)])[1:].mean(axis=0)  # ms: push1, collect1, field1, push2, ...
+    peak, peak_src = measured_peak()
+    ach2 = n * BYTES_IRK2 / (prof[3] * 1e-3) / 1e9
+    ach1 = n * BYTES_IRK1 / (prof[0] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_push<bump-on-tail, irk=2, fused push+wrap+deposit>",
+                "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": float(prof[3]),
+                "algorithmic_bytes_per_launch": n * BYTES_IRK2}
+    roofline_detail = {
+        "irk1": {"achieved": ach1, "frac": ach1 / peak, "ms_per_launch": float(prof[0]), "bytes": n * BYTES_IRK1},
+        "step": {"achieved": n * BYTES_STEP / (ms / args.steps * 1e-3) / 1e9,
+                 "frac": n * BYTES_STEP / (ms / args.steps * 1e-3) / 1e9 / peak,
+                 "note": "136 B x markers / whole-step time incl. reduce, all-reduce, field solve"},
+        "grid_kernels_ms": {"reduce+allreduce+finalize": float(prof[1] + prof[4]), "field_solve": float(prof[2] + prof[5])},
+    }
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        h2d0, d2h0 = g.counters().h2d_bytes, g.counters().d2h_bytes
+        tw0 = time.perf_counter()
+        g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])   # H2D (particle_load -> device)
+        g.collect_charge()
+        g.solve_field()
+        for it in range(1, args.steps + 1):
+            g.step(1)
+            g.get_field_ptr(hf["E"].data_ptr(), hf["rho"].data_ptr(), hf["re"].data_ptr(), hf["im"].data_ptr())
+            if it % OUTPUT_EVERY == 0 or it == args.steps:               # output_all cadence: host needs x, v, w
+                g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], w=ptr["w"])
+        g.sync()
+        tw = time.perf_counter() - tw0
+        tw = max_over_ranks(tw)
+        cc = g.counters()
+        e2e = {"value": n * world * args.steps / tw, "unit": "particle-steps/s",
+               "h2d_bytes_per_step": (cc.h2d_bytes - h2d0) / args.steps,
+               "d2h_bytes_per_step": (cc.d2h_bytes - d2h0) / args.steps,
+               "ms_per_step": 1e3 * tw / args.steps,
+               "definition": "set_markers(pinned host) + K steps, get_field after every step, get_markers(x,v,w) "
+                             f"every {OUTPUT_EVERY} steps and at the end (reference output cadence); host wall clock, "
+                             "max over ranks"}
+        # worst case: markers live on the host and make the round trip every step
+        k2 = min(args.steps, 3)
+        barrier()
+        tw0 = time.perf_counter()
+        for it in range(k2):
+            g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])
+            g.collect_charge()
+            g.solve_field()
+            g.step(1)
+            g.get_field_ptr(hf["E"].data_ptr(), hf["rho"].data_ptr(), hf["re"].data_ptr(), hf["im"].data_ptr())
+            g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], w=ptr["w"])
+        tw2 = max_over_ranks(time.perf_counter() - tw0)
+        e2e["roundtrip_every_step"] = {"value": n * world * k2 / tw2, "steps": k2,
+                                       "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n + (2 * nx + 2) * 8}
+
+    # ---- CPU baseline beside it (rank 0, bounded sample) ----
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        ncpu = int(args.cpu_markers)
+        val, secs = cpu_reference_run(args.nx, ncpu, 5, 1, cores)
+        cpu = {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{ncpu} markers x 5 steps (+1 warm-up), nx={args.nx}, {cores} emulated MPI ranks; {secs:.1f} s",
+               "note": "CPU restatement of the reference loops (oracle/), not the PETSc binary"}
+
+    if rank == 0:
+        line = {
+            "metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
+            "nccl_calls": int(c1.nccl_calls - c0.nccl_calls),
+            "roofline": roofline, "roofline_detail": roofline_detail, "cpu_baseline": cpu,
+            "deposit_mode": int(c1.deposit_mode), "grid_ctas": int(c1.grid_ctas), "cta_threads": int(c1.cta_threads),
+            "smem_bytes": int(c1.smem_bytes), "oob_markers": int(c1.oob_markers), "field_energy": energy,
+        }
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,45 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
+// ---- exp() with its polynomial in the constant bank ------------------------------------------------------
+// exp(a) = 2^n * (1 + r + r^2 q(r)), n = rint(a log2 e), r = a - n ln2 (two-term Cody-Waite with FMA),
+// q = degree-9 near-minimax polynomial (tools_py3/gen_exp_coeffs.py, approximation error 2^-55.8).  Total error
+// < 1 ulp, like libdevice's exp; the coefficients are read as constant-bank operands of DFMA instead of being
+// rebuilt in registers with 2 moves each, which is what makes libdevice's exp cost ~60 issue slots here.
+// |a| > 700 (never reached by physical velocities) falls back to libdevice.
+__constant__ double c_exp_poly[10] = {
+    0x1.af38a9b0ec855p-26, 0x1.289185613a3d6p-22, 0x1.71de0dae63bb3p-19, 0x1.a019b90d2ae7ap-16,
+    0x1.a01a01a7c41d5p-13, 0x1.6c16c1788bd90p-10, 0x1.11111111109b3p-7,  0x1.5555555553d63p-5,
+    0x1.5555555555556p-3,  0x1.0000000000001p-1};
+__constant__ double c_exp_red[3] = {0x1.71547652b82fep+0 /* log2 e */, 0x1.62e42fefa39efp-1 /* ln2 hi */,
+                                    0x1.abc9e3b39803fp-56 /* ln2 lo */};
+
+__device__ __forceinline__ double exp_fast(double a) {
+  if (!(fabs(a) <= 700.0)) return exp(a);
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+  const double t = fma(a, c_exp_red[0], magic);
+  const int n = __double2loint(t);
+  const double nf = t - magic;
+  double r = fma(nf, -c_exp_red[1], a);
+  r = fma(nf, -c_exp_red[2], r);
+  double q = c_exp_poly[0];
+#pragma unroll
+  for (int k = 1; k < 10; k++) q = fma(q, r, c_exp_poly[k]);
+  const double r2 = r * r;
+  const double pr = fma(r2, q, r) + 1.0;  // in [0.70, 1.42]
+  return __hiloint2double(__double2hiint(pr) + (n << 20), __double2loint(pr));  // * 2^n, |n| <= 1010
+}
+
+// Compile-time configuration of the model switches.  CFG < 0: read them from the kernel arguments (generic
+// instantiation); CFG >= 0: bit 0 deltaf, bit 1 linear, bit 2 right_frac (iptclshape 1,2), bit 3 all constant
+// divisors are powers of two.  The specialised instantiations drop every select / uniform branch on them.
+template <int CFG> struct Cfg {
+  static __device__ __forceinline__ bool deltaf(const int a) { return CFG < 0 ? a != 0 : (CFG & 1) != 0; }
+  static __device__ __forceinline__ bool linear(const int a) { return CFG < 0 ? a != 0 : (CFG & 2) != 0; }
+  static __device__ __forceinline__ bool right_frac(const int a) { return CFG < 0 ? a != 0 : (CFG & 4) != 0; }
+  static __device__ __forceinline__ bool pow2(const int a) { return CFG < 0 ? a != 0 : (CFG & 8) != 0; }
+};
+
 // Per-species constants, all evaluated on the host in IEEE double exactly as the Fortran compiler folds them.
 struct SpeciesConst {
   double Z, m, T;           // charge, mass, temperature
@@ -97,8 +136,8 @@ __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
     return dsub(v, ddiv(2.0, v));
   } else if (DIST == 2) {  // two-stream2 :278-292
     const double vp = dadd(v, c.v0), vm = dsub(v, c.v0);
-    const double ep = exp(-DIVC(dmul(vp, vp), twoTm));
-    const double em = exp(-DIVC(dmul(vm, vm), twoTm));
+    const double ep = exp_fast(-DIVC(dmul(vp, vp), twoTm));
+    const double em = exp_fast(-DIVC(dmul(vm, vm), twoTm));
     const double num = dadd(dmul(vp, ep), dmul(vm, em));
     const double den = dadd(ep, em);
     double r = ddiv(num, den);
@@ -106,8 +145,8 @@ __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
     return DIVC(r, T);
   } else if (DIST == 3) {  // bump-on-tail :294-321
     const double vm = dsub(v, c.v0);
-    const double e1 = exp(-DIVC(dmul(v, v), twoTm));
-    const double e2 = exp(-DIVC(dmul(vm, vm), twoT2m));
+    const double e1 = exp_fast(-DIVC(dmul(v, v), twoTm));
+    const double e2 = exp_fast(-DIVC(dmul(vm, vm), twoT2m));
     const double a = DIVC(dmul(DIVC(dmul(c.n, v), Tm), e1), sqTm);
     const double b = DIVC(dmul(DIVC(dmul(c.omn, vm), T2m), e2), sqT2m);
     const double num = dadd(a, b);
@@ -119,32 +158,33 @@ __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
 #undef DIVC
 }
 
-template <int DIST>
+template <int DIST, int CFG>
 __device__ __forceinline__ double dlnf0(const SpeciesConst &c, double v) {
-  return c.pow2 ? dlnf0_impl<DIST, true>(c, v) : dlnf0_impl<DIST, false>(c, v);
+  return Cfg<CFG>::pow2(c.pow2) ? dlnf0_impl<DIST, true>(c, v) : dlnf0_impl<DIST, false>(c, v);
 }
 
 // ---- gather + push of one marker (src/pic1dp_interaction.F90:250-338) ----
-template <int DIST>
+template <int DIST, int CFG>
 __device__ __forceinline__ void push_one(const ParticleArgs &a, const double *sE, double x, double v, double w,
                                          double p, double xb, double vb, double wb, double &xo, double &vo,
                                          double &wo) {
+  typedef Cfg<CFG> F;
   bool oob = false;  // x == lx exactly was already counted by the deposit that produced this x
-  const Shape s = shape_of(x, a.lx, a.rnx, a.nx, a.right_frac, oob);
+  const Shape s = shape_of(x, a.lx, a.rnx, a.nx, F::right_frac(a.right_frac), oob);
   const double electric = dadd(dmul(sE[s.ix], s.sl), dmul(sE[s.ixr], s.sr));  // :254-257
   xo = dadd(xb, dmul(a.dt, v));                                              // :261
   wo = w;
-  if (a.deltaf) {
-    const double tmp1 = a.linear ? dmul(p, electric) : dmul(dsub(p, w), electric);  // :268-272
-    const double tmp2 = dlnf0<DIST>(a.c, v);
-    double t = dmul(dmul(dmul(a.dt, tmp1), tmp2), a.c.Z);  // :329
-    t = a.c.pow2 ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);       // :330
+  if (F::deltaf(a.deltaf)) {
+    const double tmp1 = F::linear(a.linear) ? dmul(p, electric) : dmul(dsub(p, w), electric);  // :268-272
+    const double tmp2 = dlnf0<DIST, CFG>(a.c, v);
+    double t = dmul(dmul(dmul(a.dt, tmp1), tmp2), a.c.Z);              // :329
+    t = F::pow2(a.c.pow2) ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);          // :330
     wo = dadd(wb, t);
   }
   vo = v;
-  if (!a.linear) {
+  if (!F::linear(a.linear)) {
     double t = dmul(dmul(a.dt, electric), a.c.Z);  // :336
-    t = a.c.pow2 ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);
+    t = F::pow2(a.c.pow2) ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);
     vo = dadd(vb, t);
   }
 }
@@ -265,8 +305,9 @@ __device__ __forceinline__ void dep_flush(double *smem_after_E, int nx, double *
 // through 128-bit loads/stores.  IRK2 selects the second RK substep (reads midpoint + start-of-step state).
 // FUSED=false gives the reference's push-only side effects (x left unwrapped, no deposit).
 // ------------------------------------------------------------------------------------------------------------
-template <int DIST, bool IRK2, int DEP, bool FUSED>
-__global__ void __launch_bounds__(512) k_push(const ParticleArgs a) {
+template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
+__global__ void __launch_bounds__(1024, 1) k_push(const ParticleArgs a) {
+  typedef Cfg<CFG> F;
   extern __shared__ __align__(16) double smem[];
   double *sE = smem;
   for (int j = threadIdx.x; j < a.nx; j += blockDim.x) sE[j] = a.E[j];
@@ -275,8 +316,9 @@ __global__ void __launch_bounds__(512) k_push(const ParticleArgs a) {
   dep.g = FUSED ? dep_setup<DEP>(smem + a.nx, a.nx, my_partial) : nullptr;
   __syncthreads();
 
+  const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
   const int64_t tile = (int64_t)blockDim.x * 2;
-  const bool need_p = a.deltaf || FUSED;  // full-f deposits p (src/pic1dp_interaction.F90:88-90)
+  const bool need_p = deltaf || FUSED;  // full-f deposits p (src/pic1dp_interaction.F90:88-90)
   unsigned long long noob = 0;
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
@@ -286,54 +328,54 @@ __global__ void __launch_bounds__(512) k_push(const ParticleArgs a) {
     if (v1ok) {
       x = ld2(a.x_cur + i);
       v = ld2(a.v_cur + i);
-      if (a.deltaf) w = ld2(a.w_cur + i);
+      if (deltaf) w = ld2(a.w_cur + i);
       if (need_p) p = ld2(a.p + i);
       if (IRK2) {
         xb = ld2(a.x_bak + i);
         vb = ld2(a.v_bak + i);
-        if (a.deltaf) wb = ld2(a.w_bak + i);
+        if (deltaf) wb = ld2(a.w_bak + i);
       }
     } else if (v0ok) {
       x.x = ld1(a.x_cur + i);
       v.x = ld1(a.v_cur + i);
-      if (a.deltaf) w.x = ld1(a.w_cur + i);
+      if (deltaf) w.x = ld1(a.w_cur + i);
       if (need_p) p.x = ld1(a.p + i);
       if (IRK2) {
         xb.x = ld1(a.x_bak + i);
         vb.x = ld1(a.v_bak + i);
-        if (a.deltaf) wb.x = ld1(a.w_bak + i);
+        if (deltaf) wb.x = ld1(a.w_bak + i);
       }
     }
     if (!IRK2) {
       xb = x;
       vb = v;
       wb = w;
-    } else if (!a.deltaf) {
+    } else if (!deltaf) {
       wb = w;
     }
     double2 xo = {0.0, 0.0}, vo = {0.0, 0.0}, wo = {0.0, 0.0};
-    if (v0ok) push_one<DIST>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
-    if (v1ok) push_one<DIST>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
+    if (v0ok) push_one<DIST, CFG>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
+    if (v1ok) push_one<DIST, CFG>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
     if (FUSED) {
       if (v0ok) xo.x = wrap_x(xo.x, a.lx);
       if (v1ok) xo.y = wrap_x(xo.y, a.lx);
     }
     if (v1ok) {
       st2(a.x_out + i, xo);
-      if (!a.linear) st2(a.v_out + i, vo);
-      if (a.deltaf) st2(a.w_out + i, wo);
+      if (!linear) st2(a.v_out + i, vo);
+      if (deltaf) st2(a.w_out + i, wo);
     } else if (v0ok) {
       st1(a.x_out + i, xo.x);
-      if (!a.linear) st1(a.v_out + i, vo.x);
-      if (a.deltaf) st1(a.w_out + i, wo.x);
+      if (!linear) st1(a.v_out + i, vo.x);
+      if (deltaf) st1(a.w_out + i, wo.x);
     }
     if (FUSED) {
       // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
-      const double q0 = a.deltaf ? wo.x : p.x, q1 = a.deltaf ? wo.y : p.y;
+      const double q0 = deltaf ? wo.x : p.x, q1 = deltaf ? wo.y : p.y;
       bool o0 = false, o1 = false;
-      const Shape s0 = shape_of(xo.x, a.lx, a.rnx, a.nx, a.right_frac, o0);
+      const Shape s0 = shape_of(xo.x, a.lx, a.rnx, a.nx, right_frac, o0);
       dep.add(s0.ix, s0.ixr, dmul(s0.sl, q0), dmul(s0.sr, q0), v0ok);  // :110, :113
-      const Shape s1 = shape_of(xo.y, a.lx, a.rnx, a.nx, a.right_frac, o1);
+      const Shape s1 = shape_of(xo.y, a.lx, a.rnx, a.nx, right_frac, o1);
       dep.add(s1.ix, s1.ixr, dmul(s1.sl, q1), dmul(s1.sr, q1), v1ok);
       noob += (v0ok && o0) + (v1ok && o1);
     }
@@ -348,7 +390,7 @@ __global__ void __launch_bounds__(512) k_push(const ParticleArgs a) {
 // DEPOSIT=false: wrap only (compute_shape_x for iptclshape 1-3).
 // ------------------------------------------------------------------------------------------------------------
 template <int DEP, bool DEPOSIT>
-__global__ void __launch_bounds__(512) k_deposit(const ParticleArgs a) {
+__global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
   extern __shared__ __align__(16) double smem[];
   double *my_partial = DEPOSIT ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
   Depositor<DEP> dep;

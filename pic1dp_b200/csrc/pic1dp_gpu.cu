@@ -90,7 +90,7 @@ struct pic1dp_gpu {
   double *d_partial = nullptr, *d_red = nullptr, *d_energy = nullptr;
   unsigned long long *d_noob = nullptr;
   std::vector<double> h_Fre, h_Fim, h_ginv;
-  int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0;
+  int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0, cfg = -1;
   bool partial_valid = false;  // a fused push has already deposited into d_partial
   int nred = 1;
   ncclComm_t comm = nullptr;
@@ -164,25 +164,32 @@ static void species_const(const pic1dp_params &p, int s, SpeciesConst &c) {
 // ---- kernel dispatch tables -----------------------------------------------------------------------------
 typedef void (*PushKernel)(const ParticleArgs);
 
-template <int DIST, bool IRK2, bool FUSED>
+// cfg: -1 generic (switches read at run time), 1 = delta-f nonlinear shape 3/4, 9 = same with power-of-two divisors
+template <int DIST, bool IRK2, int CFG>
 static PushKernel pick_dep(int dep) {
   switch (dep) {
-    case DEP_SMEM_ATOMIC: return k_push<DIST, IRK2, DEP_SMEM_ATOMIC, FUSED>;
-    case DEP_GLOBAL_RED: return k_push<DIST, IRK2, DEP_GLOBAL_RED, FUSED>;
-    default: return k_push<DIST, IRK2, DEP_WARP_PRIVATE, FUSED>;
+    case DEP_SMEM_ATOMIC: return k_push<DIST, IRK2, DEP_SMEM_ATOMIC, true, CFG>;
+    case DEP_GLOBAL_RED: return k_push<DIST, IRK2, DEP_GLOBAL_RED, true, CFG>;
+    default: return k_push<DIST, IRK2, DEP_WARP_PRIVATE, true, CFG>;
   }
 }
-template <int DIST>
-static PushKernel pick_irk(int dep, bool irk2, bool fused) {
-  if (!fused) return irk2 ? k_push<DIST, true, DEP_SMEM_ATOMIC, false> : k_push<DIST, false, DEP_SMEM_ATOMIC, false>;
-  return irk2 ? pick_dep<DIST, true, true>(dep) : pick_dep<DIST, false, true>(dep);
+template <int DIST, bool IRK2>
+static PushKernel pick_cfg(int dep, bool fused, int cfg) {
+  if (!fused) return k_push<DIST, IRK2, DEP_SMEM_ATOMIC, false, -1>;
+  if (cfg == 1) return pick_dep<DIST, IRK2, 1>(dep);
+  if (cfg == 9) return pick_dep<DIST, IRK2, 9>(dep);
+  return pick_dep<DIST, IRK2, -1>(dep);
 }
-static PushKernel pick_push(int dist, int dep, bool irk2, bool fused) {
+template <int DIST>
+static PushKernel pick_irk(int dep, bool irk2, bool fused, int cfg) {
+  return irk2 ? pick_cfg<DIST, true>(dep, fused, cfg) : pick_cfg<DIST, false>(dep, fused, cfg);
+}
+static PushKernel pick_push(int dist, int dep, bool irk2, bool fused, int cfg) {
   switch (dist) {
-    case 1: return pick_irk<1>(dep, irk2, fused);
-    case 2: return pick_irk<2>(dep, irk2, fused);
-    case 3: return pick_irk<3>(dep, irk2, fused);
-    default: return pick_irk<0>(dep, irk2, fused);
+    case 1: return pick_irk<1>(dep, irk2, fused, cfg);
+    case 2: return pick_irk<2>(dep, irk2, fused, cfg);
+    case 3: return pick_irk<3>(dep, irk2, fused, cfg);
+    default: return pick_irk<0>(dep, irk2, fused, cfg);
   }
 }
 static PushKernel pick_deposit(int dep, bool deposit) {
@@ -322,42 +329,49 @@ static int create_impl(pic1dp_gpu_t *h) {
   const int nx = p.nx, M = p.nmode;
   const size_t max_smem = prop.sharedMemPerBlockOptin;
   // ---- deposit strategy and launch geometry ----
-  h->threads = 512;
+  // Kernels are compiled for <= 64 registers (launch bound 1024 threads), so an SM holds up to 1024 threads =
+  // 32 warps.  Shared/global-atomic deposits run 2 CTAs x 512 threads; the warp-private deposit needs one grid
+  // per warp in shared memory, so its CTA is as large as fits (multiple of 4 warps, <= 32).
   int dep = p.deposit_mode;
   auto smem_need = [&](int d, int thr) { return (size_t)nx * 8 * (1 + dep_grids(d, thr)); };
+  auto warp_private_threads = [&]() {
+    int w = (int)(max_smem / ((size_t)nx * 8)) - 1;
+    if (w > 32) w = 32;
+    if (w >= 4) w &= ~3;
+    return w * 32;
+  };
   if (dep == PIC1DP_DEPOSIT_AUTO) {
-    if (smem_need(DEP_WARP_PRIVATE, 512) <= max_smem)
+    if (warp_private_threads() >= 512)
       dep = DEP_WARP_PRIVATE;
     else if (smem_need(DEP_SMEM_ATOMIC, 512) <= max_smem)
       dep = DEP_SMEM_ATOMIC;
     else
       dep = DEP_GLOBAL_RED;
   }
-  if (dep == DEP_WARP_PRIVATE && smem_need(dep, h->threads) > max_smem) {
-    // fewer warps per CTA so that one private grid per warp still fits
-    while (h->threads > 64 && smem_need(dep, h->threads) > max_smem) h->threads /= 2;
-  }
-  if (smem_need(dep, h->threads) > max_smem) {
+  h->threads = (dep == DEP_WARP_PRIVATE) ? warp_private_threads() : 512;
+  if (h->threads < 32 || smem_need(dep, h->threads) > max_smem) {
     h->err = "shared-memory grid does not fit for this nx with the requested deposit_mode";
     return PIC1DP_EUNSUPPORTED;
   }
   h->dep = dep;
   h->smem_push = (int)smem_need(dep, h->threads);
   h->smem_dep = (int)((size_t)nx * 8 * dep_grids(dep, h->threads));
+  h->cfg = (p.deltaf == 1 && p.linear == 0 && p.iptclshape >= 3) ? 1 : -1;
   {
-    // occupancy: as many CTAs per SM as registers / smem allow, persistent grid = SMs x that
-    PushKernel kmax = pick_push(p.iptcldist, dep, true, true);
-    CK(cudaFuncSetAttribute(kmax, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_push));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmax, h->threads, h->smem_push));
-    if (per_sm < 1) per_sm = 1;
-    h->grid = h->nsm * per_sm;
+    int per_sm_min = 1 << 30;
+    const int cfgs[3] = {-1, 1, 9};
+    for (int irk2 = 0; irk2 < 2; irk2++)
+      for (int fused = 0; fused < 2; fused++)
+        for (int ci = 0; ci < 3; ci++) {
+          PushKernel k = pick_push(p.iptcldist, dep, irk2 == 1, fused == 1, cfgs[ci]);
+          CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_push));
+          int per_sm = 0;
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, h->threads, h->smem_push));
+          if (fused && per_sm < per_sm_min) per_sm_min = per_sm;
+        }
+    if (per_sm_min < 1) per_sm_min = 1;
+    h->grid = h->nsm * per_sm_min;  // persistent grid: every CTA resident, private grid per CTA
   }
-  for (int dist_irk = 0; dist_irk < 2; dist_irk++)
-    for (int fused = 0; fused < 2; fused++) {
-      PushKernel k = pick_push(p.iptcldist, dep, dist_irk == 1, fused == 1);
-      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_push));
-    }
   CK(cudaFuncSetAttribute(pick_deposit(dep, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           h->smem_dep > 0 ? h->smem_dep : 8));
   CK(cudaFuncSetAttribute(k_field_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
@@ -664,7 +678,6 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
   CK(cudaSetDevice(h->p.device));
   const pic1dp_params &p = h->p;
   const bool fused = p.fuse != 0;
-  PushKernel k = pick_push(p.iptcldist, h->dep, irk == 2, fused);
   if (fused && h->partial_valid && h->dep == DEP_GLOBAL_RED)  // a previous fused deposit was never collected
     CK(cudaMemsetAsync(h->d_partial, 0, (size_t)p.nspecies * h->grid * p.nx * 8, h->stream));
   for (int s = 0; s < p.nspecies; s++) {
@@ -689,6 +702,8 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
     a.x_out = S.x[out];
     a.v_out = S.v[out];
     a.w_out = S.w[out];
+    const int cfg = (h->cfg == 1) ? (S.c.pow2 ? 9 : 1) : -1;
+    PushKernel k = pick_push(p.iptcldist, h->dep, irk == 2, fused, cfg);
     k<<<h->grid, h->threads, h->smem_push, h->stream>>>(a);
     CKL(h);
     S.cur = out;
