@@ -340,9 +340,9 @@ static int create_impl(pic1dp_gpu_t *h) {
     if (w >= 4) w &= ~3;
     return w * 32;
   };
-  if (dep == PIC1DP_DEPOSIT_AUTO) {
-    if (warp_private_threads() >= 512)
-      dep = DEP_WARP_PRIVATE;
+  if (dep == PIC1DP_DEPOSIT_AUTO) {  // fastest that fits; WARP_PRIVATE is the opt-in bitwise-deterministic mode
+    if (2 * smem_need(DEP_SMEM_ATOMIC, 512) + 2048 <= (size_t)prop.sharedMemPerMultiprocessor)
+      dep = DEP_SMEM_ATOMIC;
     else if (smem_need(DEP_SMEM_ATOMIC, 512) <= max_smem)
       dep = DEP_SMEM_ATOMIC;
     else
