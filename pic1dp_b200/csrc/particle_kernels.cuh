@@ -34,10 +34,9 @@ __constant__ double c_exp_red[3] = {0x1.71547652b82fep+0 /* log2 e */, 0x1.62e42
                                     0x1.abc9e3b39803fp-56 /* ln2 lo */};
 
 __device__ __forceinline__ double exp_fast(double a) {
-  if (!(fabs(a) <= 700.0)) return exp(a);
   const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
   const double t = fma(a, c_exp_red[0], magic);
-  const int n = __double2loint(t);
+  int n = __double2loint(t);
   const double nf = t - magic;
   double r = fma(nf, -c_exp_red[1], a);
   r = fma(nf, -c_exp_red[2], r);
@@ -45,8 +44,61 @@ __device__ __forceinline__ double exp_fast(double a) {
 #pragma unroll
   for (int k = 1; k < 10; k++) q = fma(q, r, c_exp_poly[k]);
   const double r2 = r * r;
-  const double pr = fma(r2, q, r) + 1.0;  // in [0.70, 1.42]
+  double pr = fma(r2, q, r) + 1.0;  // in [0.70, 1.42]
+  if (!(fabs(a) <= 700.0)) {  // never reached by physical velocities; handled inline (no call in the hot loop)
+    if (a != a) return a;
+    if (a > 709.782712893384) return __longlong_as_double(0x7ff0000000000000LL);
+    if (a < -745.2) return 0.0;
+    const int n1 = n / 2;  // scale in two exact steps so that subnormal results round once
+    pr = pr * __hiloint2double((1023 + n1) << 20, 0);
+    n -= n1;
+    return pr * __hiloint2double((1023 + n) << 20, 0);
+  }
   return __hiloint2double(__double2hiint(pr) + (n << 20), __double2loint(pr));  // * 2^n, |n| <= 1010
+}
+
+// ---- correctly rounded division without a slow-path call ---------------------------------------------------
+// q0 = a*y, r = a - q0*b (exact, FMA), q1 = q0 + r*y is RN(a/b + d) with |d| <= 2^-104 |a/b| when y is 1/b to
+// ~1 ulp, so q1 can only be wrong when a/b lies within 2^-104 of a rounding midpoint.  The exact residual
+// r1 = a - q1*b settles it: RN(a/b) != q1 iff |r1| > b * ulp(q1) / 2, and then the neighbour towards r1 is the
+// answer.  (Not covered: q1 an exact power of two AND a/b that close to the midpoint just below it.)
+// Valid for b > 0 and |a|, b, |a/b| within 2^+-500; callers route anything else to the generic path.
+__device__ __forceinline__ double div_fix(double a, double b, double q1) {
+  const double r1 = fma(-q1, b, a);
+  const int e = __double2hiint(q1) & 0x7ff00000;
+  const double h = __hiloint2double(__double2hiint(b) + e - (1076 << 20), __double2loint(b));  // b * ulp(q1) / 2
+  if (__builtin_expect(fabs(r1) > h, 0)) {
+    // a/b = q1 + r1/b with b > 0: one ulp towards the residual = +-1 on the bit pattern
+    const long long step = ((r1 < 0.0) != (q1 < 0.0)) ? -1LL : 1LL;
+    q1 = __longlong_as_double(__double_as_longlong(q1) + step);
+  }
+  return q1;
+}
+
+// a / b for a constant divisor b > 0 with y = RN(1/b) precomputed on the host; a >= 0 (a marker coordinate).
+// a == 0, a < 2^-800 (residuals would underflow) and a < 0 take the generic division.
+__device__ __forceinline__ double div_const(double a, double b, double y) {
+  if (__builtin_expect(!(a >= 0x1p-800), 0)) return __ddiv_rn(a, b);
+  const double q0 = a * y;
+  const double r = fma(-q0, b, a);
+  return div_fix(a, b, fma(r, y, q0));
+}
+
+// general a / b, b > 0
+__device__ __forceinline__ double div_pos(double a, double b) {
+  const unsigned eb = (unsigned)(__double2hiint(b) & 0x7ff00000) - (523u << 20);  // exponent of b in [-500, 500)
+  const unsigned ea = (unsigned)(__double2hiint(a) & 0x7ff00000) - (523u << 20);
+  if (__builtin_expect(eb >= (1000u << 20) || ea >= (1000u << 20) || !(b > 0.0), 0)) return __ddiv_rn(a, b);
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));  // MUFU.RCP64H: ~20 good bits
+  double e = fma(-b, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+  e = fma(-b, y, 1.0);
+  y = fma(y, e, y);
+  const double q0 = a * y;
+  const double r = fma(-q0, b, a);
+  return div_fix(a, b, fma(r, y, q0));
 }
 
 // Compile-time configuration of the model switches.  CFG < 0: read them from the kernel arguments (generic
@@ -57,6 +109,8 @@ template <int CFG> struct Cfg {
   static __device__ __forceinline__ bool linear(const int a) { return CFG < 0 ? a != 0 : (CFG & 2) != 0; }
   static __device__ __forceinline__ bool right_frac(const int a) { return CFG < 0 ? a != 0 : (CFG & 4) != 0; }
   static __device__ __forceinline__ bool pow2(const int a) { return CFG < 0 ? a != 0 : (CFG & 8) != 0; }
+  // bit 4 (with bit 3): T/m = T2/m = m = T = 1, so x / c == x for those divisors and only 2T/m = 2 remains
+  static constexpr bool unit = CFG >= 0 && (CFG & 16) != 0;
 };
 
 // Per-species constants, all evaluated on the host in IEEE double exactly as the Fortran compiler folds them.
@@ -68,7 +122,8 @@ struct SpeciesConst {
   double sqTm, sqT2m;       // sqrt(T/m), sqrt(T2/m)
   // exact reciprocals, used only when every divisor above is a power of two (x/c == x*(1/c) bit for bit)
   double i_m, i_T, i_Tm, i_T2m, i_twoTm, i_twoT2m, i_sqTm, i_sqT2m;
-  int pow2;
+  int pow2;  // every divisor above is a power of two
+  int unit;  // m = T = T/m = T2/m = 1 (so 2T/m = 2T2/m = 2)
 };
 
 struct ParticleArgs {
@@ -84,7 +139,7 @@ struct ParticleArgs {
   unsigned long long *noob;
   int64_t np;
   int nx;
-  double lx, rnx, dt;      // dt is already halved at irk == 1 (src/pic1dp_interaction.F90:179)
+  double lx, rlx, rnx, dt; // rlx = RN(1/lx); dt is already halved at irk == 1 (src/pic1dp_interaction.F90:179)
   SpeciesConst c;
   int deltaf, linear, right_frac;
 };
@@ -92,12 +147,13 @@ struct ParticleArgs {
 // ---- periodic wrap: px = mod(px, lx); if (px < 0) px = px + lx  (src/pic1dp_interaction.F90:102-104) ----
 // fmod is exact; for lx <= x < 2 lx it equals x - lx (exact by Sterbenz), for -lx < x < 0 it returns x.
 __device__ __forceinline__ double wrap_x(double x, double lx) {
-  if (x >= 0.0 && x < lx) return x;
-  if (x >= lx && x < dadd(lx, lx)) return dsub(x, lx);
-  if (x < 0.0 && x > -lx) return dadd(x, lx);
-  double r = fmod(x, lx);
-  if (r < 0.0) r = dadd(r, lx);
-  return r;
+  double xw = (x >= lx) ? dsub(x, lx) : x;
+  xw = (x < 0.0) ? dadd(x, lx) : xw;
+  if (!(x > -lx && x < dadd(lx, lx))) {  // more than one box length away (or NaN): the general definition
+    xw = fmod(x, lx);
+    if (xw < 0.0) xw = dadd(xw, lx);
+  }
+  return xw;
 }
 
 struct Shape {
@@ -107,9 +163,11 @@ struct Shape {
 
 // ---- weights: sx = x/lx*nx; ix = floor(sx); s = 1-(sx-ix)  (src/pic1dp_interaction.F90:106-108, :250-252;
 // matrix modes src/pic1dp_particle.F90:312-323 use `frac` as the right weight) ----
-__device__ __forceinline__ Shape shape_of(double x, double lx, double rnx, int nx, int right_frac, bool &oob) {
+__device__ __forceinline__ Shape shape_of(double x, double lx, double rlx, double rnx, int nx, int right_frac,
+                                          bool &oob) {
   Shape s;
-  const double sx = dmul(ddiv(x, lx), rnx);
+  // x >= 0 here (wrapped); anything else takes div_const's generic path and is caught by the range check below
+  const double sx = dmul(div_const(x, lx, rlx), rnx);
   int ix = __double2int_rd(sx);
   double frac = dsub(sx, (double)ix);
   double sl = dsub(1.0, frac);
@@ -128,10 +186,16 @@ __device__ __forceinline__ Shape shape_of(double x, double lx, double rnx, int n
   return s;
 }
 
+// which constant divisors equal 2 (rather than 1) in the UNIT specialisation
+struct DivIsTwo {
+  static constexpr bool m = false, T = false, Tm = false, T2m = false, sqTm = false, sqT2m = false;
+  static constexpr bool twoTm = true, twoT2m = true;
+};
+
 // ---- -d f0/dv / f0  (src/pic1dp_interaction.F90:275-326) ----
-template <int DIST, bool POW2>
+template <int DIST, bool POW2, bool UNIT>
 __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
-#define DIVC(x, name) (POW2 ? dmul((x), c.i_##name) : ddiv((x), c.name))
+#define DIVC(x, name) (UNIT && !DivIsTwo::name ? (x) : UNIT ? dmul((x), 0.5) : POW2 ? dmul((x), c.i_##name) : ddiv((x), c.name))
   if (DIST == 1) {  // two-stream1 :276
     return dsub(v, ddiv(2.0, v));
   } else if (DIST == 2) {  // two-stream2 :278-292
@@ -140,8 +204,8 @@ __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
     const double em = exp_fast(-DIVC(dmul(vm, vm), twoTm));
     const double num = dadd(dmul(vp, ep), dmul(vm, em));
     const double den = dadd(ep, em);
-    double r = ddiv(num, den);
-    r = dmul(r, c.m);
+    double r = div_pos(num, den);
+    if (!UNIT) r = dmul(r, c.m);
     return DIVC(r, T);
   } else if (DIST == 3) {  // bump-on-tail :294-321
     const double vm = dsub(v, c.v0);
@@ -151,7 +215,7 @@ __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
     const double b = DIVC(dmul(DIVC(dmul(c.omn, vm), T2m), e2), sqT2m);
     const double num = dadd(a, b);
     const double den = dadd(DIVC(dmul(c.n, e1), sqTm), DIVC(dmul(c.omn, e2), sqT2m));
-    return ddiv(num, den);
+    return div_pos(num, den);
   } else {  // (shifted) Maxwellian :323-325
     return DIVC(dsub(v, c.v0), Tm);
   }
@@ -160,7 +224,8 @@ __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
 
 template <int DIST, int CFG>
 __device__ __forceinline__ double dlnf0(const SpeciesConst &c, double v) {
-  return Cfg<CFG>::pow2(c.pow2) ? dlnf0_impl<DIST, true>(c, v) : dlnf0_impl<DIST, false>(c, v);
+  if (Cfg<CFG>::unit) return dlnf0_impl<DIST, true, true>(c, v);
+  return Cfg<CFG>::pow2(c.pow2) ? dlnf0_impl<DIST, true, false>(c, v) : dlnf0_impl<DIST, false, false>(c, v);
 }
 
 // ---- gather + push of one marker (src/pic1dp_interaction.F90:250-338) ----
@@ -170,7 +235,7 @@ __device__ __forceinline__ void push_one(const ParticleArgs &a, const double *sE
                                          double &wo) {
   typedef Cfg<CFG> F;
   bool oob = false;  // x == lx exactly was already counted by the deposit that produced this x
-  const Shape s = shape_of(x, a.lx, a.rnx, a.nx, F::right_frac(a.right_frac), oob);
+  const Shape s = shape_of(x, a.lx, a.rlx, a.rnx, a.nx, F::right_frac(a.right_frac), oob);
   const double electric = dadd(dmul(sE[s.ix], s.sl), dmul(sE[s.ixr], s.sr));  // :254-257
   xo = dadd(xb, dmul(a.dt, v));                                              // :261
   wo = w;
@@ -178,13 +243,13 @@ __device__ __forceinline__ void push_one(const ParticleArgs &a, const double *sE
     const double tmp1 = F::linear(a.linear) ? dmul(p, electric) : dmul(dsub(p, w), electric);  // :268-272
     const double tmp2 = dlnf0<DIST, CFG>(a.c, v);
     double t = dmul(dmul(dmul(a.dt, tmp1), tmp2), a.c.Z);              // :329
-    t = F::pow2(a.c.pow2) ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);          // :330
+    if (!F::unit) t = F::pow2(a.c.pow2) ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);  // :330
     wo = dadd(wb, t);
   }
   vo = v;
   if (!F::linear(a.linear)) {
     double t = dmul(dmul(a.dt, electric), a.c.Z);  // :336
-    t = F::pow2(a.c.pow2) ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);
+    if (!F::unit) t = F::pow2(a.c.pow2) ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);
     vo = dadd(vb, t);
   }
 }
@@ -305,9 +370,74 @@ __device__ __forceinline__ void dep_flush(double *smem_after_E, int nx, double *
 // through 128-bit loads/stores.  IRK2 selects the second RK substep (reads midpoint + start-of-step state).
 // FUSED=false gives the reference's push-only side effects (x left unwrapped, no deposit).
 // ------------------------------------------------------------------------------------------------------------
+// one tile step of one thread: markers i, i+1.  FULL: the whole CTA tile is inside [0, np) (no tail checks).
+template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG, bool FULL>
+__device__ __forceinline__ void push_pair(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep, const int64_t i,
+                                          unsigned long long &noob) {
+  typedef Cfg<CFG> F;
+  const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
+  const bool need_p = deltaf || FUSED;  // full-f deposits p (src/pic1dp_interaction.F90:88-90)
+  const bool v0ok = FULL || i < a.np, v1ok = FULL || i + 1 < a.np;
+  double2 x = {0.0, 0.0}, v = {0.0, 0.0}, w = {0.0, 0.0}, p = {0.0, 0.0};
+  double2 xb = {0.0, 0.0}, vb = {0.0, 0.0}, wb = {0.0, 0.0};
+  if (v1ok) {
+    x = ld2(a.x_cur + i);
+    v = ld2(a.v_cur + i);
+    if (deltaf) w = ld2(a.w_cur + i);
+    if (need_p) p = ld2(a.p + i);
+    if (IRK2) {
+      xb = ld2(a.x_bak + i);
+      vb = ld2(a.v_bak + i);
+      if (deltaf) wb = ld2(a.w_bak + i);
+    }
+  } else if (v0ok) {
+    x.x = ld1(a.x_cur + i);
+    v.x = ld1(a.v_cur + i);
+    if (deltaf) w.x = ld1(a.w_cur + i);
+    if (need_p) p.x = ld1(a.p + i);
+    if (IRK2) {
+      xb.x = ld1(a.x_bak + i);
+      vb.x = ld1(a.v_bak + i);
+      if (deltaf) wb.x = ld1(a.w_bak + i);
+    }
+  }
+  if (!IRK2) {
+    xb = x;
+    vb = v;
+    wb = w;
+  } else if (!deltaf) {
+    wb = w;
+  }
+  double2 xo = {0.0, 0.0}, vo = {0.0, 0.0}, wo = {0.0, 0.0};
+  if (v0ok) push_one<DIST, CFG>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
+  if (v1ok) push_one<DIST, CFG>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
+  if (FUSED) {
+    if (v0ok) xo.x = wrap_x(xo.x, a.lx);
+    if (v1ok) xo.y = wrap_x(xo.y, a.lx);
+  }
+  if (v1ok) {
+    st2(a.x_out + i, xo);
+    if (!linear) st2(a.v_out + i, vo);
+    if (deltaf) st2(a.w_out + i, wo);
+  } else if (v0ok) {
+    st1(a.x_out + i, xo.x);
+    if (!linear) st1(a.v_out + i, vo.x);
+    if (deltaf) st1(a.w_out + i, wo.x);
+  }
+  if (FUSED) {
+    // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
+    const double q0 = deltaf ? wo.x : p.x, q1 = deltaf ? wo.y : p.y;
+    bool o0 = false, o1 = false;
+    const Shape s0 = shape_of(xo.x, a.lx, a.rlx, a.rnx, a.nx, right_frac, o0);
+    dep.add(s0.ix, s0.ixr, dmul(s0.sl, q0), dmul(s0.sr, q0), v0ok);  // :110, :113
+    const Shape s1 = shape_of(xo.y, a.lx, a.rlx, a.rnx, a.nx, right_frac, o1);
+    dep.add(s1.ix, s1.ixr, dmul(s1.sl, q1), dmul(s1.sr, q1), v1ok);
+    noob += (v0ok && o0) + (v1ok && o1);
+  }
+}
+
 template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
 __global__ void __launch_bounds__(1024, 1) k_push(const ParticleArgs a) {
-  typedef Cfg<CFG> F;
   extern __shared__ __align__(16) double smem[];
   double *sE = smem;
   for (int j = threadIdx.x; j < a.nx; j += blockDim.x) sE[j] = a.E[j];
@@ -316,69 +446,14 @@ __global__ void __launch_bounds__(1024, 1) k_push(const ParticleArgs a) {
   dep.g = FUSED ? dep_setup<DEP>(smem + a.nx, a.nx, my_partial) : nullptr;
   __syncthreads();
 
-  const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
   const int64_t tile = (int64_t)blockDim.x * 2;
-  const bool need_p = deltaf || FUSED;  // full-f deposits p (src/pic1dp_interaction.F90:88-90)
   unsigned long long noob = 0;
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
-    const bool v0ok = i < a.np, v1ok = i + 1 < a.np;
-    double2 x = {0.0, 0.0}, v = {0.0, 0.0}, w = {0.0, 0.0}, p = {0.0, 0.0};
-    double2 xb = {0.0, 0.0}, vb = {0.0, 0.0}, wb = {0.0, 0.0};
-    if (v1ok) {
-      x = ld2(a.x_cur + i);
-      v = ld2(a.v_cur + i);
-      if (deltaf) w = ld2(a.w_cur + i);
-      if (need_p) p = ld2(a.p + i);
-      if (IRK2) {
-        xb = ld2(a.x_bak + i);
-        vb = ld2(a.v_bak + i);
-        if (deltaf) wb = ld2(a.w_bak + i);
-      }
-    } else if (v0ok) {
-      x.x = ld1(a.x_cur + i);
-      v.x = ld1(a.v_cur + i);
-      if (deltaf) w.x = ld1(a.w_cur + i);
-      if (need_p) p.x = ld1(a.p + i);
-      if (IRK2) {
-        xb.x = ld1(a.x_bak + i);
-        vb.x = ld1(a.v_bak + i);
-        if (deltaf) wb.x = ld1(a.w_bak + i);
-      }
-    }
-    if (!IRK2) {
-      xb = x;
-      vb = v;
-      wb = w;
-    } else if (!deltaf) {
-      wb = w;
-    }
-    double2 xo = {0.0, 0.0}, vo = {0.0, 0.0}, wo = {0.0, 0.0};
-    if (v0ok) push_one<DIST, CFG>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
-    if (v1ok) push_one<DIST, CFG>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
-    if (FUSED) {
-      if (v0ok) xo.x = wrap_x(xo.x, a.lx);
-      if (v1ok) xo.y = wrap_x(xo.y, a.lx);
-    }
-    if (v1ok) {
-      st2(a.x_out + i, xo);
-      if (!linear) st2(a.v_out + i, vo);
-      if (deltaf) st2(a.w_out + i, wo);
-    } else if (v0ok) {
-      st1(a.x_out + i, xo.x);
-      if (!linear) st1(a.v_out + i, vo.x);
-      if (deltaf) st1(a.w_out + i, wo.x);
-    }
-    if (FUSED) {
-      // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
-      const double q0 = deltaf ? wo.x : p.x, q1 = deltaf ? wo.y : p.y;
-      bool o0 = false, o1 = false;
-      const Shape s0 = shape_of(xo.x, a.lx, a.rnx, a.nx, right_frac, o0);
-      dep.add(s0.ix, s0.ixr, dmul(s0.sl, q0), dmul(s0.sr, q0), v0ok);  // :110, :113
-      const Shape s1 = shape_of(xo.y, a.lx, a.rnx, a.nx, right_frac, o1);
-      dep.add(s1.ix, s1.ixr, dmul(s1.sl, q1), dmul(s1.sr, q1), v1ok);
-      noob += (v0ok && o0) + (v1ok && o1);
-    }
+    if (base + tile <= a.np)
+      push_pair<DIST, IRK2, DEP, FUSED, CFG, true>(a, sE, dep, i, noob);
+    else
+      push_pair<DIST, IRK2, DEP, FUSED, CFG, false>(a, sE, dep, i, noob);
   }
   if (FUSED) dep_flush<DEP>(smem + a.nx, a.nx, my_partial);
   if (FUSED && noob) atomicAdd(a.noob, noob);
@@ -418,9 +493,9 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
     }
     if (DEPOSIT) {
       bool o0 = false, o1 = false;
-      const Shape s0 = shape_of(xw.x, a.lx, a.rnx, a.nx, a.right_frac, o0);
+      const Shape s0 = shape_of(xw.x, a.lx, a.rlx, a.rnx, a.nx, a.right_frac, o0);
       dep.add(s0.ix, s0.ixr, dmul(s0.sl, q.x), dmul(s0.sr, q.x), v0ok);
-      const Shape s1 = shape_of(xw.y, a.lx, a.rnx, a.nx, a.right_frac, o1);
+      const Shape s1 = shape_of(xw.y, a.lx, a.rlx, a.rnx, a.nx, a.right_frac, o1);
       dep.add(s1.ix, s1.ixr, dmul(s1.sl, q.y), dmul(s1.sr, q.y), v1ok);
       noob += (v0ok && o0) + (v1ok && o1);
     }
@@ -434,7 +509,7 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
 __global__ void __launch_bounds__(256) k_shape_x(const ParticleArgs a, int *ix, double *sl, double *sr) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.np; i += (int64_t)gridDim.x * blockDim.x) {
     bool oob = false;
-    const Shape s = shape_of(a.x_cur[i], a.lx, a.rnx, a.nx, a.right_frac, oob);
+    const Shape s = shape_of(a.x_cur[i], a.lx, a.rlx, a.rnx, a.nx, a.right_frac, oob);
     ix[i] = s.ix;
     sl[i] = s.sl;
     sr[i] = s.sr;

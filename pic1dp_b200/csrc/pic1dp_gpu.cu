@@ -151,6 +151,8 @@ static void species_const(const pic1dp_params &p, int s, SpeciesConst &c) {
   bool all = true;
   for (double d : divs) all = all && is_pow2(d);
   c.pow2 = all ? 1 : 0;
+  c.unit = (c.m == 1.0 && c.T == 1.0 && c.Tm == 1.0 && c.T2m == 1.0 && c.twoTm == 2.0 && c.twoT2m == 2.0 &&
+            c.sqTm == 1.0 && c.sqT2m == 1.0) ? 1 : 0;
   c.i_m = 1.0 / c.m;
   c.i_T = 1.0 / c.T;
   c.i_Tm = 1.0 / c.Tm;
@@ -164,7 +166,8 @@ static void species_const(const pic1dp_params &p, int s, SpeciesConst &c) {
 // ---- kernel dispatch tables -----------------------------------------------------------------------------
 typedef void (*PushKernel)(const ParticleArgs);
 
-// cfg: -1 generic (switches read at run time), 1 = delta-f nonlinear shape 3/4, 9 = same with power-of-two divisors
+// cfg: -1 generic (switches read at run time), 1 = delta-f nonlinear shape 3/4, 9 = same with power-of-two
+// divisors, 25 = same with T = T2 = m = 1 (the reference default input)
 template <int DIST, bool IRK2, int CFG>
 static PushKernel pick_dep(int dep) {
   switch (dep) {
@@ -178,6 +181,7 @@ static PushKernel pick_cfg(int dep, bool fused, int cfg) {
   if (!fused) return k_push<DIST, IRK2, DEP_SMEM_ATOMIC, false, -1>;
   if (cfg == 1) return pick_dep<DIST, IRK2, 1>(dep);
   if (cfg == 9) return pick_dep<DIST, IRK2, 9>(dep);
+  if (cfg == 25) return pick_dep<DIST, IRK2, 25>(dep);
   return pick_dep<DIST, IRK2, -1>(dep);
 }
 template <int DIST>
@@ -359,10 +363,10 @@ static int create_impl(pic1dp_gpu_t *h) {
   h->cfg = (p.deltaf == 1 && p.linear == 0 && p.iptclshape >= 3) ? 1 : -1;
   {
     int per_sm_min = 1 << 30;
-    const int cfgs[3] = {-1, 1, 9};
+    const int cfgs[4] = {-1, 1, 9, 25};
     for (int irk2 = 0; irk2 < 2; irk2++)
       for (int fused = 0; fused < 2; fused++)
-        for (int ci = 0; ci < 3; ci++) {
+        for (int ci = 0; ci < 4; ci++) {
           PushKernel k = pick_push(p.iptcldist, dep, irk2 == 1, fused == 1, cfgs[ci]);
           CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_push));
           int per_sm = 0;
@@ -551,6 +555,7 @@ static void fill_particle_args(pic1dp_gpu_t *h, int s, ParticleArgs &a) {
   a.np = S.np;
   a.nx = p.nx;
   a.lx = p.lx;
+  a.rlx = 1.0 / p.lx;
   a.rnx = (double)p.nx;
   a.c = S.c;
   a.deltaf = p.deltaf;
@@ -702,7 +707,7 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
     a.x_out = S.x[out];
     a.v_out = S.v[out];
     a.w_out = S.w[out];
-    const int cfg = (h->cfg == 1) ? (S.c.pow2 ? 9 : 1) : -1;
+    const int cfg = (h->cfg == 1) ? (S.c.unit ? 25 : S.c.pow2 ? 9 : 1) : -1;
     PushKernel k = pick_push(p.iptcldist, h->dep, irk == 2, fused, cfg);
     k<<<h->grid, h->threads, h->smem_push, h->stream>>>(a);
     CKL(h);

@@ -245,7 +245,8 @@ def test_warp_private_deposit_is_bitwise_deterministic():
         assert np.array_equal(mk["w"], res[0][1]["w"])
 
 
-@pytest.mark.parametrize("case", ["fullf", "linear", "two_species", "matrix_shape", "multi_mode", "landau_4096"])
+@pytest.mark.parametrize("case", ["fullf", "linear", "two_species", "matrix_shape", "multi_mode", "landau_4096",
+                                  "pow2_nonunit", "nonpow2"])
 def test_model_variants_three_steps(case):
     kw = dict(nx=256, capacity=60000)
     nsp = 1
@@ -261,6 +262,10 @@ def test_model_variants_three_steps(case):
         kw.update(iptclshape=2)
     elif case == "multi_mode":
         kw.update(nmode=3, modes=[1, 2, 3])
+    elif case == "pow2_nonunit":   # every constant divisor a power of two but not 1: exact reciprocal multiplies
+        kw.update(temperature=[2.0], mass=[0.5], temperature2=[0.5])
+    elif case == "nonpow2":        # true divisions by T/m, sqrt(T/m), ...
+        kw.update(temperature=[1.3], mass=[0.9], temperature2=[0.7])
     elif case == "landau_4096":
         kw.update(nx=4096, iptcldist=0, density=[1.0], v0=[0.0], lx=4 * np.pi)
     op, gp = make_params(**kw)
