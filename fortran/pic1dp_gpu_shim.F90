@@ -1,0 +1,329 @@
+! fortran/pic1dp_gpu_shim.F90 -- ISO_C_BINDING side of the drop-in boundary (include/pic1dp_gpu.h).
+!
+! Status: SOURCE ONLY.  No Fortran compiler, MPI or PETSc exists in the build image or on the GPU boxes, so this
+! file has never been compiled; it is the binding a maintainer of PIC1D-PETSc adds (INTEGRATION.md walks through
+! it).  The same call sequence is exercised against the real library from C (host/pic1dp_host.cpp) and from Python
+! (pic1dp_b200/host.py, tests/).
+!
+! How it plugs in: the three hot-path modules keep their public procedure names and argument lists
+! (src/pic1dp_particle.F90:66,145,275,819; src/pic1dp_field.F90:55,218,315; src/pic1dp_interaction.F90:33,161).
+! Their bodies are replaced by the `gpu_*` procedures below, which forward to the C ABI and store the return code
+! in global_ierr followed by CHKERRQ -- the reference's own error convention (src/pic1dp_global.F90:59).
+! Marker Vecs stay allocated on the host (particle_load and pic1dp_output still use them); they are stale
+! between gpu_particle_refresh_host calls, which the driver makes before output_all / particle_optimize.
+module pic1dp_gpu
+use, intrinsic :: iso_c_binding
+implicit none
+private
+
+integer(c_int), parameter, public :: PIC1DP_MAX_SPECIES = 4, PIC1DP_MAX_MODES = 64
+integer(c_int), parameter, public :: PIC1DP_ABI_VERSION = 1
+
+! mirrors struct pic1dp_params (include/pic1dp_gpu.h); field order and types must match exactly
+type, bind(c), public :: pic1dp_params
+  integer(c_int32_t) :: abi_version
+  integer(c_int32_t) :: struct_bytes
+  integer(c_int32_t) :: nx
+  integer(c_int32_t) :: nmode
+  integer(c_int32_t) :: modes(PIC1DP_MAX_MODES)
+  real(c_double) :: lx
+  real(c_double) :: dt
+  integer(c_int32_t) :: nspecies
+  real(c_double) :: charge(PIC1DP_MAX_SPECIES)
+  real(c_double) :: mass(PIC1DP_MAX_SPECIES)
+  real(c_double) :: temperature(PIC1DP_MAX_SPECIES)
+  real(c_double) :: temperature2(PIC1DP_MAX_SPECIES)
+  real(c_double) :: density(PIC1DP_MAX_SPECIES)
+  real(c_double) :: v0(PIC1DP_MAX_SPECIES)
+  integer(c_int32_t) :: iptcldist
+  integer(c_int32_t) :: deltaf
+  integer(c_int32_t) :: linear
+  integer(c_int32_t) :: iptclshape
+  integer(c_int64_t) :: capacity
+  integer(c_int32_t) :: device
+  integer(c_int32_t) :: rank
+  integer(c_int32_t) :: nranks
+  integer(c_int32_t) :: deposit_mode
+  integer(c_int32_t) :: field_mode
+  integer(c_int32_t) :: fuse
+  integer(c_int32_t) :: reserved(8)
+end type pic1dp_params
+
+interface
+  subroutine pic1dp_gpu_params_default(p) bind(c, name = 'pic1dp_gpu_params_default')
+    import :: pic1dp_params
+    type(pic1dp_params), intent(out) :: p
+  end subroutine
+  integer(c_int) function pic1dp_gpu_create(p, handle) bind(c, name = 'pic1dp_gpu_create')
+    import :: pic1dp_params, c_ptr, c_int
+    type(pic1dp_params), intent(in) :: p
+    type(c_ptr), intent(out) :: handle
+  end function
+  integer(c_int) function pic1dp_gpu_destroy(handle) bind(c, name = 'pic1dp_gpu_destroy')
+    import :: c_ptr, c_int
+    type(c_ptr), value :: handle
+  end function
+  integer(c_int) function pic1dp_gpu_comm_unique_id(id) bind(c, name = 'pic1dp_gpu_comm_unique_id')
+    import :: c_int8_t, c_int
+    integer(c_int8_t), intent(out) :: id(128)
+  end function
+  integer(c_int) function pic1dp_gpu_comm_init(handle, id) bind(c, name = 'pic1dp_gpu_comm_init')
+    import :: c_ptr, c_int8_t, c_int
+    type(c_ptr), value :: handle
+    integer(c_int8_t), intent(in) :: id(128)
+  end function
+  integer(c_int) function pic1dp_gpu_set_markers(handle, isp, np, x, v, p, w) bind(c, name = 'pic1dp_gpu_set_markers')
+    import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: isp
+    integer(c_int64_t), value :: np
+    real(c_double), intent(in) :: x(*), v(*), p(*), w(*)
+  end function
+  integer(c_int) function pic1dp_gpu_get_markers(handle, isp, x, v, p, w, np) bind(c, name = 'pic1dp_gpu_get_markers')
+    import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: isp
+    real(c_double), intent(out) :: x(*), v(*), p(*), w(*)
+    integer(c_int64_t), intent(out) :: np
+  end function
+  integer(c_int) function pic1dp_gpu_compute_shape_x(handle) bind(c, name = 'pic1dp_gpu_compute_shape_x')
+    import :: c_ptr, c_int
+    type(c_ptr), value :: handle
+  end function
+  integer(c_int) function pic1dp_gpu_collect_charge(handle) bind(c, name = 'pic1dp_gpu_collect_charge')
+    import :: c_ptr, c_int
+    type(c_ptr), value :: handle
+  end function
+  integer(c_int) function pic1dp_gpu_solve_field(handle) bind(c, name = 'pic1dp_gpu_solve_field')
+    import :: c_ptr, c_int
+    type(c_ptr), value :: handle
+  end function
+  integer(c_int) function pic1dp_gpu_push(handle, irk) bind(c, name = 'pic1dp_gpu_push')
+    import :: c_ptr, c_int, c_int32_t
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: irk
+  end function
+  integer(c_int) function pic1dp_gpu_get_field(handle, electric, chargeden, mode_re, mode_im) &
+      bind(c, name = 'pic1dp_gpu_get_field')
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: handle
+    real(c_double), intent(out) :: electric(*), chargeden(*), mode_re(*), mode_im(*)
+  end function
+  integer(c_int) function pic1dp_gpu_sync(handle) bind(c, name = 'pic1dp_gpu_sync')
+    import :: c_ptr, c_int
+    type(c_ptr), value :: handle
+  end function
+end interface
+
+type(c_ptr), save, public :: gpu_handle = c_null_ptr
+
+public :: pic1dp_gpu_params_default, pic1dp_gpu_create, pic1dp_gpu_destroy
+public :: pic1dp_gpu_comm_unique_id, pic1dp_gpu_comm_init
+public :: pic1dp_gpu_set_markers, pic1dp_gpu_get_markers, pic1dp_gpu_compute_shape_x
+public :: pic1dp_gpu_collect_charge, pic1dp_gpu_solve_field, pic1dp_gpu_push
+public :: pic1dp_gpu_get_field, pic1dp_gpu_sync
+
+end module pic1dp_gpu
+
+
+! ----------------------------------------------------------------------------------------------------------------
+! Replacement bodies.  Each `gpu_*` subroutine below is what the reference procedure of the same role calls (or
+! becomes) when the code is built with -D__PIC1DP_GPU.  They live in one module here for readability; in the
+! reference tree they go into pic1dp_particle / pic1dp_field / pic1dp_interaction (see INTEGRATION.md).
+! ----------------------------------------------------------------------------------------------------------------
+module pic1dp_gpu_glue
+use, intrinsic :: iso_c_binding
+use pic1dp_gpu
+use pic1dp_global   ! global_ierr, global_irk, global_mype, global_npe
+use pic1dp_input    ! input_* parameters
+implicit none
+#include "finclude/petscdef.h"
+
+contains
+
+! particle_init + field_init: after the reference has created its host Vecs (src/pic1dp_particle.F90:89-129,
+! src/pic1dp_field.F90:67-155), create the device-resident state.
+subroutine gpu_init(local_capacity)
+implicit none
+#include "finclude/petsc.h90"
+PetscInt, intent(in) :: local_capacity   ! particle_ip_high - particle_ip_low
+type(pic1dp_params) :: p
+integer(c_int8_t) :: id(128)
+integer :: imode
+
+call pic1dp_gpu_params_default(p)
+p%nx = input_nx
+p%nmode = input_nmode
+do imode = 0, input_nmode - 1
+  p%modes(imode + 1) = input_modes(imode)
+end do
+p%lx = input_lx
+p%dt = input_dt
+p%nspecies = input_nspecies
+p%charge(1 : input_nspecies) = input_species_charge
+p%mass(1 : input_nspecies) = input_species_mass
+p%temperature(1 : input_nspecies) = input_species_temperature
+p%temperature2(1 : input_nspecies) = input_species_temperature2
+p%density(1 : input_nspecies) = input_species_density
+p%v0(1 : input_nspecies) = input_species_v0
+p%iptcldist = input_iptcldist
+p%deltaf = input_deltaf
+p%linear = input_linear
+p%iptclshape = input_iptclshape
+p%capacity = local_capacity
+p%device = mod(global_mype, 8)      ! one MPI rank per GPU of the box
+p%rank = global_mype
+p%nranks = global_npe
+
+global_ierr = pic1dp_gpu_create(p, gpu_handle)
+CHKERRQ(global_ierr)
+
+if (global_npe > 1) then
+  ! replaces MPI_COMM_WORLD for the density all-reduce (src/pic1dp_interaction.F90:132-133)
+  if (global_mype == 0) then
+    global_ierr = pic1dp_gpu_comm_unique_id(id)
+    CHKERRQ(global_ierr)
+  end if
+  call MPI_Bcast(id, 128, MPI_BYTE, 0, MPI_COMM_WORLD, global_ierr)
+  CHKERRQ(global_ierr)
+  global_ierr = pic1dp_gpu_comm_init(gpu_handle, id)
+  CHKERRQ(global_ierr)
+end if
+end subroutine gpu_init
+
+! after particle_load (src/pic1dp_particle.F90:145-269): host Vecs -> device
+subroutine gpu_particle_upload(ispecies, np, vx, vv, vp, vw)
+implicit none
+#include "finclude/petsc.h90"
+PetscInt, intent(in) :: ispecies, np
+Vec, intent(in) :: vx, vv, vp, vw
+PetscScalar, dimension(:), pointer :: px, pv, pp, pw
+
+call VecGetArrayF90(vx, px, global_ierr)
+CHKERRQ(global_ierr)
+call VecGetArrayF90(vv, pv, global_ierr)
+CHKERRQ(global_ierr)
+call VecGetArrayF90(vp, pp, global_ierr)
+CHKERRQ(global_ierr)
+call VecGetArrayF90(vw, pw, global_ierr)
+CHKERRQ(global_ierr)
+global_ierr = pic1dp_gpu_set_markers(gpu_handle, int(ispecies - 1, c_int32_t), int(np, c_int64_t), px, pv, pp, pw)
+CHKERRQ(global_ierr)
+call VecRestoreArrayF90(vx, px, global_ierr)
+CHKERRQ(global_ierr)
+call VecRestoreArrayF90(vv, pv, global_ierr)
+CHKERRQ(global_ierr)
+call VecRestoreArrayF90(vp, pp, global_ierr)
+CHKERRQ(global_ierr)
+call VecRestoreArrayF90(vw, pw, global_ierr)
+CHKERRQ(global_ierr)
+end subroutine gpu_particle_upload
+
+! before output_all / particle_optimize (src/pic1dp_output.F90:128-150, :228-237): device -> host Vecs
+subroutine gpu_particle_refresh_host(ispecies, vx, vv, vp, vw)
+implicit none
+#include "finclude/petsc.h90"
+PetscInt, intent(in) :: ispecies
+Vec, intent(in) :: vx, vv, vp, vw
+PetscScalar, dimension(:), pointer :: px, pv, pp, pw
+integer(c_int64_t) :: np
+
+call VecGetArrayF90(vx, px, global_ierr)
+CHKERRQ(global_ierr)
+call VecGetArrayF90(vv, pv, global_ierr)
+CHKERRQ(global_ierr)
+call VecGetArrayF90(vp, pp, global_ierr)
+CHKERRQ(global_ierr)
+call VecGetArrayF90(vw, pw, global_ierr)
+CHKERRQ(global_ierr)
+global_ierr = pic1dp_gpu_get_markers(gpu_handle, int(ispecies - 1, c_int32_t), px, pv, pp, pw, np)
+CHKERRQ(global_ierr)
+call VecRestoreArrayF90(vx, px, global_ierr)
+CHKERRQ(global_ierr)
+call VecRestoreArrayF90(vv, pv, global_ierr)
+CHKERRQ(global_ierr)
+call VecRestoreArrayF90(vp, pp, global_ierr)
+CHKERRQ(global_ierr)
+call VecRestoreArrayF90(vw, pw, global_ierr)
+CHKERRQ(global_ierr)
+end subroutine gpu_particle_refresh_host
+
+! body of particle_compute_shape_x (src/pic1dp_particle.F90:275-350)
+subroutine gpu_particle_compute_shape_x
+implicit none
+#include "finclude/petsc.h90"
+global_ierr = pic1dp_gpu_compute_shape_x(gpu_handle)
+CHKERRQ(global_ierr)
+end subroutine gpu_particle_compute_shape_x
+
+! body of interaction_collect_charge (src/pic1dp_interaction.F90:33-155)
+subroutine gpu_interaction_collect_charge
+implicit none
+#include "finclude/petsc.h90"
+global_ierr = pic1dp_gpu_collect_charge(gpu_handle)
+CHKERRQ(global_ierr)
+end subroutine gpu_interaction_collect_charge
+
+! body of field_solve_electric (src/pic1dp_field.F90:218-270)
+subroutine gpu_field_solve_electric
+implicit none
+#include "finclude/petsc.h90"
+global_ierr = pic1dp_gpu_solve_field(gpu_handle)
+CHKERRQ(global_ierr)
+end subroutine gpu_field_solve_electric
+
+! body of interaction_push_particle (src/pic1dp_interaction.F90:161-370); global_irk is the implicit input
+subroutine gpu_interaction_push_particle
+implicit none
+#include "finclude/petsc.h90"
+global_ierr = pic1dp_gpu_push(gpu_handle, int(global_irk, c_int32_t))
+CHKERRQ(global_ierr)
+end subroutine gpu_interaction_push_particle
+
+! before output_field (src/pic1dp_output.F90:178-187): replicated grid quantities -> the local slices of the
+! distributed field Vecs.  ebuf/rbuf are host work arrays of length input_nx, mre/mim of length input_nmode.
+subroutine gpu_field_refresh_host(v_electric, v_chargeden, v_mode_re, v_mode_im, ix_low, ix_high, im_low, im_high)
+implicit none
+#include "finclude/petsc.h90"
+Vec, intent(in) :: v_electric, v_chargeden, v_mode_re, v_mode_im
+PetscInt, intent(in) :: ix_low, ix_high, im_low, im_high
+real(c_double) :: ebuf(0 : input_nx - 1), rbuf(0 : input_nx - 1)
+real(c_double) :: mre(0 : input_nmode - 1), mim(0 : input_nmode - 1)
+PetscScalar, dimension(:), pointer :: pa
+
+global_ierr = pic1dp_gpu_get_field(gpu_handle, ebuf, rbuf, mre, mim)
+CHKERRQ(global_ierr)
+call VecGetArrayF90(v_electric, pa, global_ierr)
+CHKERRQ(global_ierr)
+pa(1 : ix_high - ix_low) = ebuf(ix_low : ix_high - 1)
+call VecRestoreArrayF90(v_electric, pa, global_ierr)
+CHKERRQ(global_ierr)
+call VecGetArrayF90(v_chargeden, pa, global_ierr)
+CHKERRQ(global_ierr)
+pa(1 : ix_high - ix_low) = rbuf(ix_low : ix_high - 1)
+call VecRestoreArrayF90(v_chargeden, pa, global_ierr)
+CHKERRQ(global_ierr)
+if (im_high > im_low) then
+  call VecGetArrayF90(v_mode_re, pa, global_ierr)
+  CHKERRQ(global_ierr)
+  pa(1 : im_high - im_low) = mre(im_low : im_high - 1)
+  call VecRestoreArrayF90(v_mode_re, pa, global_ierr)
+  CHKERRQ(global_ierr)
+  call VecGetArrayF90(v_mode_im, pa, global_ierr)
+  CHKERRQ(global_ierr)
+  pa(1 : im_high - im_low) = mim(im_low : im_high - 1)
+  call VecRestoreArrayF90(v_mode_im, pa, global_ierr)
+  CHKERRQ(global_ierr)
+end if
+end subroutine gpu_field_refresh_host
+
+! particle_final + field_final (src/pic1dp_particle.F90:819-858, src/pic1dp_field.F90:315-348)
+subroutine gpu_final
+implicit none
+#include "finclude/petsc.h90"
+global_ierr = pic1dp_gpu_destroy(gpu_handle)
+CHKERRQ(global_ierr)
+gpu_handle = c_null_ptr
+end subroutine gpu_final
+
+end module pic1dp_gpu_glue

@@ -1,0 +1,509 @@
+// host/pic1dp_host.cpp -- C++ host side above the C ABI (include/pic1dp_gpu.h).
+//
+// The reference host is Fortran 2003; no Fortran compiler exists in this image, so the host side is restated in
+// C++ with the reference's own structure and names: the argument-less procedures of pic1dp_particle /
+// pic1dp_field / pic1dp_interaction over module-global state, the RNG module multirand that feeds particle_load,
+// and the driver sequence of `program pic1dp` (/root/reference/src/pic1dp.F90:43-125).  Every procedure forwards
+// to libpic1dp_b200.so and leaves its status in global_ierr, checked by CHKERRQ like the reference does after every
+// PETSc call.  One host thread per GPU ("rank"); ranks rendezvous through the library's NCCL communicator.
+//
+// Build:  g++ -O2 -std=c++17 -pthread -Iinclude host/pic1dp_host.cpp -Lpic1dp_b200 -lpic1dp_b200 \
+//             -Wl,-rpath,'$ORIGIN/../pic1dp_b200' -o host/pic1dp_host
+// Run:    host/pic1dp_host nparticle_max=6400000 nx=192 time_max=50 ngpus=1 seed_type=1 out=run.txt
+//
+// This is product code: it never touches oracle/.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "pic1dp_gpu.h"
+
+// ===================================================================================================== global
+namespace pic1dp_global {
+// src/pic1dp_global.F90:57-64
+struct RankState {
+  int global_mype = 0, global_npe = 1;
+  int global_ierr = 0;
+  int global_irk = 1;
+  int global_itime = 0;
+  double global_time = 0.0;
+};
+const double PETSC_PI = 3.14159265358979323846264338327950288419716939937510582;
+const double PETSC_SQRT_MACHINE_EPSILON = 1.490116119384766e-08;
+}  // namespace pic1dp_global
+
+#define CHKERRQ(st, h)                                                                              \
+  do {                                                                                              \
+    if ((st).global_ierr) {                                                                         \
+      fprintf(stderr, "[%d] %s:%d error %d (%s): %s\n", (st).global_mype, __FILE__, __LINE__,       \
+              (st).global_ierr, pic1dp_gpu_strerror((st).global_ierr), pic1dp_gpu_last_error(h));   \
+      exit(1);                                                                                      \
+    }                                                                                               \
+  } while (0)
+
+// ====================================================================================================== input
+namespace pic1dp_input {
+// run-time version of the compile-time parameters of src/pic1dp_input.F90:32-256 (same names, same defaults)
+struct Input {
+  int64_t input_ntime_max = 900000;
+  double input_time_max = 500.0;
+  int input_linear = 0;
+  double input_lx = 2.0 * 3.1415926535897932384626 / 0.36;
+  int input_iptcldist = 3;
+  int input_nspecies = 1;
+  double input_species_charge = -1.0, input_species_mass = 1.0, input_species_temperature = 1.0,
+         input_species_temperature2 = 1.0, input_species_density = 0.9, input_species_v0 = 5.0;
+  int input_nmode = 1;
+  int input_modes[PIC1DP_MAX_MODES] = {1};
+  int input_init_nmode = 1;
+  int input_init_mode[PIC1DP_MAX_MODES] = {1};
+  double input_init_mode_cos[PIC1DP_MAX_MODES] = {0.0}, input_init_mode_sin[PIC1DP_MAX_MODES] = {1e-5};
+  int input_deltaf = 1;
+  double input_dt = 0.05;
+  int64_t input_nparticle_max = 6400000;
+  int input_imarker = 2;
+  double input_v_max = 8.0;
+  int input_nx = 192;
+  int input_iptclshape = 4;
+  int input_multirand_al_int = 3, input_multirand_seed_type = 3, input_multirand_warmup = 5;
+  bool input_multirand_selftest = true;
+  double input_output_interval = 0.5;
+  // placement / implementation (not in the reference)
+  int ngpus = 1, deposit_mode = 0, field_mode = 0, fuse = 1;
+  std::string out = "pic1dp_energy.txt";
+};
+
+static bool parse(Input &in, int argc, char **argv) {
+  for (int i = 1; i < argc; i++) {
+    std::string a(argv[i]);
+    size_t eq = a.find('=');
+    if (eq == std::string::npos) return false;
+    std::string k = a.substr(0, eq), v = a.substr(eq + 1);
+    double d = atof(v.c_str());
+    if (k == "nparticle_max") in.input_nparticle_max = (int64_t)d;
+    else if (k == "nx") in.input_nx = (int)d;
+    else if (k == "time_max") in.input_time_max = d;
+    else if (k == "ntime_max") in.input_ntime_max = (int64_t)d;
+    else if (k == "dt") in.input_dt = d;
+    else if (k == "lx") in.input_lx = d;
+    else if (k == "linear") in.input_linear = (int)d;
+    else if (k == "deltaf") in.input_deltaf = (int)d;
+    else if (k == "iptcldist") in.input_iptcldist = (int)d;
+    else if (k == "iptclshape") in.input_iptclshape = (int)d;
+    else if (k == "density") in.input_species_density = d;
+    else if (k == "v0") in.input_species_v0 = d;
+    else if (k == "temperature") in.input_species_temperature = d;
+    else if (k == "temperature2") in.input_species_temperature2 = d;
+    else if (k == "mass") in.input_species_mass = d;
+    else if (k == "charge") in.input_species_charge = d;
+    else if (k == "v_max") in.input_v_max = d;
+    else if (k == "init_sin") in.input_init_mode_sin[0] = d;
+    else if (k == "init_cos") in.input_init_mode_cos[0] = d;
+    else if (k == "al_int") in.input_multirand_al_int = (int)d;
+    else if (k == "seed_type") in.input_multirand_seed_type = (int)d;
+    else if (k == "warmup") in.input_multirand_warmup = (int)d;
+    else if (k == "output_interval") in.input_output_interval = d;
+    else if (k == "ngpus") in.ngpus = (int)d;
+    else if (k == "deposit_mode") in.deposit_mode = (int)d;
+    else if (k == "field_mode") in.field_mode = (int)d;
+    else if (k == "fuse") in.fuse = (int)d;
+    else if (k == "out") in.out = v;
+    else return false;
+  }
+  return true;
+}
+
+// input_init (src/pic1dp_input.F90:287-308)
+static void input_init(const Input &in) {
+  if (in.input_iptcldist >= 1 && in.input_imarker == 1) {
+    fprintf(stderr, "Error: case of input_iptcldist >= 1 and input_imarker = 1 not implemented yet.\n");
+    exit(1);
+  }
+  if (in.input_linear == 1 && in.input_deltaf == 0) {
+    fprintf(stderr, "Error: case of input_linear = 1 and input_deltaf = 0 not implemented yet.\n");
+    exit(1);
+  }
+}
+}  // namespace pic1dp_input
+
+// ================================================================================================== multirand
+// Product-side RNG with the reference's three engines and seeding rules (src/multirand.F90).  Self test against
+// the reference's known-answer values runs at start-up like input_multirand_selftest = .true. does.
+namespace multirand {
+struct Generator {
+  enum { NSEED = 20635 };
+  std::vector<uint64_t> s = std::vector<uint64_t>(NSEED, 0);
+  int iseed = 0, al = 3;
+
+  uint64_t kiss() {  // :921-945
+    uint64_t t = (s[0] << 58) + s[3];
+    const uint64_t c0 = s[0] >> 63;
+    s[3] = (c0 == (t >> 63)) ? (s[0] >> 6) + c0 : (s[0] >> 6) - ((s[0] + t) >> 63) + 1;
+    s[0] += t;
+    s[1] ^= s[1] << 13;
+    s[1] ^= s[1] >> 17;
+    s[1] ^= s[1] << 43;
+    s[2] = 6906969069ULL * s[2] + 1234567ULL;
+    return s[0] + s[1] + s[2];
+  }
+  uint64_t mt() {  // :952-997
+    const int nn = 312, mm = 156;
+    const uint64_t um = 0xFFFFFFFF80000000ULL, lm = 0x7FFFFFFFULL, mag[2] = {0, 0xB5026F5AA96619E9ULL};
+    if (iseed >= nn) {
+      for (int i = 0; i < nn; i++) {
+        const uint64_t x = (s[i] & um) | (s[(i + 1) % nn] & lm);
+        s[i] = s[(i + mm) % nn] ^ (x >> 1) ^ mag[x & 1];
+      }
+      iseed = 0;
+    }
+    uint64_t x = s[iseed++];
+    x ^= (x >> 29) & 0x5555555555555555ULL;
+    x ^= (x << 17) & 0x71D67FFFEDA60000ULL;
+    x ^= (x << 37) & 0xFFF7EEE000000000ULL;
+    return x ^ (x >> 43);
+  }
+  uint64_t superkiss() {  // :1004-1039
+    const int nn = 20632;
+    if (iseed >= nn) {
+      for (int i = 0; i < nn; i++) {
+        const uint64_t h = s[nn] & 1, z = ((s[i] << 41) >> 1) + ((s[i] << 39) >> 1) + (s[nn] >> 1);
+        s[nn] = (s[i] >> 23) + (s[i] >> 25) + (z >> 63);
+        s[i] = ~((z << 1) + h);
+      }
+      iseed = 0;
+    }
+    s[nn + 1] = s[nn + 1] * 6906969069ULL + 123;
+    s[nn + 2] ^= s[nn + 2] << 13;
+    s[nn + 2] ^= s[nn + 2] >> 17;
+    s[nn + 2] ^= s[nn + 2] << 43;
+    return s[iseed++] + s[nn + 1] + s[nn + 2];
+  }
+  int64_t int64() { return (int64_t)(al == 2 ? mt() : al == 3 ? superkiss() : kiss()); }
+  double real64() { return (double)int64() / 18446744073709551615.0 + 0.5; }  // INT2REAL64, :49
+
+  void default_seeds(int al_) {  // :476-518
+    al = al_;
+    std::fill(s.begin(), s.end(), 0);
+    iseed = 0;
+    if (al == 2) {
+      s[0] = 5489;
+      for (int i = 1; i < 312; i++) s[i] = 6364136223846793005ULL * (s[i - 1] ^ (s[i - 1] >> 62)) + (uint64_t)i;
+      iseed = 312;
+    } else if (al == 3) {
+      s[20632] = 36243678541ULL;
+      s[20633] = 12367890123456ULL;
+      s[20634] = 521288629546311ULL;
+      for (int i = 0; i < 20632; i++) {
+        s[20633] = s[20633] * 6906969069ULL + 123;
+        s[20634] ^= s[20634] << 13;
+        s[20634] ^= s[20634] >> 17;
+        s[20634] ^= s[20634] << 43;
+        s[i] = s[20633] + s[20634];
+      }
+      iseed = 20632;
+    } else {
+      s[0] = 1234567890987654321ULL;
+      s[1] = 362436362436362436ULL;
+      s[2] = 1066149217761810ULL;
+      s[3] = 123456123456123456ULL;
+    }
+  }
+  bool selftest(int al_) {  // first known-answer value of each engine, :396-419
+    default_seeds(al_);
+    const int64_t first = int64();
+    return first == (al_ == 2 ? -3932459287431434586LL : al_ == 3 ? 6140839658375754198LL : 8932985056925012148LL);
+  }
+  // multirand_init, seed types 1 (constant) and 3 (/dev/urandom): :244-381
+  void init(int al_, int seed_type, int mype, int warmup) {
+    static const int64_t primes1[100] = {
+        15484219, 15484223, 15484243, 15484247, 15484279, 15484333, 15484363, 15484387, 15484393, 15484409, 15484421,
+        15484453, 15484457, 15484459, 15484471, 15484489, 15484517, 15484519, 15484549, 15484559, 15484591, 15484627,
+        15484631, 15484643, 15484661, 15484697, 15484709, 15484723, 15484769, 15484771, 15484783, 15484817, 15484823,
+        15484873, 15484877, 15484879, 15484901, 15484919, 15484939, 15484951, 15484961, 15484999, 15485039, 15485053,
+        15485059, 15485077, 15485083, 15485143, 15485161, 15485179, 15485191, 15485221, 15485243, 15485251, 15485257,
+        15485273, 15485287, 15485291, 15485293, 15485299, 15485311, 15485321, 15485339, 15485341, 15485357, 15485363,
+        15485383, 15485389, 15485401, 15485411, 15485429, 15485441, 15485447, 15485471, 15485473, 15485497, 15485537,
+        15485539, 15485543, 15485549, 15485557, 15485567, 15485581, 15485609, 15485611, 15485621, 15485651, 15485653,
+        15485669, 15485677, 15485689, 15485711, 15485737, 15485747, 15485761, 15485773, 15485783, 15485801, 15485807,
+        15485837};
+    static const int64_t primes2[100] = {
+        7001, 7013, 7019, 7027, 7039, 7043, 7057, 7069, 7079, 7103, 7109, 7121, 7127, 7129, 7151, 7159, 7177, 7187, 7193,
+        7207, 7211, 7213, 7219, 7229, 7237, 7243, 7247, 7253, 7283, 7297, 7307, 7309, 7321, 7331, 7333, 7349, 7351, 7369,
+        7393, 7411, 7417, 7433, 7451, 7457, 7459, 7477, 7481, 7487, 7489, 7499, 7507, 7517, 7523, 7529, 7537, 7541, 7547,
+        7549, 7559, 7561, 7573, 7577, 7583, 7589, 7591, 7603, 7607, 7621, 7639, 7643, 7649, 7669, 7673, 7681, 7687, 7691,
+        7699, 7703, 7717, 7723, 7727, 7741, 7753, 7757, 7759, 7789, 7793, 7817, 7823, 7829, 7841, 7853, 7867, 7873, 7877,
+        7879, 7883, 7901, 7907, 7919};
+    al = al_;
+    const int nseed = al == 2 ? 312 : al == 3 ? 20635 : 4;
+    std::fill(s.begin(), s.end(), 0);
+    bool seeded = false;
+    if (seed_type == 3) {
+      FILE *f = fopen("/dev/urandom", "rb");
+      if (f && fread(s.data(), 8, nseed, f) == (size_t)nseed) {
+        seeded = true;
+        if (al == 3 && s[20634] == 0) s[20634] = 521288629546311ULL;
+        if (al == 1 && s[1] == 0) s[1] = 362436362436362436ULL;
+      }
+      if (f) fclose(f);
+    }
+    if (!seeded) {  // constant seeds, rank dependent (:301-350)
+      auto iabs = [](int64_t a) { return a < 0 ? -a : a; };
+      const int64_t clock = primes1[1];
+      int64_t k4[4];
+      for (int i = 0; i < 4; i++) k4[i] = clock + primes1[iabs(clock + primes2[iabs(clock) % 100] * mype) % 100] * mype;
+      for (int i = 0; i < 4; i++) k4[i] += primes2[iabs(k4[i] + primes1[iabs(clock) % 100] * i) % 100] * i;
+      for (int i = 0; i < 4; i++) s[i] = (uint64_t)k4[i];
+      std::vector<uint64_t> tmp(NSEED, 0);
+      for (int i = 0; i < 20; i++) tmp[0] = kiss();
+      for (int i = 1; i < nseed; i++) tmp[i] = kiss();
+      if (al == 1) {
+        while (tmp[1] == 0) tmp[1] = kiss();
+        while (tmp[0] == 0 && tmp[3] == 0) {
+          tmp[0] = kiss();
+          tmp[3] = kiss();
+        }
+      }
+      s = tmp;
+    }
+    iseed = al == 2 ? 312 : al == 3 ? 20632 : 0;
+    for (int64_t i = 0; i < (int64_t)warmup * nseed; i++) (void)int64();
+  }
+  void real_array(double *a, int64_t n) {
+    for (int64_t i = 0; i < n; i++) a[i] = real64();
+  }
+};
+}  // namespace multirand
+
+// ================================================================================= per-rank "module" state
+struct Rank {
+  pic1dp_global::RankState g;
+  const pic1dp_input::Input *in = nullptr;
+  pic1dp_gpu_t *h = nullptr;
+  int64_t particle_ip_low = 0, particle_ip_high = 0, particle_np = 0;
+  std::vector<double> x, v, p, w;  // host copies of particle_x, _v, _p, _w (src/pic1dp_particle.F90:34-36)
+  std::vector<double> field_electric, field_chargeden, field_mode_re, field_mode_im;
+};
+
+namespace pic1dp_particle {
+// particle_init (src/pic1dp_particle.F90:66-139) + field_init (src/pic1dp_field.F90:55-212)
+static void particle_init(Rank &r, const uint8_t *uid) {
+  const pic1dp_input::Input &in = *r.in;
+  const int64_t n = in.input_nparticle_max, npe = r.g.global_npe, me = r.g.global_mype;
+  r.particle_ip_low = (n / npe) * me + (me < n % npe ? me : n % npe);  // PETSC_DECIDE split, :91, :129
+  r.particle_ip_high = r.particle_ip_low + n / npe + (me < n % npe ? 1 : 0);
+  pic1dp_params p;
+  pic1dp_gpu_params_default(&p);
+  p.nx = in.input_nx;
+  p.nmode = in.input_nmode;
+  for (int m = 0; m < in.input_nmode; m++) p.modes[m] = in.input_modes[m];
+  p.lx = in.input_lx;
+  p.dt = in.input_dt;
+  p.nspecies = 1;
+  p.charge[0] = in.input_species_charge;
+  p.mass[0] = in.input_species_mass;
+  p.temperature[0] = in.input_species_temperature;
+  p.temperature2[0] = in.input_species_temperature2;
+  p.density[0] = in.input_species_density;
+  p.v0[0] = in.input_species_v0;
+  p.iptcldist = in.input_iptcldist;
+  p.deltaf = in.input_deltaf;
+  p.linear = in.input_linear;
+  p.iptclshape = in.input_iptclshape;
+  p.capacity = r.particle_ip_high - r.particle_ip_low;
+  p.device = (int)me;
+  p.rank = (int)me;
+  p.nranks = (int)npe;
+  p.deposit_mode = in.deposit_mode;
+  p.field_mode = in.field_mode;
+  p.fuse = in.fuse;
+  r.g.global_ierr = pic1dp_gpu_create(&p, &r.h);
+  CHKERRQ(r.g, (pic1dp_gpu_t *)nullptr);
+  if (npe > 1) {
+    r.g.global_ierr = pic1dp_gpu_comm_init(r.h, uid);
+    CHKERRQ(r.g, r.h);
+  }
+  r.field_electric.resize(in.input_nx);
+  r.field_chargeden.resize(in.input_nx);
+  r.field_mode_re.resize(in.input_nmode);
+  r.field_mode_im.resize(in.input_nmode);
+}
+
+// particle_load (src/pic1dp_particle.F90:145-269), uniform-v markers (input_imarker = 2), then host -> device
+static void particle_load(Rank &r) {
+  const pic1dp_input::Input &in = *r.in;
+  using pic1dp_global::PETSC_PI;
+  multirand::Generator rng;
+  if (in.input_multirand_selftest && !rng.selftest(in.input_multirand_al_int))
+    fprintf(stderr, "[%d][multirand_selftest] Warning: unexpected head sequence.\n", r.g.global_mype);
+  rng.init(in.input_multirand_al_int, in.input_multirand_seed_type, r.g.global_mype, in.input_multirand_warmup);
+  const int64_t n = r.particle_ip_high - r.particle_ip_low;
+  r.x.resize(n);
+  r.v.resize(n);
+  r.p.resize(n);
+  r.w.resize(n);
+  const double T = in.input_species_temperature, T2 = in.input_species_temperature2, m = in.input_species_mass;
+  const double dens = in.input_species_density, v0 = in.input_species_v0, lx = in.input_lx, vmax = in.input_v_max;
+  const double ninit = (double)in.input_nparticle_max;
+  rng.real_array(r.v.data(), n);  // :180
+  for (int64_t i = 0; i < n; i++) r.v[i] = (r.v[i] - 0.5) * 2.0 * vmax;
+  for (int64_t i = 0; i < n; i++) {
+    const double pv = r.v[i];
+    double pp;
+    if (in.input_iptcldist == 1)
+      pp = dens * lx * 2.0 * vmax / ninit * (pv * pv) * exp(-(pv * pv) / 2.0) / sqrt(2.0 * PETSC_PI);
+    else if (in.input_iptcldist == 2)
+      pp = dens * lx * 2.0 * vmax / ninit *
+           (exp(-((pv + v0) * (pv + v0)) / (2.0 * T / m)) + exp(-((pv - v0) * (pv - v0)) / (2.0 * T / m))) /
+           sqrt(8.0 * PETSC_PI * T / m);
+    else if (in.input_iptcldist == 3)
+      pp = 1.0 * lx * 2.0 * vmax / ninit *
+           (dens * exp(-(pv * pv) / (2.0 * T / m)) / sqrt(2.0 * PETSC_PI * T / m) +
+            (1.0 - dens) * exp(-((pv - v0) * (pv - v0)) / (2.0 * T2 / m)) / sqrt(2.0 * PETSC_PI * T2 / m));
+    else
+      pp = dens * lx * 2.0 * vmax / ninit * exp(-((pv - v0) * (pv - v0)) / (2.0 * T / m)) / sqrt(2.0 * PETSC_PI * T / m);
+    r.p[i] = pp;
+  }
+  rng.real_array(r.x.data(), n);  // :222
+  for (int64_t i = 0; i < n; i++) r.x[i] = r.x[i] * lx;
+  for (int64_t i = 0; i < n; i++) r.w[i] = 0.0;
+  for (int im = 0; im < in.input_init_nmode; im++)
+    for (int64_t i = 0; i < n; i++) {
+      const double k = 2.0 * PETSC_PI / lx * (double)in.input_init_mode[im];
+      r.w[i] = r.w[i] + in.input_init_mode_cos[im] * cos(k * r.x[i]) + in.input_init_mode_sin[im] * sin(k * r.x[i]);
+    }
+  for (int64_t i = 0; i < n; i++) r.w[i] = r.w[i] * r.p[i] * 1.0;  // input_pertb_shape == 1
+  if (in.input_linear == 0)
+    for (int64_t i = 0; i < n; i++) r.p[i] = r.p[i] + 1.0 * r.w[i];
+  r.particle_np = n;  // input_species_nparticle_init == input_nparticle_max: nothing to unload (:240-248)
+  r.g.global_ierr = pic1dp_gpu_set_markers(r.h, 0, n, r.x.data(), r.v.data(), r.p.data(), r.w.data());
+  CHKERRQ(r.g, r.h);
+}
+
+static void particle_compute_shape_x(Rank &r) {  // :275-350
+  r.g.global_ierr = pic1dp_gpu_compute_shape_x(r.h);
+  CHKERRQ(r.g, r.h);
+}
+static void particle_final(Rank &r) {  // :819-858 (+ field_final)
+  r.g.global_ierr = pic1dp_gpu_destroy(r.h);
+  r.h = nullptr;
+}
+}  // namespace pic1dp_particle
+
+namespace pic1dp_field {
+static void field_solve_electric(Rank &r) {  // src/pic1dp_field.F90:218-270
+  r.g.global_ierr = pic1dp_gpu_solve_field(r.h);
+  CHKERRQ(r.g, r.h);
+}
+}  // namespace pic1dp_field
+
+namespace pic1dp_interaction {
+static void interaction_collect_charge(Rank &r) {  // src/pic1dp_interaction.F90:33-155
+  r.g.global_ierr = pic1dp_gpu_collect_charge(r.h);
+  CHKERRQ(r.g, r.h);
+}
+static void interaction_push_particle(Rank &r) {  // :161-370, implicit input global_irk
+  r.g.global_ierr = pic1dp_gpu_push(r.h, r.g.global_irk);
+  CHKERRQ(r.g, r.h);
+}
+}  // namespace pic1dp_interaction
+
+namespace pic1dp_output {
+// scalar part of output_field (src/pic1dp_output.F90:117-124, :178-181): t, int E^2 dx, mode_re, mode_im
+static void output_field(Rank &r, FILE *f) {
+  double energy = 0.0;
+  r.g.global_ierr = pic1dp_gpu_field_energy(r.h, &energy);
+  CHKERRQ(r.g, r.h);
+  r.g.global_ierr = pic1dp_gpu_get_field(r.h, r.field_electric.data(), r.field_chargeden.data(), r.field_mode_re.data(),
+                                         r.field_mode_im.data());
+  CHKERRQ(r.g, r.h);
+  if (f && r.g.global_mype == 0)
+    fprintf(f, "%.17g %.17g %.17g %.17g\n", r.g.global_time, energy, r.field_mode_re[0], r.field_mode_im[0]);
+}
+}  // namespace pic1dp_output
+
+// ===================================================================================================== driver
+static int check_termination(const Rank &r) {  // src/pic1dp.F90:133-148
+  return (r.g.global_itime >= r.in->input_ntime_max ||
+          r.g.global_time + pic1dp_global::PETSC_SQRT_MACHINE_EPSILON >= r.in->input_time_max)
+             ? 1
+             : 0;
+}
+
+static void run_rank(const pic1dp_input::Input *in, int mype, int npe, const uint8_t *uid, double *steps_per_s) {
+  Rank r;
+  r.in = in;
+  r.g.global_mype = mype;
+  r.g.global_npe = npe;
+  FILE *f = (mype == 0) ? fopen(in->out.c_str(), "w") : nullptr;
+  pic1dp_input::input_init(*in);
+  pic1dp_particle::particle_init(r, uid);  // + field_init
+  pic1dp_particle::particle_load(r);
+  if (in->input_iptclshape < 4) pic1dp_particle::particle_compute_shape_x(r);  // src/pic1dp.F90:65
+  r.g.global_itime = 0;
+  r.g.global_time = 0.0;
+  pic1dp_interaction::interaction_collect_charge(r);  // :71
+  pic1dp_field::field_solve_electric(r);              // :72
+  pic1dp_output::output_field(r, f);                  // :74
+  pic1dp_gpu_timer_start(r.h);
+  int itermination = check_termination(r);
+  while (itermination == 0) {  // :78-109
+    for (r.g.global_irk = 1; r.g.global_irk <= 2; r.g.global_irk++) {
+      pic1dp_interaction::interaction_push_particle(r);
+      // particle_optimize: disabled in the default input (input_nmerge = nremove = nsplit = 0)
+      if (in->input_iptclshape < 4) pic1dp_particle::particle_compute_shape_x(r);
+      pic1dp_interaction::interaction_collect_charge(r);
+      pic1dp_field::field_solve_electric(r);
+    }
+    r.g.global_itime++;
+    r.g.global_time += in->input_dt;
+    itermination = check_termination(r);
+    const double eps = pic1dp_global::PETSC_SQRT_MACHINE_EPSILON;
+    if (fmod(r.g.global_time + eps, in->input_output_interval) <
+            fmod(r.g.global_time + eps - in->input_dt, in->input_output_interval) ||
+        itermination == 1)
+      pic1dp_output::output_field(r, f);  // :98-108
+  }
+  float ms = 0.f;
+  pic1dp_gpu_timer_stop(r.h, &ms);
+  if (steps_per_s) *steps_per_s = (double)r.particle_np * r.g.global_itime / (ms * 1e-3);
+  pic1dp_counters c;
+  pic1dp_gpu_get_counters(r.h, &c);
+  if (mype == 0)
+    printf("steps=%d markers/rank=%lld kernels=%lld nccl=%lld oob=%lld deposit_mode=%d  %.3e particle-steps/s/rank (wall incl. outputs)\n",
+           r.g.global_itime, (long long)r.particle_np, (long long)c.kernel_launches, (long long)c.nccl_calls,
+           (long long)c.oob_markers, c.deposit_mode, (double)r.particle_np * r.g.global_itime / (ms * 1e-3));
+  pic1dp_particle::particle_final(r);
+  if (f) fclose(f);
+}
+
+int main(int argc, char **argv) {
+  pic1dp_input::Input in;
+  if (!pic1dp_input::parse(in, argc, argv)) {
+    fprintf(stderr, "usage: %s [key=value ...]  (keys: nparticle_max nx time_max dt ngpus seed_type out ...)\n", argv[0]);
+    return 2;
+  }
+  printf("PIC1D hot path on B200 (libpic1dp_b200, ABI %d): %lld markers, nx=%d, dt=%g, t_max=%g, %d GPU(s)\n",
+         pic1dp_gpu_abi_version(), (long long)in.input_nparticle_max, in.input_nx, in.input_dt, in.input_time_max, in.ngpus);
+  uint8_t uid[PIC1DP_UNIQUE_ID_BYTES] = {0};
+  if (in.ngpus > 1) {
+    int rc = pic1dp_gpu_comm_unique_id(uid);
+    if (rc) {
+      fprintf(stderr, "comm_unique_id: %s: %s\n", pic1dp_gpu_strerror(rc), pic1dp_gpu_last_error(nullptr));
+      return 1;
+    }
+  }
+  std::vector<std::thread> th;
+  std::vector<double> rate(in.ngpus, 0.0);
+  for (int r = 0; r < in.ngpus; r++) th.emplace_back(run_rank, &in, r, in.ngpus, uid, &rate[r]);
+  for (auto &t : th) t.join();
+  return 0;
+}

@@ -42,6 +42,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_SRC = os.path.join(HERE, "..", "host", "pic1dp_host.cpp")
+HOST_EXE = os.path.join(HERE, "..", "host", "pic1dp_host")
+
+
+def build_host(force: bool = False) -> str:
+    """C++ host driver above the C ABI (host/pic1dp_host.cpp): the reference's `program pic1dp` sequence."""
+    build()
+    if not force and os.path.exists(HOST_EXE) and os.path.getmtime(HOST_EXE) >= max(
+            os.path.getmtime(HOST_SRC), os.path.getmtime(LIB)):
+        return HOST_EXE
+    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(HERE, "..", "include"), HOST_SRC,
+           "-L", HERE, "-lpic1dp_b200", "-Wl,-rpath,$ORIGIN/../pic1dp_b200", "-o", HOST_EXE]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return HOST_EXE
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

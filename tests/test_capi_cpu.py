@@ -116,3 +116,18 @@ def test_petsc_decide_split():
             if r:
                 assert spans[r][0] == spans[r - 1][1]
             assert spans[r][1] - spans[r][0] == n // npe + (1 if r < n % npe else 0)
+
+
+def test_cpp_host_driver_builds_and_fails_loudly_without_gpu():
+    """host/pic1dp_host (C++ mirror of `program pic1dp`) links against the C ABI; with no GPU it must exit non-zero
+    with the library's no-device error instead of computing on the CPU."""
+    import torch
+    from pic1dp_b200 import build
+    exe = build.build_host()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = subprocess.run([exe, "nparticle_max=1000", "time_max=1"], capture_output=True, text=True)
+    assert out.returncode == 1
+    assert "no CUDA device" in out.stderr
+    bad = subprocess.run([exe, "linear=1", "deltaf=0"], capture_output=True, text=True)  # input_init check
+    assert bad.returncode == 1 and "not implemented" in bad.stderr
