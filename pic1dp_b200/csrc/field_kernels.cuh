@@ -30,35 +30,48 @@ struct GridArgs {
   double *energy;
 };
 
-// one thread per cell; CTA partials summed in ascending CTA order (deterministic)
-__global__ void __launch_bounds__(128) k_reduce_charge(const GridArgs g) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.nx) return;
+// CTA = 32 cells x 8 warps.  Warp q sums the private grids q, q+8, q+16, ... of its 32 cells in that order (4 loads
+// in flight), then warp 0 adds the 8 partial sums in warp order: a fixed summation tree, hence deterministic.
+__global__ void __launch_bounds__(256) k_reduce_charge(const GridArgs g) {
+  __shared__ double s_part[8][33];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   double c2 = 0.0;
   for (int s = 0; s < g.nspecies; s++) {
-    double *ps = g.partial + (size_t)s * g.ngrids * g.nx + j;
     double c1 = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < g.ngrids; k++) {
-      const double t = ps[(size_t)k * g.nx];
-      c1 = (k == 0) ? t : dadd(c1, t);
+    if (j < g.nx) {
+      double *ps = g.partial + (size_t)s * g.ngrids * g.nx + j;
+      int k = wq;
+      for (; k + 24 < g.ngrids; k += 32) {
+        const double t0 = ps[(size_t)k * g.nx], t1 = ps[(size_t)(k + 8) * g.nx];
+        const double t2 = ps[(size_t)(k + 16) * g.nx], t3 = ps[(size_t)(k + 24) * g.nx];
+        c1 = dadd(dadd(dadd(dadd(c1, t0), t1), t2), t3);
+      }
+      for (; k < g.ngrids; k += 8) c1 = dadd(c1, ps[(size_t)k * g.nx]);
+      if (g.zero_partials)
+        for (k = wq; k < g.ngrids; k += 8) ps[(size_t)k * g.nx] = 0.0;
     }
-    if (g.zero_partials)
-      for (int k = 0; k < g.ngrids; k++) ps[(size_t)k * g.nx] = 0.0;
-    if (g.matrix_path)
-      g.red[(size_t)s * g.nx + j] = c1;  // field_tmp = S^T w per species (:52-59)
-    else
-      c2 = dadd(c2, dmul(c1, g.Z[s]));   // charge2 += charge1 * Z (:126-127)
+    s_part[wq][lane] = c1;
+    __syncthreads();
+    if (wq == 0 && j < g.nx) {
+      double t = s_part[0][lane];
+#pragma unroll
+      for (int q = 1; q < 8; q++) t = dadd(t, s_part[q][lane]);
+      if (g.matrix_path)
+        g.red[(size_t)s * g.nx + j] = t;  // field_tmp = S^T w per species (:52-59)
+      else
+        c2 = dadd(c2, dmul(t, g.Z[s]));   // charge2 += charge1 * Z (:126-127)
+    }
+    __syncthreads();
   }
-  if (!g.matrix_path) g.red[j] = c2;
+  if (wq == 0 && j < g.nx && !g.matrix_path) g.red[j] = c2;
 }
 
-__global__ void __launch_bounds__(128) k_finalize_rho(const GridArgs g) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.nx) return;
+// rho from the (all-)reduced grid: charge1 * nx / lx and the full-f offset (:140-148); matrix path :64-78
+__device__ __forceinline__ double finalize_rho(const GridArgs &g, int j) {
   double rho;
   if (!g.matrix_path) {
-    rho = ddiv(dmul(g.red[j], g.rnx), g.lx);  // charge1 * nx / lx (:140-141)
+    rho = ddiv(dmul(g.red[j], g.rnx), g.lx);  // :140-141
     if (!g.deltaf)
       for (int s = 0; s < g.nspecies; s++) rho = dsub(rho, dmul(g.Z[s], g.n[s]));  // :142-148
   } else {
@@ -70,20 +83,35 @@ __global__ void __launch_bounds__(128) k_finalize_rho(const GridArgs g) {
     }
     rho = dmul(rho, g.nx_over_lx);  // VecScale :77
   }
-  g.rho[j] = rho;
+  return rho;
+}
+
+__global__ void __launch_bounds__(128) k_finalize_rho(const GridArgs g) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < g.nx) g.rho[j] = finalize_rho(g, j);
 }
 
 // Single CTA, 1024 threads.  smem: rho[nx] + 2*nmode mode values.
 // SEQ=true : thread m walks j = 0..nx-1 in order (bit-identical to sequential-AIJ MatMultTranspose).
 // SEQ=false: warp per mode, lanes stride j, fixed shuffle tree (deterministic).
-template <bool SEQ>
+// FINALIZE: also does k_finalize_rho's work first (one launch less per substep inside step()).
+template <bool SEQ, bool FINALIZE>
 __global__ void __launch_bounds__(1024) k_field_solve(const GridArgs g) {
   extern __shared__ __align__(16) double smem[];
   double *s_rho = smem;
   double *s_re = smem + g.nx;
   double *s_im = s_re + g.nmode;
   const int M = g.nmode, nx = g.nx;
-  for (int j = threadIdx.x; j < nx; j += blockDim.x) s_rho[j] = g.rho[j];
+  for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+    double r;
+    if (FINALIZE) {
+      r = finalize_rho(g, j);
+      g.rho[j] = r;
+    } else {
+      r = g.rho[j];
+    }
+    s_rho[j] = r;
+  }
   __syncthreads();
   if (SEQ) {
     for (int m = threadIdx.x; m < M; m += blockDim.x) {

@@ -378,8 +378,10 @@ static int create_impl(pic1dp_gpu_t *h) {
   }
   CK(cudaFuncSetAttribute(pick_deposit(dep, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           h->smem_dep > 0 ? h->smem_dep : 8));
-  CK(cudaFuncSetAttribute(k_field_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
-  CK(cudaFuncSetAttribute(k_field_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
+  CK(cudaFuncSetAttribute(k_field_solve<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
+  CK(cudaFuncSetAttribute(k_field_solve<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
+  CK(cudaFuncSetAttribute(k_field_solve<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
+  CK(cudaFuncSetAttribute(k_field_solve<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (nx + 2 * M) * 8));
 
   // ---- markers ----
   const size_t cap = ((size_t)p.capacity + 1) & ~(size_t)1;  // even, for 128-bit accesses
@@ -630,13 +632,12 @@ int pic1dp_gpu_get_shape_x(pic1dp_gpu_t *h, int32_t isp, int32_t *indexes, doubl
   return PIC1DP_OK;
 }
 
-static int reduce_and_finalize(pic1dp_gpu_t *h, cudaEvent_t mid) {
+// sum of the private grids (+ species charge), all-reduce over ranks, optionally rho = ... (k_finalize_rho)
+static int reduce_charge(pic1dp_gpu_t *h, bool finalize) {
   GridArgs g;
   fill_grid_args(h, g);
-  const int nb = (h->p.nx + 127) / 128;
-  k_reduce_charge<<<nb, 128, 0, h->stream>>>(g);
+  k_reduce_charge<<<(h->p.nx + 31) / 32, 256, 0, h->stream>>>(g);
   CKL(h);
-  (void)mid;
   if (h->p.nranks > 1) {
     if (!h->comm) { h->err = "collect_charge: nranks > 1 but comm_init was not called"; return PIC1DP_ESTATE; }
     ncclResult_t r = g_nccl.AllReduce(h->d_red, h->d_red, (size_t)h->nred * h->p.nx, ncclDouble, ncclSum, h->comm,
@@ -644,13 +645,14 @@ static int reduce_and_finalize(pic1dp_gpu_t *h, cudaEvent_t mid) {
     if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return PIC1DP_ENCCL; }
     h->nccl_calls++;
   }
-  k_finalize_rho<<<nb, 128, 0, h->stream>>>(g);
-  CKL(h);
+  if (finalize) {
+    k_finalize_rho<<<(h->p.nx + 127) / 128, 128, 0, h->stream>>>(g);
+    CKL(h);
+  }
   return PIC1DP_OK;
 }
 
-int pic1dp_gpu_collect_charge(pic1dp_gpu_t *h) {
-  if (!h) return PIC1DP_EINVAL;
+static int collect_charge_impl(pic1dp_gpu_t *h, bool finalize) {
   int rc = check_loaded(h, "collect_charge");
   if (rc) return rc;
   CK(cudaSetDevice(h->p.device));
@@ -659,21 +661,32 @@ int pic1dp_gpu_collect_charge(pic1dp_gpu_t *h) {
     if (rc) return rc;
   }
   h->partial_valid = false;
-  return reduce_and_finalize(h, nullptr);
+  return reduce_charge(h, finalize);
 }
 
-int pic1dp_gpu_solve_field(pic1dp_gpu_t *h) {
+int pic1dp_gpu_collect_charge(pic1dp_gpu_t *h) {
   if (!h) return PIC1DP_EINVAL;
+  return collect_charge_impl(h, true);
+}
+
+// finalize_first: rho has not been formed yet (step() skips k_finalize_rho and lets the solve kernel do it)
+static int solve_field_impl(pic1dp_gpu_t *h, bool finalize_first) {
   CK(cudaSetDevice(h->p.device));
   GridArgs g;
   fill_grid_args(h, g);
   const int smem = (h->p.nx + 2 * h->p.nmode) * 8;
-  if (h->p.field_mode == PIC1DP_FIELD_SEQUENTIAL)
-    k_field_solve<true><<<1, 1024, smem, h->stream>>>(g);
-  else
-    k_field_solve<false><<<1, 1024, smem, h->stream>>>(g);
+  const bool seq = h->p.field_mode == PIC1DP_FIELD_SEQUENTIAL;
+  if (seq && finalize_first) k_field_solve<true, true><<<1, 1024, smem, h->stream>>>(g);
+  else if (seq) k_field_solve<true, false><<<1, 1024, smem, h->stream>>>(g);
+  else if (finalize_first) k_field_solve<false, true><<<1, 1024, smem, h->stream>>>(g);
+  else k_field_solve<false, false><<<1, 1024, smem, h->stream>>>(g);
   CKL(h);
   return PIC1DP_OK;
+}
+
+int pic1dp_gpu_solve_field(pic1dp_gpu_t *h) {
+  if (!h) return PIC1DP_EINVAL;
+  return solve_field_impl(h, false);
 }
 
 int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
@@ -727,9 +740,9 @@ int pic1dp_gpu_step(pic1dp_gpu_t *h, int32_t nsteps) {
         rc = pic1dp_gpu_compute_shape_x(h);
         if (rc) return rc;
       }
-      rc = pic1dp_gpu_collect_charge(h);
+      rc = collect_charge_impl(h, false);   // rho is formed inside the solve kernel: one launch less
       if (rc) return rc;
-      rc = pic1dp_gpu_solve_field(h);
+      rc = solve_field_impl(h, true);
       if (rc) return rc;
     }
   return PIC1DP_OK;
