@@ -207,6 +207,26 @@ int pic1dp_gpu_get_operators(pic1dp_gpu_t *h, double *F_re, double *F_im, double
 /* field energy |E|_2^2 * lx / nx (src/pic1dp_output.F90:120-123), reduced on the device */
 int pic1dp_gpu_field_energy(pic1dp_gpu_t *h, double *energy);
 
+/*
+ * output_field: the scalars output_field writes per record (src/pic1dp_output.F90:117-172), reduced on the device
+ * and over ranks (VecNorm / VecSum are collective): scalars[0] = |E|^2*lx/nx, then per species s:
+ * scalars[1+3s] = sum v^2, scalars[2+3s] = sum v^2 p (+ sum v^2 w when linear, :152-155),
+ * scalars[3+3s] = sum v^2 w (delta-f) or the full-f perturbed energy (:156-170).  1 + 3*nspecies doubles.
+ * Replaces the host-side VecPointwiseMult/VecSum over marker Vecs: no marker leaves the GPU.
+ */
+int pic1dp_gpu_output_field(pic1dp_gpu_t *h, double *scalars);
+
+/*
+ * output_ptcldist: the six arrays output_ptcldist writes per species (src/pic1dp_output.F90:196-477): bilinear x-v
+ * histograms of markers g, total f and perturbed delta f on an nx_opd x nv_opd grid ([iv*nx_opd + ix]) and their
+ * v-only counterparts, binned on the device, summed over ranks (MPI_Reduce, :333-357; here every rank receives the
+ * result), scaled by 1/(dx dv) (:362-371) and, for full-f, reduced by the equilibrium (:372-455).
+ * markers with |v| >= v_max are skipped (:241).  Any output pointer may be NULL.
+ */
+int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int32_t nv_opd, double v_max,
+                               double *markr_xv, double *total_xv, double *pertb_xv, double *markr_v,
+                               double *total_v, double *pertb_v);
+
 /* block until all queued work of this handle is done; surfaces asynchronous CUDA errors */
 int pic1dp_gpu_sync(pic1dp_gpu_t *h);
 

@@ -84,6 +84,9 @@ def lib() -> C.CDLL:
         L.orc_field_energy.argtypes = [pp, dp]
         L.orc_field_energy.restype = C.c_double
         L.orc_particle_load.argtypes = [pp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, dp, dp, dp, dp]
+        L.orc_output_field.argtypes = [pp, C.c_int, C.POINTER(C.c_int64), C.POINTER(dp), C.POINTER(dp), C.POINTER(dp), dp, dp]
+        L.orc_output_ptcldist.argtypes = [pp, C.c_int, C.c_int, C.POINTER(C.c_int64)] + [C.POINTER(dp)] * 4 + \
+            [C.c_int, C.c_int, C.c_double] + [dp] * 6
         L.orc_petsc_decide.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_run.argtypes = [pp, C.c_int, C.POINTER(OrcRankState), C.c_int, dp, dp, dp, dp, dp, C.c_int]
         L.orc_run.restype = C.c_double
@@ -175,6 +178,30 @@ class Oracle:
 
     def field_energy(self, E):
         return self.L.orc_field_energy(C.byref(self.p), _dp(np.ascontiguousarray(E)))
+
+    def _ptrs(self, states, key):
+        S, R = len(states), len(states[0])
+        dpt = C.POINTER(C.c_double)
+        return (dpt * (S * R))(*[_dp(states[s][r][key]) for s in range(S) for r in range(R)])
+
+    def output_field(self, states, E):
+        """states: list[species][rank] of marker dicts.  Returns [energy, (sum v2, sum v2 p, sum v2 w | pert) ...]."""
+        S, R = len(states), len(states[0])
+        npa = (C.c_int64 * (S * R))(*[states[s][r]["x"].size for s in range(S) for r in range(R)])
+        out = np.zeros(1 + 3 * S)
+        self.L.orc_output_field(C.byref(self.p), R, npa, self._ptrs(states, "v"), self._ptrs(states, "p"),
+                                self._ptrs(states, "w"), _dp(np.ascontiguousarray(E)), _dp(out))
+        return out
+
+    def output_ptcldist(self, states, isp, nx_opd=64, nv_opd=64, v_max=8.0):
+        S, R = len(states), len(states[0])
+        npa = (C.c_int64 * (S * R))(*[states[s][r]["x"].size for s in range(S) for r in range(R)])
+        nc = nx_opd * nv_opd
+        outs = [np.zeros(nc), np.zeros(nc), np.zeros(nc), np.zeros(nv_opd), np.zeros(nv_opd), np.zeros(nv_opd)]
+        self.L.orc_output_ptcldist(C.byref(self.p), isp, R, npa, self._ptrs(states, "x"), self._ptrs(states, "v"),
+                                   self._ptrs(states, "p"), self._ptrs(states, "w"), nx_opd, nv_opd, float(v_max),
+                                   *[_dp(o) for o in outs])
+        return dict(zip(("markr_xv", "total_xv", "pertb_xv", "markr_v", "total_v", "pertb_v"), outs))
 
     def particle_load(self, isp, al_int, mype, warmup, nlocal, ninit_total):
         x, v, pp, w = (np.zeros(nlocal) for _ in range(4))

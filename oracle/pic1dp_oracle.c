@@ -287,6 +287,142 @@ double orc_field_energy(const orc_params *p, const double *E) {
   return nrm * nrm * p->lx / (double)p->nx;
 }
 
+/* src/pic1dp_output.F90:117-172 */
+void orc_output_field(const orc_params *p, int nranks, const int64_t *np, double **v, double **pp, double **w,
+                      const double *E, double *out) {
+  out[0] = orc_field_energy(p, E);
+  for (int s = 0; s < p->nspecies; s++) {
+    double vv = 0.0, vvp = 0.0, vvw = 0.0;
+    for (int r = 0; r < nranks; r++) {
+      const int k = s * nranks + r;
+      double a = 0.0, b = 0.0, c = 0.0;
+      for (int64_t i = 0; i < np[k]; i++) {
+        const double t1 = v[k][i] * v[k][i]; /* :128 */
+        a += t1;                             /* :133 */
+        b += t1 * pp[k][i];                  /* :138-141 */
+        if (p->deltaf == 1) c += t1 * w[k][i]; /* :147-150 */
+      }
+      vv = (r == 0) ? a : vv + a;
+      vvp = (r == 0) ? b : vvp + b;
+      vvw = (r == 0) ? c : vvw + c;
+    }
+    out[1 + 3 * s] = vv;
+    out[2 + 3 * s] = vvp;
+    double energy;
+    if (p->deltaf == 1) {
+      energy = vvw;
+      if (p->linear == 1) out[2 + 3 * s] = out[2 + 3 * s] + energy; /* :154 */
+    } else {
+      energy = vvp;
+      if (p->iptcldist == 1)
+        energy = energy - 3.0 * p->density[s] * p->lx; /* :160 */
+      else if (p->iptcldist == 0)
+        energy = energy - p->temperature[s] / p->mass[s] * p->density[s] * p->lx; /* :166-168 */
+    }
+    out[3 + 3 * s] = energy; /* :171 */
+  }
+}
+
+/* src/pic1dp_output.F90:196-477 */
+void orc_output_ptcldist(const orc_params *p, int isp, int nranks, const int64_t *np, double **x, double **v,
+                         double **pp, double **w, int nx_opd, int nv_opd, double v_max, double *markr_xv,
+                         double *total_xv, double *pertb_xv, double *markr_v, double *total_v, double *pertb_v) {
+  const int nc = nx_opd * nv_opd;
+  const double delv_inv = (double)(nv_opd - 1) / (2.0 * v_max); /* :207-208 */
+  const double delx_inv = (double)nx_opd / p->lx;               /* :209 */
+  double *mxv = (double *)malloc(sizeof(double) * nc), *txv = (double *)malloc(sizeof(double) * nc);
+  double *pxv = (double *)malloc(sizeof(double) * nc);
+  double *mv = (double *)malloc(sizeof(double) * nv_opd), *tv = (double *)malloc(sizeof(double) * nv_opd);
+  double *pv_ = (double *)malloc(sizeof(double) * nv_opd);
+  for (int r = 0; r < nranks; r++) {
+    const int k = isp * nranks + r;
+    for (int c = 0; c < nc; c++) mxv[c] = txv[c] = pxv[c] = 0.0;
+    for (int c = 0; c < nv_opd; c++) mv[c] = tv[c] = pv_[c] = 0.0;
+    for (int64_t ip = 0; ip < np[k]; ip++) {
+      const double vi = v[k][ip];
+      if (fabs(vi) >= v_max) continue; /* :241 */
+      double sx = x[k][ip] / p->lx * (double)nx_opd; /* :243 */
+      int ix = (int)floor(sx);
+      sx = 1.0 - (sx - (double)ix);
+      double sv = (vi + v_max) / (v_max * 2.0) * (double)(nv_opd - 1); /* :247-248 */
+      const int iv = (int)floor(sv);
+      sv = 1.0 - (sv - (double)iv);
+      if (ix >= nx_opd) { /* x == lx exactly: out of bounds in the reference; defined as cell 0, weight 1 */
+        ix = 0;
+        sx = 1.0;
+      }
+      const double P = pp[k][ip], W = (p->deltaf == 1) ? w[k][ip] : 0.0;
+      mxv[iv * nx_opd + ix] += sx * sv;
+      txv[iv * nx_opd + ix] += sx * sv * P;
+      if (p->deltaf == 1) pxv[iv * nx_opd + ix] += sx * sv * W;
+      mxv[(iv + 1) * nx_opd + ix] += sx * (1.0 - sv);
+      txv[(iv + 1) * nx_opd + ix] += sx * (1.0 - sv) * P;
+      if (p->deltaf == 1) pxv[(iv + 1) * nx_opd + ix] += sx * (1.0 - sv) * W;
+      ix = ix + 1;
+      if (ix > nx_opd - 1) ix = 0; /* :272 */
+      sx = 1.0 - sx;               /* :273 */
+      mxv[iv * nx_opd + ix] += sx * sv;
+      txv[iv * nx_opd + ix] += sx * sv * P;
+      if (p->deltaf == 1) pxv[iv * nx_opd + ix] += sx * sv * W;
+      mxv[(iv + 1) * nx_opd + ix] += sx * (1.0 - sv);
+      txv[(iv + 1) * nx_opd + ix] += sx * (1.0 - sv) * P;
+      if (p->deltaf == 1) pxv[(iv + 1) * nx_opd + ix] += sx * (1.0 - sv) * W;
+      mv[iv] += sv; /* :297-312 */
+      tv[iv] += sv * P;
+      if (p->deltaf == 1) pv_[iv] += sv * W;
+      mv[iv + 1] += (1.0 - sv);
+      tv[iv + 1] += (1.0 - sv) * P;
+      if (p->deltaf == 1) pv_[iv + 1] += (1.0 - sv) * W;
+    }
+    if (p->linear == 1) { /* :326-329 */
+      for (int c = 0; c < nc; c++) txv[c] = txv[c] + pxv[c];
+      for (int c = 0; c < nv_opd; c++) tv[c] = tv[c] + pv_[c];
+    }
+    for (int c = 0; c < nc; c++) { /* MPI_Reduce, rank order */
+      markr_xv[c] = (r == 0) ? mxv[c] : markr_xv[c] + mxv[c];
+      total_xv[c] = (r == 0) ? txv[c] : total_xv[c] + txv[c];
+      pertb_xv[c] = (r == 0) ? pxv[c] : pertb_xv[c] + pxv[c];
+    }
+    for (int c = 0; c < nv_opd; c++) {
+      markr_v[c] = (r == 0) ? mv[c] : markr_v[c] + mv[c];
+      total_v[c] = (r == 0) ? tv[c] : total_v[c] + tv[c];
+      pertb_v[c] = (r == 0) ? pv_[c] : pertb_v[c] + pv_[c];
+    }
+  }
+  for (int c = 0; c < nc; c++) { /* :362-363 */
+    markr_xv[c] = markr_xv[c] * delx_inv * delv_inv;
+    total_xv[c] = total_xv[c] * delx_inv * delv_inv;
+  }
+  for (int c = 0; c < nv_opd; c++) {
+    markr_v[c] = markr_v[c] * delv_inv;
+    total_v[c] = total_v[c] * delv_inv;
+  }
+  if (p->deltaf == 1) {
+    for (int c = 0; c < nc; c++) pertb_xv[c] = pertb_xv[c] * delx_inv * delv_inv;
+    for (int c = 0; c < nv_opd; c++) pertb_v[c] = pertb_v[c] * delv_inv;
+  } else { /* :371-455 */
+    const double n = p->density[isp], v0 = p->v0[isp], T = p->temperature[isp], T2 = p->temperature2[isp];
+    const double m = p->mass[isp];
+    for (int iv = 0; iv < nv_opd; iv++) {
+      const double sv = ((double)iv / (double)(nv_opd - 1) * 2.0 - 1.0) * v_max;
+      double f0;
+      if (p->iptcldist == 1)
+        f0 = n * (sv * sv) * exp(-(sv * sv) / 2.0) / sqrt(2.0 * ORC_PI);
+      else if (p->iptcldist == 2)
+        f0 = n * (exp(-((sv + v0) * (sv + v0)) / (2.0 * T / m)) + exp(-((sv - v0) * (sv - v0)) / (2.0 * T / m))) /
+             (sqrt(8.0 * ORC_PI) * T / m);
+      else if (p->iptcldist == 3)
+        f0 = n * exp(-(sv * sv) / (2.0 * T / m)) / (sqrt(2.0 * ORC_PI) * T / m) +
+             (1.0 - n) * exp(-((sv - v0) * (sv - v0)) / (2.0 * T2 / m)) / (sqrt(2.0 * ORC_PI) * T2 / m);
+      else
+        f0 = n * exp(-((sv - v0) * (sv - v0)) / (2.0 * T / m)) / (sqrt(2.0 * ORC_PI) * T / m);
+      for (int ix = 0; ix < nx_opd; ix++) pertb_xv[iv * nx_opd + ix] = total_xv[iv * nx_opd + ix] - f0;
+      pertb_v[iv] = total_v[iv] - p->lx * f0;
+    }
+  }
+  free(mxv); free(txv); free(pxv); free(mv); free(tv); free(pv_);
+}
+
 void orc_petsc_decide(int64_t n, int npe, int rank, int64_t *low, int64_t *high) {
   int64_t base = n / npe, rem = n % npe;
   int64_t lo = base * rank + (rank < rem ? rank : rem);

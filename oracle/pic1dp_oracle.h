@@ -94,6 +94,17 @@ double orc_dlnf0(const orc_params *p, int isp, double v);
 /* ---- diagnostics: src/pic1dp_output.F90:117-124 ---- */
 double orc_field_energy(const orc_params *p, const double *E);
 
+/* ---- output_field scalars: src/pic1dp_output.F90:117-172.  Per-rank sequential sums (VecSum), added in rank order.
+ * out[0] = energy, out[1+3s..3+3s] per species.  x/v/p/w: [nspecies*nranks] pointers, species-major. ---- */
+void orc_output_field(const orc_params *p, int nranks, const int64_t *np, double **v, double **pp, double **w,
+                      const double *E, double *out);
+
+/* ---- output_ptcldist for one species: src/pic1dp_output.F90:196-477 (per-rank histograms, MPI_Reduce in rank
+ * order, scaling, linear / full-f post-processing).  Arrays sized nx_opd*nv_opd and nv_opd. ---- */
+void orc_output_ptcldist(const orc_params *p, int isp, int nranks, const int64_t *np, double **x, double **v,
+                         double **pp, double **w, int nx_opd, int nv_opd, double v_max, double *markr_xv,
+                         double *total_xv, double *pertb_xv, double *markr_v, double *total_v, double *pertb_v);
+
 /* ---- loader: src/pic1dp_particle.F90:172-264 with multirand (seed_type 1, constant seeds) ----
  * nlocal markers of species isp for rank mype; arrays x,v,pp,w length nlocal. */
 void orc_particle_load(const orc_params *p, int isp, int al_int, int mype, int warmup, int64_t nlocal,

@@ -71,6 +71,7 @@ EXPORTS = [
     "pic1dp_gpu_set_markers", "pic1dp_gpu_get_markers", "pic1dp_gpu_compute_shape_x", "pic1dp_gpu_get_shape_x",
     "pic1dp_gpu_collect_charge", "pic1dp_gpu_solve_field", "pic1dp_gpu_push", "pic1dp_gpu_step",
     "pic1dp_gpu_get_field", "pic1dp_gpu_set_field", "pic1dp_gpu_get_operators", "pic1dp_gpu_field_energy",
+    "pic1dp_gpu_output_field", "pic1dp_gpu_output_ptcldist",
     "pic1dp_gpu_sync", "pic1dp_gpu_timer_start", "pic1dp_gpu_timer_stop", "pic1dp_gpu_get_counters",
     "pic1dp_gpu_profile_step",
 ]
@@ -117,6 +118,8 @@ def load() -> C.CDLL:
     L.pic1dp_gpu_set_field.argtypes = [vp, dp, dp]
     L.pic1dp_gpu_get_operators.argtypes = [vp, dp, dp, dp]
     L.pic1dp_gpu_field_energy.argtypes = [vp, dp]
+    L.pic1dp_gpu_output_field.argtypes = [vp, dp]
+    L.pic1dp_gpu_output_ptcldist.argtypes = [vp, i32, i32, i32, C.c_double, dp, dp, dp, dp, dp, dp]
     L.pic1dp_gpu_sync.argtypes = [vp]
     L.pic1dp_gpu_timer_start.argtypes = [vp]
     L.pic1dp_gpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]

@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 
+#include "diag_kernels.cuh"
 #include "field_kernels.cuh"
 #include "particle_kernels.cuh"
 
@@ -90,6 +91,9 @@ struct pic1dp_gpu {
   double *d_partial = nullptr, *d_red = nullptr, *d_energy = nullptr;
   unsigned long long *d_noob = nullptr;
   std::vector<double> h_Fre, h_Fim, h_ginv;
+  // diagnostics scratch (allocated on first use)
+  double *d_diag_part = nullptr, *d_diag_sums = nullptr, *d_hist = nullptr, *d_hist_out = nullptr;
+  int diag_grid = 0, hist_cells = 0, hist_copies = 16;
   int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0, cfg = -1;
   bool partial_valid = false;  // a fused push has already deposited into d_partial
   int nred = 1;
@@ -296,7 +300,8 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
     }
     if (S.p) cudaFree(S.p);
   }
-  double *bufs[] = {h->d_E, h->d_rho, h->d_mre, h->d_mim, h->d_Fre, h->d_Fim, h->d_ginv, h->d_partial, h->d_red, h->d_energy};
+  double *bufs[] = {h->d_E, h->d_rho, h->d_mre, h->d_mim, h->d_Fre, h->d_Fim, h->d_ginv, h->d_partial, h->d_red, h->d_energy,
+                    h->d_diag_part, h->d_diag_sums, h->d_hist, h->d_hist_out};
   for (double *b : bufs)
     if (b) cudaFree(b);
   if (h->d_noob) cudaFree(h->d_noob);
@@ -815,6 +820,179 @@ int pic1dp_gpu_field_energy(pic1dp_gpu_t *h, double *energy) {
   CK(cudaMemcpyAsync(energy, h->d_energy, 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->d2h += 8;
+  return PIC1DP_OK;
+}
+
+static int allreduce_inplace(pic1dp_gpu_t *h, double *buf, size_t count) {
+  if (h->p.nranks == 1) return PIC1DP_OK;
+  if (!h->comm) { h->err = "nranks > 1 but comm_init was not called"; return PIC1DP_ESTATE; }
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->stream);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r); return PIC1DP_ENCCL; }
+  h->nccl_calls++;
+  return PIC1DP_OK;
+}
+
+static int diag_setup(pic1dp_gpu_t *h, int ncell) {
+  if (!h->d_diag_part) {
+    h->diag_grid = h->nsm * 4;
+    CK(cudaMalloc(&h->d_diag_part, (size_t)h->diag_grid * 3 * 8));
+    CK(cudaMalloc(&h->d_diag_sums, (size_t)3 * PIC1DP_MAX_SPECIES * 8));
+  }
+  if (ncell > h->hist_cells) {
+    if (h->d_hist) cudaFree(h->d_hist);
+    if (h->d_hist_out) cudaFree(h->d_hist_out);
+    h->d_hist = h->d_hist_out = nullptr;
+    CK(cudaMalloc(&h->d_hist, (size_t)h->hist_copies * 3 * ncell * 8));
+    CK(cudaMalloc(&h->d_hist_out, (size_t)3 * ncell * 8));
+    CK(cudaMemsetAsync(h->d_hist, 0, (size_t)h->hist_copies * 3 * ncell * 8, h->stream));
+    h->hist_cells = ncell;
+  }
+  return PIC1DP_OK;
+}
+
+static void fill_diag_args(pic1dp_gpu_t *h, int s, DiagArgs &a) {
+  Species &S = h->sp[s];
+  memset(&a, 0, sizeof(a));
+  a.x = S.x[S.cur];
+  a.v = S.v[S.cur];
+  a.p = S.p;
+  a.w = S.w[S.cur];
+  a.np = S.np;
+  a.deltaf = h->p.deltaf;
+  a.sum_partial = h->d_diag_part;
+  a.lx = h->p.lx;
+  a.hist = h->d_hist;
+  a.ncopies = h->hist_copies;
+}
+
+int pic1dp_gpu_output_field(pic1dp_gpu_t *h, double *scalars) {
+  if (!h || !scalars) return PIC1DP_EINVAL;
+  int rc = check_loaded(h, "output_field");
+  if (rc) return rc;
+  CK(cudaSetDevice(h->p.device));
+  rc = diag_setup(h, 0);
+  if (rc) return rc;
+  const pic1dp_params &p = h->p;
+  for (int s = 0; s < p.nspecies; s++) {
+    DiagArgs a;
+    fill_diag_args(h, s, a);
+    k_diag<true, false><<<h->diag_grid, 512, 0, h->stream>>>(a);
+    CKL(h);
+    k_diag_sums_final<<<1, 32, 0, h->stream>>>(h->d_diag_part, h->diag_grid, h->d_diag_sums + 3 * s);
+    CKL(h);
+  }
+  rc = allreduce_inplace(h, h->d_diag_sums, (size_t)3 * p.nspecies);  // VecSum is collective
+  if (rc) return rc;
+  GridArgs g;
+  fill_grid_args(h, g);
+  k_field_energy<<<1, 1024, 0, h->stream>>>(g);
+  CKL(h);
+  double sums[3 * PIC1DP_MAX_SPECIES];
+  CK(cudaMemcpyAsync(sums, h->d_diag_sums, (size_t)3 * p.nspecies * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&scalars[0], h->d_energy, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->d2h += 8 + 3 * p.nspecies * 8;
+  for (int s = 0; s < p.nspecies; s++) {
+    const double vv = sums[3 * s], vvp = sums[3 * s + 1], vvw = sums[3 * s + 2];
+    scalars[1 + 3 * s] = vv;       // src/pic1dp_output.F90:135
+    scalars[2 + 3 * s] = vvp;      // :143
+    double energy;
+    if (p.deltaf == 1) {
+      energy = vvw;                                              // :150
+      if (p.linear == 1) scalars[2 + 3 * s] = vvp + energy;      // :154
+    } else {
+      energy = vvp;  // "at this point energy is total energy"   // :157
+      if (p.iptcldist == 1) energy = energy - 3.0 * p.density[s] * p.lx;                                   // :160
+      else if (p.iptcldist == 0) energy = energy - p.temperature[s] / p.mass[s] * p.density[s] * p.lx;     // :166-168
+    }
+    scalars[3 + 3 * s] = energy;   // :171
+  }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int32_t nv_opd, double v_max,
+                               double *markr_xv, double *total_xv, double *pertb_xv, double *markr_v,
+                               double *total_v, double *pertb_v) {
+  if (!h || isp < 0 || isp >= h->p.nspecies || nx_opd < 1 || nv_opd < 2 || !(v_max > 0.0) ||
+      (int64_t)nx_opd * nv_opd > (1 << 22)) {
+    if (h) h->err = "output_ptcldist: bad argument";
+    return PIC1DP_EINVAL;
+  }
+  int rc = check_loaded(h, "output_ptcldist");
+  if (rc) return rc;
+  CK(cudaSetDevice(h->p.device));
+  const int ncell = nx_opd * nv_opd;
+  rc = diag_setup(h, ncell);
+  if (rc) return rc;
+  const pic1dp_params &p = h->p;
+  DiagArgs a;
+  fill_diag_args(h, isp, a);
+  a.nx_opd = nx_opd;
+  a.nv_opd = nv_opd;
+  a.v_max = v_max;
+  k_diag<false, true><<<h->diag_grid, 512, 0, h->stream>>>(a);
+  CKL(h);
+  // the private copies are laid out for hist_cells; only the first 3*ncell entries of each copy are used
+  // (stride between copies is 3*ncell of THIS call, see k_diag), so reduce with the same stride
+  k_diag_hist_final<<<(3 * ncell + 255) / 256, 256, 0, h->stream>>>(h->d_hist, h->hist_copies, 3 * ncell, h->d_hist_out);
+  CKL(h);
+  rc = allreduce_inplace(h, h->d_hist_out, (size_t)3 * ncell);  // MPI_Reduce :333-357 (every rank gets the sum)
+  if (rc) return rc;
+  std::vector<double> raw((size_t)3 * ncell);
+  CK(cudaMemcpyAsync(raw.data(), h->d_hist_out, (size_t)3 * ncell * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->d2h += (int64_t)3 * ncell * 8;
+  double *m_xv = raw.data(), *t_xv = m_xv + ncell, *p_xv = t_xv + ncell;
+  std::vector<double> m_v(nv_opd, 0.0), t_v(nv_opd, 0.0), p_v(nv_opd, 0.0);
+  for (int iv = 0; iv < nv_opd; iv++)  // v-only histograms = sums over x of the x-v ones (sx + (1-sx) = 1)
+    for (int ix = 0; ix < nx_opd; ix++) {
+      m_v[iv] += m_xv[iv * nx_opd + ix];
+      t_v[iv] += t_xv[iv * nx_opd + ix];
+      p_v[iv] += p_xv[iv * nx_opd + ix];
+    }
+  if (p.linear == 1) {  // :326-329
+    for (int c = 0; c < ncell; c++) t_xv[c] = t_xv[c] + p_xv[c];
+    for (int iv = 0; iv < nv_opd; iv++) t_v[iv] = t_v[iv] + p_v[iv];
+  }
+  const double delv_inv = (double)(nv_opd - 1) / (2.0 * v_max);  // :207-208
+  const double delx_inv = (double)nx_opd / p.lx;                 // :209
+  for (int c = 0; c < ncell; c++) {                              // :362-363
+    m_xv[c] = m_xv[c] * delx_inv * delv_inv;
+    t_xv[c] = t_xv[c] * delx_inv * delv_inv;
+  }
+  for (int iv = 0; iv < nv_opd; iv++) {                          // :364-365
+    m_v[iv] = m_v[iv] * delv_inv;
+    t_v[iv] = t_v[iv] * delv_inv;
+  }
+  if (p.deltaf == 1) {                                           // :366-369
+    for (int c = 0; c < ncell; c++) p_xv[c] = p_xv[c] * delx_inv * delv_inv;
+    for (int iv = 0; iv < nv_opd; iv++) p_v[iv] = p_v[iv] * delv_inv;
+  } else {                                                       // :371-455: subtract the equilibrium
+    const double PETSC_PI = 3.14159265358979323846264338327950288419716939937510582;
+    const double n = p.density[isp], v0 = p.v0[isp], T = p.temperature[isp], T2 = p.temperature2[isp], m = p.mass[isp];
+    for (int iv = 0; iv < nv_opd; iv++) {
+      const double sv = ((double)iv / (double)(nv_opd - 1) * 2.0 - 1.0) * v_max;  // :374-375
+      double f0;
+      if (p.iptcldist == 1)
+        f0 = n * (sv * sv) * exp(-(sv * sv) / 2.0) / sqrt(2.0 * PETSC_PI);
+      else if (p.iptcldist == 2)
+        f0 = n * (exp(-((sv + v0) * (sv + v0)) / (2.0 * T / m)) + exp(-((sv - v0) * (sv - v0)) / (2.0 * T / m))) /
+             (sqrt(8.0 * PETSC_PI) * T / m);
+      else if (p.iptcldist == 3)
+        f0 = n * exp(-(sv * sv) / (2.0 * T / m)) / (sqrt(2.0 * PETSC_PI) * T / m) +
+             (1.0 - n) * exp(-((sv - v0) * (sv - v0)) / (2.0 * T2 / m)) / (sqrt(2.0 * PETSC_PI) * T2 / m);
+      else
+        f0 = n * exp(-((sv - v0) * (sv - v0)) / (2.0 * T / m)) / (sqrt(2.0 * PETSC_PI) * T / m);
+      for (int ix = 0; ix < nx_opd; ix++) p_xv[iv * nx_opd + ix] = t_xv[iv * nx_opd + ix] - f0;
+      p_v[iv] = t_v[iv] - p.lx * f0;
+    }
+  }
+  if (markr_xv) memcpy(markr_xv, m_xv, (size_t)ncell * 8);
+  if (total_xv) memcpy(total_xv, t_xv, (size_t)ncell * 8);
+  if (pertb_xv) memcpy(pertb_xv, p_xv, (size_t)ncell * 8);
+  if (markr_v) memcpy(markr_v, m_v.data(), (size_t)nv_opd * 8);
+  if (total_v) memcpy(total_v, t_v.data(), (size_t)nv_opd * 8);
+  if (pertb_v) memcpy(pertb_v, p_v.data(), (size_t)nv_opd * 8);
   return PIC1DP_OK;
 }
 

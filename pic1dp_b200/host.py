@@ -174,6 +174,20 @@ class Pic1dGpu:
         self._ck(self.L.pic1dp_gpu_field_energy(self._h, C.byref(e)), "field_energy")
         return e.value
 
+    # ---- on-device diagnostics of pic1dp_output ----
+    def output_field(self) -> np.ndarray:
+        """[|E|^2 lx/nx, then per species sum v^2, sum v^2 p, sum v^2 w | perturbed energy] (output_field)."""
+        out = np.empty(1 + 3 * self.params.nspecies)
+        self._ck(self.L.pic1dp_gpu_output_field(self._h, _dp(out)), "output_field")
+        return out
+
+    def output_ptcldist(self, isp: int, nx_opd: int = 64, nv_opd: int = 64, v_max: float = 8.0):
+        nc = nx_opd * nv_opd
+        outs = [np.empty(nc), np.empty(nc), np.empty(nc), np.empty(nv_opd), np.empty(nv_opd), np.empty(nv_opd)]
+        self._ck(self.L.pic1dp_gpu_output_ptcldist(self._h, isp, nx_opd, nv_opd, float(v_max), *[_dp(o) for o in outs]),
+                 "output_ptcldist")
+        return dict(zip(("markr_xv", "total_xv", "pertb_xv", "markr_v", "total_v", "pertb_v"), outs))
+
     # ---- instrumentation ----
     def sync(self):
         self._ck(self.L.pic1dp_gpu_sync(self._h), "sync")

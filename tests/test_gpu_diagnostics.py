@@ -1,0 +1,104 @@
+"""On-device diagnostics against the oracle's restatement of output_field / output_ptcldist,
+and the pic1dp.out writer against the py3 restatement of the reference's reader."""
+import numpy as np
+import pytest
+
+import pic1dp_b200 as P
+from helpers import OracleRun, copy_state, make_params, rel_err, synth_markers
+from pic1dp_b200.output import OutputWriter
+from tools_py3.output_data import OutputData
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["deltaf", "linear", "fullf_maxwell", "fullf_bump", "two_species"])
+def test_output_field_and_ptcldist_match_oracle(case):
+    kw, nsp = dict(nx=192, capacity=120000), 1
+    if case == "linear":
+        kw.update(linear=1)
+    elif case == "fullf_maxwell":
+        kw.update(deltaf=0, iptcldist=0, density=[1.0], v0=[0.5], temperature=[1.2])
+    elif case == "fullf_bump":
+        kw.update(deltaf=0)
+    elif case == "two_species":
+        nsp = 2
+        kw.update(nspecies=2, charge=[-1.0, 1.0], mass=[1.0, 4.0], temperature=[1.0, 0.5], temperature2=[1.0, 0.5],
+                  density=[0.9, 1.0], v0=[5.0, 0.0])
+    op, gp = make_params(**kw)
+    sts = [synth_markers(op, 120000 - 11 * s, seed=60 + s, isp=s) for s in range(nsp)]
+    for st in sts:
+        st["v"][:50] = np.linspace(-9.0, 9.0, 50)  # some |v| >= v_max markers must be skipped by the histogram
+        st["x"][50] = op.lx                          # x == lx exactly
+    ref = OracleRun(op, [[copy_state(s)] for s in sts])
+    ref.init_field()
+    ref.step()
+    with P.Pic1dGpu(gp) as g:
+        for s, st in enumerate(sts):
+            g.set_markers(s, st["x"], st["v"], st["p"], st["w"])
+        g.collect_charge()
+        g.solve_field()
+        g.step(1)
+        sc = g.output_field()
+        sc_ref = ref.o.output_field(ref.st, ref.E)
+        # sums of positive terms: relative tolerance on each; the perturbed sums cancel -> relative to sum |terms|
+        assert abs(sc[0] / sc_ref[0] - 1.0) < 1e-12
+        for s in range(nsp):
+            v, p, w = (ref.st[s][0][k] for k in ("v", "p", "w"))
+            scales = [np.sum(v * v), np.sum(v * v * np.abs(p)), np.sum(v * v * np.abs(p)) if op.deltaf == 0 else np.sum(v * v * np.abs(w))]
+            for q in range(3):
+                assert abs(sc[1 + 3 * s + q] - sc_ref[1 + 3 * s + q]) < 1e-12 * scales[q], (case, s, q)
+        for s in range(nsp):
+            d = g.output_ptcldist(s, 64, 64, 8.0)
+            dr = ref.o.output_ptcldist(ref.st, s, 64, 64, 8.0)
+            for k in d:
+                scale = np.max(np.abs(dr["total_xv" if k.endswith("xv") else "total_v"])) if "pertb" in k and op.deltaf == 0 \
+                    else np.max(np.abs(dr[k]))
+                assert rel_err(d[k], dr[k], scale) < 1e-11, (case, s, k)
+            # the v-only histograms are the x-integrals of the x-v ones
+            assert rel_err(d["markr_xv"].reshape(64, 64).sum(axis=1) * op.lx / 64, d["markr_v"]) < 1e-12
+
+
+def test_ptcldist_odd_grid_sizes_and_repeat_calls():
+    op, gp = make_params(nx=192, capacity=50000)
+    st = synth_markers(op, 50000, seed=70)
+    ref = OracleRun(op, [[copy_state(st)]])
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        for nxo, nvo, vm in ((64, 64, 8.0), (16, 8, 4.0), (100, 33, 8.0), (64, 64, 8.0)):
+            d = g.output_ptcldist(0, nxo, nvo, vm)
+            dr = ref.o.output_ptcldist(ref.st, 0, nxo, nvo, vm)
+            for k in d:
+                assert rel_err(d[k], dr[k]) < 1e-11, (nxo, nvo, k)
+
+
+def test_output_file_is_readable_by_the_reference_reader_layout(tmp_path):
+    """100 steps of a quiet-start run written as pic1dp.out every 10 steps; the py3 OutputData restatement reads it
+    back: header, scalars, fields, distributions; growth rate fit works on the file."""
+    from test_gpu_physics import quiet_start
+    op, gp = make_params(nx=192, capacity=400000)
+    st = quiet_start(op, 500, 800)
+    path = tmp_path / "pic1dp.out"
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        g.collect_charge()
+        g.solve_field()
+        with OutputWriter(path, g) as out:
+            out.output_all(0.0)
+            for k in range(1, 61):
+                g.step(10)
+                last = out.output_all(0.5 * k)
+        fld = g.get_field()
+        h2d, d2h = g.counters().h2d_bytes, g.counters().d2h_bytes
+    od = OutputData(str(path))
+    assert (od.nspecies, od.nmode, od.nx, od.nx_pd, od.nv_pd) == (1, 1, 192, 64, 64)
+    assert od.lx == op.lx and od.v_max == 8.0 and od.ntime == 61
+    sc = od.get_scalar_t()
+    assert np.allclose(sc[0], 0.5 * np.arange(61)) and sc[1, -1] == last[0]
+    assert np.array_equal(od.get_field_x(60)[0, :192], fld["electric"])
+    assert np.array_equal(od.get_mode_t()[1, -1:], fld["mode_im"])
+    f = od.get_ptcldist_xv(60, 0, 1)
+    assert f.shape == (64, 64) and abs(np.sum(f) * (op.lx / 64) * (16.0 / 63) - op.lx) < 0.02 * op.lx  # int f dx dv = n lx
+    gamma = od.growthrate_energy_fit(15.0, 30.0) / 2.0
+    assert abs(gamma / 0.0838311 - 1.0) < 0.05
+    # no marker array ever crossed PCIe after the initial load
+    assert d2h < 61 * (3 * 64 * 64 + 4 * 192 + 64) * 8 * 2
