@@ -11,8 +11,8 @@ weak scaling; markers are synthetic (numpy PCG64, seed = 1234 + rank) with the l
 
 Keys of the JSON line: see the measurement contract in DESIGN.md.  `value` = device-timed (CUDA events on the
 library's stream), markers resident in HBM; `e2e` = same metric through the C ABI with host (pinned) buffers:
-set_markers H2D inside the timed region, get_field D2H after every step and get_markers D2H at the reference's
-output cadence (every 10 steps, src/pic1dp_input.F90:250 / src/pic1dp.F90:98-108) and at the end.
+set_markers H2D inside the timed region, get_field D2H after every step and the output step at the reference's
+cadence (every 10 steps, src/pic1dp_input.F90:250 / src/pic1dp.F90:98-108) and at the end.
 """
 from __future__ import annotations
 
@@ -275,28 +275,41 @@ def main():
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
-        barrier()
-        h2d0, d2h0 = g.counters().h2d_bytes, g.counters().d2h_bytes
-        tw0 = time.perf_counter()
-        g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])   # H2D (particle_load -> device)
-        g.collect_charge()
-        g.solve_field()
-        for it in range(1, args.steps + 1):
-            g.step(1)
-            g.get_field_ptr(hf["E"].data_ptr(), hf["rho"].data_ptr(), hf["re"].data_ptr(), hf["im"].data_ptr())
-            if it % OUTPUT_EVERY == 0 or it == args.steps:               # output_all cadence: host needs x, v, w
-                g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], w=ptr["w"])
-        g.sync()
-        tw = time.perf_counter() - tw0
-        tw = max_over_ranks(tw)
-        cc = g.counters()
-        e2e = {"value": n * world * args.steps / tw, "unit": "particle-steps/s",
-               "h2d_bytes_per_step": (cc.h2d_bytes - h2d0) / args.steps,
-               "d2h_bytes_per_step": (cc.d2h_bytes - d2h0) / args.steps,
-               "ms_per_step": 1e3 * tw / args.steps,
-               "definition": "set_markers(pinned host) + K steps, get_field after every step, get_markers(x,v,w) "
-                             f"every {OUTPUT_EVERY} steps and at the end (reference output cadence); host wall clock, "
-                             "max over ranks"}
+        def e2e_run(mode, k):
+            """set_markers from pinned host memory + k steps; every step the fields come back to the host; every
+            OUTPUT_EVERY steps (and at the end) the output step runs: mode 'device' = output_field + output_ptcldist
+            reduced on the GPU (a few KB of D2H), mode 'host' = get_markers(x, v, w) so that the Fortran host's own
+            output code can run on fresh Vecs (24 B/marker of D2H)."""
+            barrier()
+            cc0 = g.counters()
+            t_0 = time.perf_counter()
+            g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])   # H2D (particle_load -> device)
+            g.collect_charge()
+            g.solve_field()
+            for it in range(1, k + 1):
+                g.step(1)
+                g.get_field_ptr(hf["E"].data_ptr(), hf["rho"].data_ptr(), hf["re"].data_ptr(), hf["im"].data_ptr())
+                if it % OUTPUT_EVERY == 0 or it == k:                        # output_all cadence
+                    if mode == "device":
+                        g.output_field()
+                        g.output_ptcldist(0, 64, 64, 8.0)
+                    else:
+                        g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], w=ptr["w"])
+            g.sync()
+            tw = max_over_ranks(time.perf_counter() - t_0)
+            cc = g.counters()
+            return {"value": n * world * k / tw, "unit": "particle-steps/s", "steps": k, "ms_per_step": 1e3 * tw / k,
+                    "h2d_bytes_per_step": (cc.h2d_bytes - cc0.h2d_bytes) / k,
+                    "d2h_bytes_per_step": (cc.d2h_bytes - cc0.d2h_bytes) / k}
+
+        e2e = e2e_run("device", args.steps)
+        e2e["definition"] = ("reference driver loop through the C ABI, host wall clock, max over ranks: set_markers "
+                             "(pinned host -> device, 32 B/marker) + K steps, get_field (E, rho, modes) to the host "
+                             f"after every step, output_all every {OUTPUT_EVERY} steps and at the end (reference "
+                             "cadence, src/pic1dp.F90:98-108) as pic1dp_gpu_output_field + pic1dp_gpu_output_ptcldist "
+                             "(device-side reductions, results to the host)")
+        e2e["host_refresh_outputs"] = e2e_run("host", args.steps)
+        e2e["host_refresh_outputs"]["definition"] = "same, but each output step is get_markers(x, v, w) to pinned host memory"
         # worst case: markers live on the host and make the round trip every step
         k2 = min(args.steps, 3)
         barrier()
@@ -311,6 +324,14 @@ def main():
         tw2 = max_over_ranks(time.perf_counter() - tw0)
         e2e["roundtrip_every_step"] = {"value": n * world * k2 / tw2, "steps": k2,
                                        "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n + (2 * nx + 2) * 8}
+        # device time of one output step
+        g.timer_start()
+        g.output_field()
+        t_of = g.timer_stop()
+        g.timer_start()
+        g.output_ptcldist(0, 64, 64, 8.0)
+        t_op = g.timer_stop()
+        e2e["output_step_ms"] = {"output_field": t_of, "output_ptcldist": t_op}
 
     # ---- CPU baseline beside it (rank 0, bounded sample) ----
     cpu = None
