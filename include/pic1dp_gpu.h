@@ -51,8 +51,9 @@ enum {
 
 /* deposit (S^T w) strategies; all give the same sum up to fp64 summation order */
 enum {
-  PIC1DP_DEPOSIT_AUTO = 0,       /* fastest strategy whose grid fits (SMEM_ATOMIC, else GLOBAL_RED) */
-  PIC1DP_DEPOSIT_SMEM_ATOMIC = 1,/* per-CTA shared-memory grid, fp64 atomicAdd; CTA partials reduced in fixed order */
+  PIC1DP_DEPOSIT_AUTO = 0,       /* fastest strategy that fits: WARP_PRIVATE for nx <= 256, SMEM_ATOMIC, else GLOBAL_RED */
+  PIC1DP_DEPOSIT_SMEM_ATOMIC = 1,/* per-CTA shared-memory grid of {left,right} pairs, 128-bit CAS; CTA partials reduced
+                                    in fixed order */
   PIC1DP_DEPOSIT_GLOBAL_RED = 2, /* RED.ADD.F64 into an L2-resident per-CTA private grid */
   PIC1DP_DEPOSIT_WARP_PRIVATE = 3/* per-warp private shared-memory grid, lane-ordered duplicate merge: bitwise
                                     run-to-run deterministic ("deterministic deposition") */

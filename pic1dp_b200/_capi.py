@@ -16,7 +16,9 @@ OK, EINVAL, ECUDA, ENCCL, ENOMEM, ESTATE, ECAPACITY, ENODEVICE, EUNSUPPORTED = r
 DEPOSIT_AUTO, DEPOSIT_SMEM_ATOMIC, DEPOSIT_GLOBAL_RED, DEPOSIT_WARP_PRIVATE = range(4)
 FIELD_TREE, FIELD_SEQUENTIAL = range(2)
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpic1dp_b200.so")
+# PIC1DP_B200_LIB overrides the library path (kernel A/B experiments under scratch/); the product default is in-tree
+_LIB_PATH = os.environ.get("PIC1DP_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                               "libpic1dp_b200.so")
 
 
 class Params(C.Structure):

@@ -33,10 +33,11 @@ __constant__ double c_exp_poly[10] = {
 __constant__ double c_exp_red[3] = {0x1.71547652b82fep+0 /* log2 e */, 0x1.62e42fefa39efp-1 /* ln2 hi */,
                                     0x1.abc9e3b39803fp-56 /* ln2 lo */};
 
+__device__ double exp_slow(double a);
 __device__ __forceinline__ double exp_fast(double a) {
   const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
   const double t = fma(a, c_exp_red[0], magic);
-  int n = __double2loint(t);
+  const int n = __double2loint(t);
   const double nf = t - magic;
   double r = fma(nf, -c_exp_red[1], a);
   r = fma(nf, -c_exp_red[2], r);
@@ -44,51 +45,55 @@ __device__ __forceinline__ double exp_fast(double a) {
 #pragma unroll
   for (int k = 1; k < 10; k++) q = fma(q, r, c_exp_poly[k]);
   const double r2 = r * r;
-  double pr = fma(r2, q, r) + 1.0;  // in [0.70, 1.42]
-  if (!(fabs(a) <= 700.0)) {  // never reached by physical velocities; handled inline (no call in the hot loop)
-    if (a != a) return a;
-    if (a > 709.782712893384) return __longlong_as_double(0x7ff0000000000000LL);
-    if (a < -745.2) return 0.0;
-    const int n1 = n / 2;  // scale in two exact steps so that subnormal results round once
-    pr = pr * __hiloint2double((1023 + n1) << 20, 0);
-    n -= n1;
-    return pr * __hiloint2double((1023 + n) << 20, 0);
-  }
+  const double pr = fma(r2, q, r) + 1.0;  // in [0.70, 1.42]
+  if (__builtin_expect(!(fabs(a) <= 700.0), 0)) return exp_slow(a);  // never reached by physical velocities
   return __hiloint2double(__double2hiint(pr) + (n << 20), __double2loint(pr));  // * 2^n, |n| <= 1010
 }
 
-// ---- correctly rounded division without a slow-path call ---------------------------------------------------
+// ---- correctly rounded division with a straight-line fast path ---------------------------------------------
 // q0 = a*y, r = a - q0*b (exact, FMA), q1 = q0 + r*y is RN(a/b + d) with |d| <= 2^-104 |a/b| when y is 1/b to
-// ~1 ulp, so q1 can only be wrong when a/b lies within 2^-104 of a rounding midpoint.  The exact residual
-// r1 = a - q1*b settles it: RN(a/b) != q1 iff |r1| > b * ulp(q1) / 2, and then the neighbour towards r1 is the
-// answer.  (Not covered: q1 an exact power of two AND a/b that close to the midpoint just below it.)
-// Valid for b > 0 and |a|, b, |a/b| within 2^+-500; callers route anything else to the generic path.
-__device__ __forceinline__ double div_fix(double a, double b, double q1) {
+// ~1 ulp, so q1 can only differ from RN(a/b) when a/b lies within 2^-104 of a rounding midpoint.  The exact
+// residual r1 = a - q1*b detects that: RN(a/b) != q1 implies |r1| > b * ulp(q1) / 2; such operands (and anything
+// outside 2^+-500) are re-divided with the IEEE routine on a rare noinline path.  (Not covered: q1 an exact power
+// of two AND a/b within 2^-104 of the midpoint just below it, where the lower half-ulp is smaller.)
+// rare paths: IEEE division, libdevice exp, fmod
+// (measured: __noinline__ rare paths cost 7% on the irk=2 kernel -- ABI call sites constrain register allocation --
+// so they are inlined; __builtin_expect keeps them off the fall-through path)
+#ifdef PIC1DP_EXP_NOINLINE_RARE
+#define PIC1DP_RARE __noinline__
+#else
+#define PIC1DP_RARE __forceinline__
+#endif
+__device__ PIC1DP_RARE double div_slow(double a, double b) { return __ddiv_rn(a, b); }
+__device__ PIC1DP_RARE double exp_slow(double a) { return exp(a); }
+__device__ PIC1DP_RARE double wrap_slow(double x, double lx) {
+  double r = fmod(x, lx);
+  if (r < 0.0) r = __dadd_rn(r, lx);
+  return r;
+}
+
+// true when q1 (within an ulp of a/b) is NOT provably RN(a/b): |a - q1*b| > b*ulp(q1)/2
+__device__ __forceinline__ bool div_suspect(double a, double b, double q1) {
   const double r1 = fma(-q1, b, a);
   const int e = __double2hiint(q1) & 0x7ff00000;
   const double h = __hiloint2double(__double2hiint(b) + e - (1076 << 20), __double2loint(b));  // b * ulp(q1) / 2
-  if (__builtin_expect(fabs(r1) > h, 0)) {
-    // a/b = q1 + r1/b with b > 0: one ulp towards the residual = +-1 on the bit pattern
-    const long long step = ((r1 < 0.0) != (q1 < 0.0)) ? -1LL : 1LL;
-    q1 = __longlong_as_double(__double_as_longlong(q1) + step);
-  }
-  return q1;
+  return fabs(r1) > h;
 }
 
 // a / b for a constant divisor b > 0 with y = RN(1/b) precomputed on the host; a >= 0 (a marker coordinate).
-// a == 0, a < 2^-800 (residuals would underflow) and a < 0 take the generic division.
+// a == 0, a < 2^-800 (residuals would underflow), a < 0, NaN and the near-midpoint case take the IEEE division.
 __device__ __forceinline__ double div_const(double a, double b, double y) {
-  if (__builtin_expect(!(a >= 0x1p-800), 0)) return __ddiv_rn(a, b);
   const double q0 = a * y;
   const double r = fma(-q0, b, a);
-  return div_fix(a, b, fma(r, y, q0));
+  double q1 = fma(r, y, q0);
+  if (__builtin_expect(!(a >= 0x1p-800) || div_suspect(a, b, q1), 0)) q1 = div_slow(a, b);
+  return q1;
 }
 
 // general a / b, b > 0
 __device__ __forceinline__ double div_pos(double a, double b) {
   const unsigned eb = (unsigned)(__double2hiint(b) & 0x7ff00000) - (523u << 20);  // exponent of b in [-500, 500)
   const unsigned ea = (unsigned)(__double2hiint(a) & 0x7ff00000) - (523u << 20);
-  if (__builtin_expect(eb >= (1000u << 20) || ea >= (1000u << 20) || !(b > 0.0), 0)) return __ddiv_rn(a, b);
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));  // MUFU.RCP64H: ~20 good bits
   double e = fma(-b, y, 1.0);
@@ -98,7 +103,9 @@ __device__ __forceinline__ double div_pos(double a, double b) {
   y = fma(y, e, y);
   const double q0 = a * y;
   const double r = fma(-q0, b, a);
-  return div_fix(a, b, fma(r, y, q0));
+  double q1 = fma(r, y, q0);
+  if (__builtin_expect((eb | ea) >= (1000u << 20) || !(b > 0.0) || div_suspect(a, b, q1), 0)) q1 = div_slow(a, b);
+  return q1;
 }
 
 // Compile-time configuration of the model switches.  CFG < 0: read them from the kernel arguments (generic
@@ -149,10 +156,8 @@ struct ParticleArgs {
 __device__ __forceinline__ double wrap_x(double x, double lx) {
   double xw = (x >= lx) ? dsub(x, lx) : x;
   xw = (x < 0.0) ? dadd(x, lx) : xw;
-  if (!(x > -lx && x < dadd(lx, lx))) {  // more than one box length away (or NaN): the general definition
-    xw = fmod(x, lx);
-    if (xw < 0.0) xw = dadd(xw, lx);
-  }
+  // more than one box length away (or NaN): the general definition
+  if (__builtin_expect(!(x > -lx && x < dadd(lx, lx)), 0)) xw = wrap_slow(x, lx);
   return xw;
 }
 
@@ -262,14 +267,36 @@ enum { DEP_SMEM_ATOMIC = 1, DEP_GLOBAL_RED = 2, DEP_WARP_PRIVATE = 3 };
 template <int DEP>
 struct Depositor;
 
-// per-CTA shared grid, fp64 atomicAdd (lowers to an ATOMS.CAS loop on sm_100a)
+// per-CTA shared grid of pairs {sum of left weights landing in cell j, sum of right weights of markers whose LEFT
+// cell is j}: both contributions of a marker go to one 16-byte slot, so one ATOMS.CAS.128 loop replaces two 64-bit
+// CAS loops (sm_100a has no native fp64 shared atomic add).  rho[j] = pair[j].x + pair[j-1].y at flush time.
 template <>
 struct Depositor<DEP_SMEM_ATOMIC> {
-  double *g;
+  double *g;  // pair grid, 2*nx doubles
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
-    if (valid) {
-      atomicAdd(&g[ix], a);
-      atomicAdd(&g[ixr], b);
+    (void)ixr;
+    if (!valid) return;
+#ifdef PIC1DP_EXP_CAS64  // experiment: two 64-bit CAS loops on the same pair slot
+    atomicAdd(g + 2 * ix, a);
+    atomicAdd(g + 2 * ix + 1, b);
+    return;
+#endif
+    double2 *slot = reinterpret_cast<double2 *>(g) + ix;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
+    double2 old = *slot;
+    for (;;) {
+      const unsigned long long e0 = __double_as_longlong(old.x), e1 = __double_as_longlong(old.y);
+      const unsigned long long d0 = __double_as_longlong(dadd(old.x, a)), d1 = __double_as_longlong(dadd(old.y, b));
+      unsigned long long f0, f1;
+      asm volatile(
+          "{\n\t.reg .b128 c, d, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
+          "atom.shared.cas.b128 o, [%6], c, d;\n\tmov.b128 {%0, %1}, o;\n\t}"
+          : "=l"(f0), "=l"(f1)
+          : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "r"(addr)
+          : "memory");
+      if (f0 == e0 && f1 == e1) break;
+      old.x = __longlong_as_double(f0);
+      old.y = __longlong_as_double(f1);
     }
   }
 };
@@ -334,11 +361,12 @@ __device__ __forceinline__ double ld1(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
 __device__ __forceinline__ void st1(double *p, double v) { __stcs(p, v); }
 
-// Shared-memory layout of the particle kernels: [E : nx] [deposit grid(s) : nx * ngrids]
+// Shared-memory layout of the particle kernels: [E : nx rounded up to even] [deposit grid(s) : nx * ngrids]
+// (16-byte alignment of the pair grid for the 128-bit CAS)
 template <int DEP>
 __device__ __forceinline__ double *dep_setup(double *smem_after_E, int nx, double *my_partial) {
   if (DEP == DEP_SMEM_ATOMIC) {
-    for (int j = threadIdx.x; j < nx; j += blockDim.x) smem_after_E[j] = 0.0;
+    for (int j = threadIdx.x; j < 2 * nx; j += blockDim.x) smem_after_E[j] = 0.0;
     return smem_after_E;
   } else if (DEP == DEP_WARP_PRIVATE) {
     const int nw = blockDim.x >> 5;
@@ -353,7 +381,10 @@ template <int DEP>
 __device__ __forceinline__ void dep_flush(double *smem_after_E, int nx, double *my_partial) {
   if (DEP == DEP_SMEM_ATOMIC) {
     __syncthreads();
-    for (int j = threadIdx.x; j < nx; j += blockDim.x) my_partial[j] = smem_after_E[j];
+    for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+      const int jl = (j == 0) ? nx - 1 : j - 1;  // right weights of the cell to the left (periodic, :111-112)
+      my_partial[j] = dadd(smem_after_E[2 * j], smem_after_E[2 * jl + 1]);
+    }
   } else if (DEP == DEP_WARP_PRIVATE) {
     __syncthreads();
     const int nw = blockDim.x >> 5;
@@ -443,7 +474,7 @@ __global__ void __launch_bounds__(1024, 1) k_push(const ParticleArgs a) {
   for (int j = threadIdx.x; j < a.nx; j += blockDim.x) sE[j] = a.E[j];
   double *my_partial = FUSED ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
   Depositor<DEP> dep;
-  dep.g = FUSED ? dep_setup<DEP>(smem + a.nx, a.nx, my_partial) : nullptr;
+  dep.g = FUSED ? dep_setup<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial) : nullptr;
   __syncthreads();
 
   const int64_t tile = (int64_t)blockDim.x * 2;
@@ -455,7 +486,7 @@ __global__ void __launch_bounds__(1024, 1) k_push(const ParticleArgs a) {
     else
       push_pair<DIST, IRK2, DEP, FUSED, CFG, false>(a, sE, dep, i, noob);
   }
-  if (FUSED) dep_flush<DEP>(smem + a.nx, a.nx, my_partial);
+  if (FUSED) dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
   if (FUSED && noob) atomicAdd(a.noob, noob);
 }
 

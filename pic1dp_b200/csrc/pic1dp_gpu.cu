@@ -209,7 +209,8 @@ static PushKernel pick_deposit(int dep, bool deposit) {
   }
 }
 
-static int dep_grids(int dep, int threads) { return dep == DEP_WARP_PRIVATE ? threads / 32 : (dep == DEP_SMEM_ATOMIC ? 1 : 0); }
+// shared-memory deposit grids of nx doubles each (the atomic deposit keeps one grid of {left, right} pairs)
+static int dep_grids(int dep, int threads) { return dep == DEP_WARP_PRIVATE ? threads / 32 : (dep == DEP_SMEM_ATOMIC ? 2 : 0); }
 
 // ---- public API -----------------------------------------------------------------------------------------
 extern "C" {
@@ -342,20 +343,27 @@ static int create_impl(pic1dp_gpu_t *h) {
   // 32 warps.  Shared/global-atomic deposits run 2 CTAs x 512 threads; the warp-private deposit needs one grid
   // per warp in shared memory, so its CTA is as large as fits (multiple of 4 warps, <= 32).
   int dep = p.deposit_mode;
-  auto smem_need = [&](int d, int thr) { return (size_t)nx * 8 * (1 + dep_grids(d, thr)); };
+  auto smem_need = [&](int d, int thr) { return (size_t)8 * (((nx + 1) & ~1) + (size_t)nx * dep_grids(d, thr)); };
   auto warp_private_threads = [&]() {
-    int w = (int)(max_smem / ((size_t)nx * 8)) - 1;
+    int w = (int)((max_smem - 8) / ((size_t)nx * 8)) - 1;
     if (w > 32) w = 32;
     if (w >= 4) w &= ~3;
     return w * 32;
   };
-  if (dep == PIC1DP_DEPOSIT_AUTO) {  // fastest that fits; WARP_PRIVATE is the opt-in bitwise-deterministic mode
-    if (2 * smem_need(DEP_SMEM_ATOMIC, 512) + 2048 <= (size_t)prop.sharedMemPerMultiprocessor)
-      dep = DEP_SMEM_ATOMIC;
+  if (dep == PIC1DP_DEPOSIT_AUTO) {
+    // measured on B200 (profiles/r01_config_sweep.md): the warp-private deposit wins on small grids (nx <= 256: more
+    // intra-CTA contention for the CAS loop, and 32 private grids still fit), the 128-bit-CAS deposit elsewhere;
+    // RED.ADD.F64 to L2 only when the pair grid does not fit in shared memory.
+    if (nx <= 256 && warp_private_threads() >= 1024)
+      dep = DEP_WARP_PRIVATE;
     else if (smem_need(DEP_SMEM_ATOMIC, 512) <= max_smem)
       dep = DEP_SMEM_ATOMIC;
     else
       dep = DEP_GLOBAL_RED;
+  }
+  if (dep == DEP_WARP_PRIVATE && warp_private_threads() < 256) {
+    h->err = "WARP_PRIVATE deposit needs one nx-sized shared-memory grid per warp: fewer than 8 warps fit for this nx";
+    return PIC1DP_EUNSUPPORTED;
   }
   h->threads = (dep == DEP_WARP_PRIVATE) ? warp_private_threads() : 512;
   if (h->threads < 32 || smem_need(dep, h->threads) > max_smem) {
