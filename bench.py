@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--markers", type=float, default=1e8, help="markers per GPU")
     ap.add_argument("--nx", type=int, default=1024)
     ap.add_argument("--deposit", type=int, default=0, help="PIC1DP_DEPOSIT_* (0 = auto)")
+    ap.add_argument("--load-path", type=int, default=0, help="PIC1DP_LOAD_* (0 auto, 1 direct, 2 TMA ring)")
     ap.add_argument("--cpu-markers", type=float, default=2e7, help="markers of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -205,7 +206,7 @@ def main():
     import pic1dp_b200 as P
 
     n = int(args.markers)
-    gp = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit)
+    gp = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit, load_path=args.load_path)
     g = P.Pic1dGpu(gp)
     if world > 1:
         uid = [g.comm_unique_id() if rank == 0 else None]

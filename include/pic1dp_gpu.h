@@ -59,6 +59,13 @@ enum {
                                     run-to-run deterministic ("deterministic deposition") */
 };
 
+/* how the fused kernel reads marker arrays */
+enum {
+  PIC1DP_LOAD_AUTO = 0,
+  PIC1DP_LOAD_DIRECT = 1, /* 128-bit streaming loads into registers, 2 markers per thread */
+  PIC1DP_LOAD_TMA = 2     /* cp.async.bulk tiles into a shared-memory ring (mbarrier pipeline), 1 marker per thread */
+};
+
 /* field-solve summation order for the partial-DFT projections */
 enum {
   PIC1DP_FIELD_TREE = 0,      /* fixed-shape block tree reduction (deterministic, fast) */
@@ -103,7 +110,8 @@ typedef struct pic1dp_params {
   int32_t field_mode;                       /* PIC1DP_FIELD_* */
   int32_t fuse;                             /* 1: push also wraps x and deposits (collect_charge then only reduces);
                                                0: each call has exactly the reference's side effects */
-  int32_t reserved[8];
+  int32_t load_path;                        /* PIC1DP_LOAD_*: how marker tiles reach the SM (delta-f nonlinear kernels) */
+  int32_t reserved[7];
 } pic1dp_params;
 
 typedef struct pic1dp_gpu pic1dp_gpu_t; /* opaque handle: the module-global state of the three Fortran modules */

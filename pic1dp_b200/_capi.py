@@ -15,6 +15,7 @@ UNIQUE_ID_BYTES = 128
 OK, EINVAL, ECUDA, ENCCL, ENOMEM, ESTATE, ECAPACITY, ENODEVICE, EUNSUPPORTED = range(9)
 DEPOSIT_AUTO, DEPOSIT_SMEM_ATOMIC, DEPOSIT_GLOBAL_RED, DEPOSIT_WARP_PRIVATE = range(4)
 FIELD_TREE, FIELD_SEQUENTIAL = range(2)
+LOAD_AUTO, LOAD_DIRECT, LOAD_TMA = range(3)
 
 # PIC1DP_B200_LIB overrides the library path (kernel A/B experiments under scratch/); the product default is in-tree
 _LIB_PATH = os.environ.get("PIC1DP_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
@@ -48,7 +49,8 @@ class Params(C.Structure):
         ("deposit_mode", C.c_int32),
         ("field_mode", C.c_int32),
         ("fuse", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("load_path", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

@@ -108,6 +108,31 @@ __device__ __forceinline__ double div_pos(double a, double b) {
   return q1;
 }
 
+// two independent exponentials evaluated as interleaved straight-line code with a single rare-path test, so the
+// two 12-deep FMA chains overlap in the fp64 pipe
+__device__ __forceinline__ void exp_fast2(double a0, double a1, double &e0, double &e1) {
+  const double magic = 6755399441055744.0;
+  const double t0 = fma(a0, c_exp_red[0], magic), t1 = fma(a1, c_exp_red[0], magic);
+  const int n0 = __double2loint(t0), n1 = __double2loint(t1);
+  const double f0 = t0 - magic, f1 = t1 - magic;
+  double r0 = fma(f0, -c_exp_red[1], a0), r1 = fma(f1, -c_exp_red[1], a1);
+  r0 = fma(f0, -c_exp_red[2], r0);
+  r1 = fma(f1, -c_exp_red[2], r1);
+  double q0 = c_exp_poly[0], q1 = c_exp_poly[0];
+#pragma unroll
+  for (int k = 1; k < 10; k++) {
+    q0 = fma(q0, r0, c_exp_poly[k]);
+    q1 = fma(q1, r1, c_exp_poly[k]);
+  }
+  const double p0 = fma(r0 * r0, q0, r0) + 1.0, p1 = fma(r1 * r1, q1, r1) + 1.0;
+  e0 = __hiloint2double(__double2hiint(p0) + (n0 << 20), __double2loint(p0));
+  e1 = __hiloint2double(__double2hiint(p1) + (n1 << 20), __double2loint(p1));
+  if (__builtin_expect(!(fabs(a0) <= 700.0 && fabs(a1) <= 700.0), 0)) {  // never reached by physical velocities
+    e0 = exp_slow(a0);
+    e1 = exp_slow(a1);
+  }
+}
+
 // Compile-time configuration of the model switches.  CFG < 0: read them from the kernel arguments (generic
 // instantiation); CFG >= 0: bit 0 deltaf, bit 1 linear, bit 2 right_frac (iptclshape 1,2), bit 3 all constant
 // divisors are powers of two.  The specialised instantiations drop every select / uniform branch on them.
@@ -205,8 +230,8 @@ __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
     return dsub(v, ddiv(2.0, v));
   } else if (DIST == 2) {  // two-stream2 :278-292
     const double vp = dadd(v, c.v0), vm = dsub(v, c.v0);
-    const double ep = exp_fast(-DIVC(dmul(vp, vp), twoTm));
-    const double em = exp_fast(-DIVC(dmul(vm, vm), twoTm));
+    double ep, em;
+    exp_fast2(-DIVC(dmul(vp, vp), twoTm), -DIVC(dmul(vm, vm), twoTm), ep, em);
     const double num = dadd(dmul(vp, ep), dmul(vm, em));
     const double den = dadd(ep, em);
     double r = div_pos(num, den);
@@ -214,8 +239,8 @@ __device__ __forceinline__ double dlnf0_impl(const SpeciesConst &c, double v) {
     return DIVC(r, T);
   } else if (DIST == 3) {  // bump-on-tail :294-321
     const double vm = dsub(v, c.v0);
-    const double e1 = exp_fast(-DIVC(dmul(v, v), twoTm));
-    const double e2 = exp_fast(-DIVC(dmul(vm, vm), twoT2m));
+    double e1, e2;
+    exp_fast2(-DIVC(dmul(v, v), twoTm), -DIVC(dmul(vm, vm), twoT2m), e1, e2);
     const double a = DIVC(dmul(DIVC(dmul(c.n, v), Tm), e1), sqTm);
     const double b = DIVC(dmul(DIVC(dmul(c.omn, vm), T2m), e2), sqT2m);
     const double num = dadd(a, b);
@@ -488,6 +513,116 @@ __global__ void __launch_bounds__(1024, 1) k_push(const ParticleArgs a) {
   }
   if (FUSED) dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
   if (FUSED && noob) atomicAdd(a.noob, noob);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// TMA-pipelined variant of the fused substep kernel (delta-f, nonlinear; the flagship path).
+// Marker tiles of TILE markers are streamed into a STAGES-deep shared-memory ring with 1-D bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) issued by one thread STAGES-1 tiles ahead; consumers wait on
+// the stage's "full" mbarrier, pull their marker into registers, release the stage ("empty" mbarrier, one arrival per
+// warp) and compute.  Loads never occupy registers or stall a warp on the scoreboard, and warps may drift up to
+// STAGES-1 tiles apart.  One marker per thread per tile; outputs go straight to global memory.
+// ------------------------------------------------------------------------------------------------------------
+namespace tma {
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+}  // namespace tma
+
+template <int DIST, bool IRK2, int DEP, int CFG>
+__global__ void __launch_bounds__(1024, 1) k_push_tma(const ParticleArgs a) {
+  constexpr int TILE = 512;                 // == blockDim.x
+  constexpr int NARR = IRK2 ? 7 : 4;        // x v w p [xb vb wb]
+  constexpr int STAGES = IRK2 ? 3 : 4;
+  extern __shared__ __align__(16) double smem[];
+  double *sE = smem;
+  for (int j = threadIdx.x; j < a.nx; j += blockDim.x) sE[j] = a.E[j];
+  double *my_partial = a.partial + (size_t)blockIdx.x * a.nx;
+  Depositor<DEP> dep;
+  double *dep_base = smem + ((a.nx + 1) & ~1);
+  dep.g = dep_setup<DEP>(dep_base, a.nx, my_partial);
+  const int ngr = (DEP == DEP_WARP_PRIVATE) ? (int)(blockDim.x >> 5) : (DEP == DEP_SMEM_ATOMIC ? 2 : 0);
+  double *ring = dep_base + (((size_t)a.nx * ngr + 1) & ~(size_t)1);  // [STAGES][NARR][TILE]
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + (size_t)STAGES * NARR * TILE);
+  const unsigned full0 = tma::smem_u32(bars), empty0 = tma::smem_u32(bars + STAGES);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      tma::mbar_init(full0 + 8 * s, 1);
+      tma::mbar_init(empty0 + 8 * s, blockDim.x >> 5);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t ntiles = (a.np + TILE - 1) / TILE;
+  const int64_t my_tiles = (ntiles > (int64_t)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const double *src[7] = {a.x_cur, a.v_cur, a.w_cur, a.p, a.x_bak, a.v_bak, a.w_bak};
+  auto issue = [&](int64_t k) {  // thread 0: start the bulk copies of this CTA's k-th tile
+    const int st = (int)(k % STAGES);
+    if (k >= STAGES) tma::mbar_wait(empty0 + 8 * st, (unsigned)(((k / STAGES) - 1) & 1));
+    const int64_t m0 = ((int64_t)blockIdx.x + k * gridDim.x) * TILE;
+    const int64_t cnt = (a.np - m0 < TILE) ? a.np - m0 : TILE;
+    const unsigned bytes = (unsigned)(((cnt + 1) & ~(int64_t)1) * 8);  // arrays are padded to an even count
+    tma::mbar_expect_tx(full0 + 8 * st, bytes * NARR);
+#pragma unroll
+    for (int q = 0; q < NARR; q++)
+      tma::bulk_g2s(tma::smem_u32(ring + ((size_t)st * NARR + q) * TILE), src[q] + m0, bytes, full0 + 8 * st);
+  };
+  if (threadIdx.x == 0)
+    for (int64_t k = 0; k < STAGES - 1 && k < my_tiles; k++) issue(k);
+
+  unsigned long long noob = 0;
+  for (int64_t k = 0; k < my_tiles; k++) {
+    if (threadIdx.x == 0 && k + STAGES - 1 < my_tiles) issue(k + STAGES - 1);
+    const int st = (int)(k % STAGES);
+    tma::mbar_wait(full0 + 8 * st, (unsigned)((k / STAGES) & 1));
+    const double *rs = ring + (size_t)st * NARR * TILE + threadIdx.x;
+    const double x = rs[0], v = rs[TILE], w = rs[2 * TILE], p = rs[3 * TILE];
+    double xb = x, vb = v, wb = w;
+    if (IRK2) {
+      xb = rs[4 * TILE];
+      vb = rs[5 * TILE];
+      wb = rs[6 * TILE];
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) tma::mbar_arrive(empty0 + 8 * st);
+    const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * TILE + threadIdx.x;
+    const bool ok = i < a.np;
+    double xo = 0.0, vo = 0.0, wo = 0.0;
+    if (ok) {
+      push_one<DIST, CFG>(a, sE, x, v, w, p, xb, vb, wb, xo, vo, wo);
+      xo = wrap_x(xo, a.lx);
+      st1(a.x_out + i, xo);
+      st1(a.v_out + i, vo);
+      st1(a.w_out + i, wo);
+    }
+    bool o0 = false;
+    const Shape s0 = shape_of(xo, a.lx, a.rlx, a.rnx, a.nx, Cfg<CFG>::right_frac(a.right_frac), o0);
+    dep.add(s0.ix, s0.ixr, dmul(s0.sl, wo), dmul(s0.sr, wo), ok);
+    noob += (ok && o0);
+  }
+  dep_flush<DEP>(dep_base, a.nx, my_partial);
+  if (noob) atomicAdd(a.noob, noob);
 }
 
 // ------------------------------------------------------------------------------------------------------------

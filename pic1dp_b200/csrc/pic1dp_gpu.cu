@@ -95,6 +95,8 @@ struct pic1dp_gpu {
   double *d_diag_part = nullptr, *d_diag_sums = nullptr, *d_hist = nullptr, *d_hist_out = nullptr;
   int diag_grid = 0, hist_cells = 0, hist_copies = 16;
   int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0, cfg = -1;
+  bool use_tma = false;
+  int tma_smem[2] = {0, 0};  // dynamic shared memory of the TMA kernels, irk = 1, 2
   bool partial_valid = false;  // a fused push has already deposited into d_partial
   int nred = 1;
   ncclComm_t comm = nullptr;
@@ -200,6 +202,30 @@ static PushKernel pick_push(int dist, int dep, bool irk2, bool fused, int cfg) {
     default: return pick_irk<0>(dep, irk2, fused, cfg);
   }
 }
+// TMA-pipelined flagship kernels (delta-f nonlinear, fused): cfg in {1, 9, 25}
+template <int DIST, bool IRK2, int CFG>
+static PushKernel pick_tma_dep(int dep) {
+  switch (dep) {
+    case DEP_SMEM_ATOMIC: return k_push_tma<DIST, IRK2, DEP_SMEM_ATOMIC, CFG>;
+    case DEP_GLOBAL_RED: return k_push_tma<DIST, IRK2, DEP_GLOBAL_RED, CFG>;
+    default: return k_push_tma<DIST, IRK2, DEP_WARP_PRIVATE, CFG>;
+  }
+}
+template <int DIST>
+static PushKernel pick_tma_dist(int dep, bool irk2, int cfg) {
+  if (cfg == 25) return irk2 ? pick_tma_dep<DIST, true, 25>(dep) : pick_tma_dep<DIST, false, 25>(dep);
+  if (cfg == 9) return irk2 ? pick_tma_dep<DIST, true, 9>(dep) : pick_tma_dep<DIST, false, 9>(dep);
+  return irk2 ? pick_tma_dep<DIST, true, 1>(dep) : pick_tma_dep<DIST, false, 1>(dep);
+}
+static PushKernel pick_tma(int dist, int dep, bool irk2, int cfg) {
+  switch (dist) {
+    case 1: return pick_tma_dist<1>(dep, irk2, cfg);
+    case 2: return pick_tma_dist<2>(dep, irk2, cfg);
+    case 3: return pick_tma_dist<3>(dep, irk2, cfg);
+    default: return pick_tma_dist<0>(dep, irk2, cfg);
+  }
+}
+
 static PushKernel pick_deposit(int dep, bool deposit) {
   if (!deposit) return k_deposit<DEP_SMEM_ATOMIC, false>;
   switch (dep) {
@@ -280,8 +306,9 @@ static int validate(const pic1dp_params *p, std::string &err) {
       err = "mass and temperatures must be positive";
       return PIC1DP_EINVAL;
     }
-  if (p->deposit_mode < 0 || p->deposit_mode > 3 || p->field_mode < 0 || p->field_mode > 1) {
-    err = "bad deposit_mode / field_mode";
+  if (p->deposit_mode < 0 || p->deposit_mode > 3 || p->field_mode < 0 || p->field_mode > 1 || p->load_path < 0 ||
+      p->load_path > 2) {
+    err = "bad deposit_mode / field_mode / load_path";
     return PIC1DP_EINVAL;
   }
   return PIC1DP_OK;
@@ -387,6 +414,33 @@ static int create_impl(pic1dp_gpu_t *h) {
           if (fused && per_sm < per_sm_min) per_sm_min = per_sm;
         }
     if (per_sm_min < 1) per_sm_min = 1;
+    // TMA-pipelined variant (512 threads, ring of 3-4 stages): usable when it reaches the same residency
+    h->use_tma = false;
+    if (h->cfg == 1 && p.load_path != PIC1DP_LOAD_DIRECT && (dep != DEP_WARP_PRIVATE || h->threads >= 512)) {
+      const int tthr = 512;
+      bool ok = true;
+      for (int irk2 = 0; irk2 < 2 && ok; irk2++) {
+        const size_t ring = (size_t)(irk2 ? 3 * 7 : 4 * 4) * 512 * 8 + 64;
+        const size_t need = 8 * (((size_t)(nx + 1) & ~(size_t)1) + (((size_t)nx * dep_grids(dep, tthr) + 1) & ~(size_t)1)) + ring;
+        h->tma_smem[irk2] = (int)need;
+        if (need > max_smem) { ok = false; break; }
+        const int cfgs3[3] = {1, 9, 25};
+        for (int ci = 0; ci < 3; ci++) {
+          PushKernel k = pick_tma(p.iptcldist, dep, irk2 == 1, cfgs3[ci]);
+          CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+          int per_sm = 0;
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, tthr, need));
+          if (per_sm * tthr < per_sm_min * h->threads) ok = false;  // fewer resident threads than the direct kernel
+          if (ok && per_sm < per_sm_min) per_sm_min = per_sm;
+        }
+      }
+      // AUTO: measured faster only ... (decided from profiles/r01_tma_ab.md); explicit request always honoured
+      h->use_tma = ok && (p.load_path == PIC1DP_LOAD_TMA);
+      if (p.load_path == PIC1DP_LOAD_TMA && !ok) {
+        h->err = "load_path = TMA: the shared-memory ring does not fit beside the deposit grids for this nx";
+        return PIC1DP_EUNSUPPORTED;
+      }
+    }
     h->grid = h->nsm * per_sm_min;  // persistent grid: every CTA resident, private grid per CTA
   }
   CK(cudaFuncSetAttribute(pick_deposit(dep, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -734,8 +788,13 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
     a.v_out = S.v[out];
     a.w_out = S.w[out];
     const int cfg = (h->cfg == 1) ? (S.c.unit ? 25 : S.c.pow2 ? 9 : 1) : -1;
-    PushKernel k = pick_push(p.iptcldist, h->dep, irk == 2, fused, cfg);
-    k<<<h->grid, h->threads, h->smem_push, h->stream>>>(a);
+    if (fused && h->use_tma && cfg > 0) {
+      PushKernel k = pick_tma(p.iptcldist, h->dep, irk == 2, cfg);
+      k<<<h->grid, 512, h->tma_smem[irk - 1], h->stream>>>(a);
+    } else {
+      PushKernel k = pick_push(p.iptcldist, h->dep, irk == 2, fused, cfg);
+      k<<<h->grid, h->threads, h->smem_push, h->stream>>>(a);
+    }
     CKL(h);
     S.cur = out;
   }

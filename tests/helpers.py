@@ -14,7 +14,7 @@ def make_params(**over):
     """Matching (oracle params, GPU params) pair.  GPU-only keys: capacity, device, deposit_mode, field_mode, fuse,
     rank, nranks."""
     gpu_only = {k: over.pop(k) for k in list(over) if k in ("capacity", "device", "deposit_mode", "field_mode",
-                                                            "fuse", "rank", "nranks")}
+                                                            "fuse", "rank", "nranks", "load_path")}
     op = O.default_params(**over)
     gp = P.default_params(**over, **gpu_only)
     return op, gp
