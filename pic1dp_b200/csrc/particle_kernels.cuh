@@ -13,6 +13,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Resident threads per SM the particle kernels are compiled for: 1024 -> 64 registers/thread, 768 -> 85, 512 -> 128.
+#ifndef PIC1DP_MAXTHREADS
+#define PIC1DP_MAXTHREADS 1024
+#endif
+
 namespace pic1dp {
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -285,6 +290,228 @@ __device__ __forceinline__ void push_one(const ParticleArgs &a, const double *sE
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// N-wide forms of the functions above.  The per-marker code is a chain of dependent fp64 operations (exact
+// division, two exponentials, another division); processing the N = 2 markers of a thread as explicitly interleaved
+// straight-line code, with the rare-path tests of all lanes OR-ed into one branch, lets the scheduler overlap the
+// independent chains instead of stalling on fixed-latency dependencies.  Every lane performs exactly the scalar
+// sequence of operations, so results are bit-identical to the scalar functions.
+// ------------------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void div_const_n(const double (&a)[N], double b, double y, double (&q)[N]) {
+  bool rare = false;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const double q0 = a[k] * y;
+    const double r = fma(-q0, b, a[k]);
+    q[k] = fma(r, y, q0);
+    rare |= !(a[k] >= 0x1p-800) || div_suspect(a[k], b, q[k]);
+  }
+  if (__builtin_expect(rare, 0)) {
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k] = div_slow(a[k], b);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void div_pos_n(const double (&a)[N], const double (&b)[N], double (&q)[N]) {
+  bool rare = false;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const unsigned eb = (unsigned)(__double2hiint(b[k]) & 0x7ff00000) - (523u << 20);
+    const unsigned ea = (unsigned)(__double2hiint(a[k]) & 0x7ff00000) - (523u << 20);
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b[k]));
+    double e = fma(-b[k], y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-b[k], y, 1.0);
+    y = fma(y, e, y);
+    const double q0 = a[k] * y;
+    const double r = fma(-q0, b[k], a[k]);
+    q[k] = fma(r, y, q0);
+    rare |= (eb | ea) >= (1000u << 20) || !(b[k] > 0.0) || div_suspect(a[k], b[k], q[k]);
+  }
+  if (__builtin_expect(rare, 0)) {
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k] = div_slow(a[k], b[k]);
+  }
+}
+
+template <int M>
+__device__ __forceinline__ void exp_fast_n(const double (&a)[M], double (&e)[M]) {
+  const double magic = 6755399441055744.0;
+  double r[M], q[M];
+  int n[M];
+  bool rare = false;
+#pragma unroll
+  for (int k = 0; k < M; k++) {
+    const double t = fma(a[k], c_exp_red[0], magic);
+    n[k] = __double2loint(t);
+    const double f = t - magic;
+    r[k] = fma(f, -c_exp_red[1], a[k]);
+    r[k] = fma(f, -c_exp_red[2], r[k]);
+    q[k] = c_exp_poly[0];
+    rare |= !(fabs(a[k]) <= 700.0);
+  }
+#pragma unroll
+  for (int j = 1; j < 10; j++) {
+#pragma unroll
+    for (int k = 0; k < M; k++) q[k] = fma(q[k], r[k], c_exp_poly[j]);
+  }
+#pragma unroll
+  for (int k = 0; k < M; k++) {
+    const double pr = fma(r[k] * r[k], q[k], r[k]) + 1.0;
+    e[k] = __hiloint2double(__double2hiint(pr) + (n[k] << 20), __double2loint(pr));
+  }
+  if (__builtin_expect(rare, 0)) {  // never reached by physical velocities
+#pragma unroll
+    for (int k = 0; k < M; k++) e[k] = exp_slow(a[k]);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void wrap_n(double (&x)[N], double lx) {
+  bool rare = false;
+  double xw[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    xw[k] = (x[k] >= lx) ? dsub(x[k], lx) : x[k];
+    xw[k] = (x[k] < 0.0) ? dadd(x[k], lx) : xw[k];
+    rare |= !(x[k] > -lx && x[k] < dadd(lx, lx));
+  }
+  if (__builtin_expect(rare, 0)) {
+#pragma unroll
+    for (int k = 0; k < N; k++)
+      if (!(x[k] > -lx && x[k] < dadd(lx, lx))) xw[k] = wrap_slow(x[k], lx);
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) x[k] = xw[k];
+}
+
+template <int N>
+__device__ __forceinline__ void shape_n(const double (&x)[N], double lx, double rlx, double rnx, int nx, int right_frac,
+                                        Shape (&s)[N], bool (&oob)[N]) {
+  double q[N];
+  div_const_n<N>(x, lx, rlx, q);
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const double sx = dmul(q[k], rnx);
+    int ix = __double2int_rd(sx);
+    double frac = dsub(sx, (double)ix);
+    double sl = dsub(1.0, frac);
+    oob[k] = (unsigned)ix >= (unsigned)nx;
+    if (oob[k]) {
+      ix = 0;
+      sl = 1.0;
+      frac = 0.0;
+    }
+    s[k].ix = ix;
+    s[k].sl = sl;
+    s[k].sr = right_frac ? frac : dsub(1.0, sl);
+    int ixr = ix + 1;
+    if (ixr > nx - 1) ixr = 0;
+    s[k].ixr = ixr;
+  }
+}
+
+template <int DIST, bool POW2, bool UNIT, int N>
+__device__ __forceinline__ void dlnf0_impl_n(const SpeciesConst &c, const double (&v)[N], double (&out)[N]) {
+#define DIVC(x, name) (UNIT && !DivIsTwo::name ? (x) : UNIT ? dmul((x), 0.5) : POW2 ? dmul((x), c.i_##name) : ddiv((x), c.name))
+  if (DIST == 1) {
+#pragma unroll
+    for (int k = 0; k < N; k++) out[k] = dsub(v[k], ddiv(2.0, v[k]));
+  } else if (DIST == 2) {
+    double arg[2 * N], e[2 * N], num[N], den[N], r[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double vp = dadd(v[k], c.v0), vm = dsub(v[k], c.v0);
+      arg[2 * k] = -DIVC(dmul(vp, vp), twoTm);
+      arg[2 * k + 1] = -DIVC(dmul(vm, vm), twoTm);
+    }
+    exp_fast_n<2 * N>(arg, e);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double vp = dadd(v[k], c.v0), vm = dsub(v[k], c.v0);
+      num[k] = dadd(dmul(vp, e[2 * k]), dmul(vm, e[2 * k + 1]));
+      den[k] = dadd(e[2 * k], e[2 * k + 1]);
+    }
+    div_pos_n<N>(num, den, r);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      double t = r[k];
+      if (!UNIT) t = dmul(t, c.m);
+      out[k] = DIVC(t, T);
+    }
+  } else if (DIST == 3) {
+    double arg[2 * N], e[2 * N], num[N], den[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double vm = dsub(v[k], c.v0);
+      arg[2 * k] = -DIVC(dmul(v[k], v[k]), twoTm);
+      arg[2 * k + 1] = -DIVC(dmul(vm, vm), twoT2m);
+    }
+    exp_fast_n<2 * N>(arg, e);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double vm = dsub(v[k], c.v0), e1 = e[2 * k], e2 = e[2 * k + 1];
+      const double a = DIVC(dmul(DIVC(dmul(c.n, v[k]), Tm), e1), sqTm);
+      const double b = DIVC(dmul(DIVC(dmul(c.omn, vm), T2m), e2), sqT2m);
+      num[k] = dadd(a, b);
+      den[k] = dadd(DIVC(dmul(c.n, e1), sqTm), DIVC(dmul(c.omn, e2), sqT2m));
+    }
+    div_pos_n<N>(num, den, out);
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; k++) out[k] = DIVC(dsub(v[k], c.v0), Tm);
+  }
+#undef DIVC
+}
+
+// gather + push of N markers (src/pic1dp_interaction.F90:250-338), lane by lane the same operations as push_one
+template <int DIST, int CFG, int N>
+__device__ __forceinline__ void push_n(const ParticleArgs &a, const double *sE, const double (&x)[N],
+                                       const double (&v)[N], const double (&w)[N], const double (&p)[N],
+                                       const double (&xb)[N], const double (&vb)[N], const double (&wb)[N],
+                                       double (&xo)[N], double (&vo)[N], double (&wo)[N]) {
+  typedef Cfg<CFG> F;
+  Shape s[N];
+  bool oob[N];
+  shape_n<N>(x, a.lx, a.rlx, a.rnx, a.nx, F::right_frac(a.right_frac), s, oob);
+  double electric[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    electric[k] = dadd(dmul(sE[s[k].ix], s[k].sl), dmul(sE[s[k].ixr], s[k].sr));  // :254-257
+    xo[k] = dadd(xb[k], dmul(a.dt, v[k]));                                          // :261
+    wo[k] = w[k];
+    vo[k] = v[k];
+  }
+  if (F::deltaf(a.deltaf)) {
+    double tmp2[N];
+    if (F::unit)
+      dlnf0_impl_n<DIST, true, true, N>(a.c, v, tmp2);
+    else if (F::pow2(a.c.pow2))
+      dlnf0_impl_n<DIST, true, false, N>(a.c, v, tmp2);
+    else
+      dlnf0_impl_n<DIST, false, false, N>(a.c, v, tmp2);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double tmp1 = F::linear(a.linear) ? dmul(p[k], electric[k]) : dmul(dsub(p[k], w[k]), electric[k]);  // :268-272
+      double t = dmul(dmul(dmul(a.dt, tmp1), tmp2[k]), a.c.Z);                          // :329
+      if (!F::unit) t = F::pow2(a.c.pow2) ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);           // :330
+      wo[k] = dadd(wb[k], t);
+    }
+  }
+  if (!F::linear(a.linear)) {
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      double t = dmul(dmul(a.dt, electric[k]), a.c.Z);  // :336
+      if (!F::unit) t = F::pow2(a.c.pow2) ? dmul(t, a.c.i_m) : ddiv(t, a.c.m);
+      vo[k] = dadd(vb[k], t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Deposit strategies.  Each adds (sl*w) to cell ix and (sr*w) to cell ixr of an on-chip grid.
 // ------------------------------------------------------------------------------------------------------------
 enum { DEP_SMEM_ATOMIC = 1, DEP_GLOBAL_RED = 2, DEP_WARP_PRIVATE = 3 };
@@ -465,11 +692,29 @@ __device__ __forceinline__ void push_pair(const ParticleArgs &a, const double *s
     wb = w;
   }
   double2 xo = {0.0, 0.0}, vo = {0.0, 0.0}, wo = {0.0, 0.0};
-  if (v0ok) push_one<DIST, CFG>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
-  if (v1ok) push_one<DIST, CFG>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
-  if (FUSED) {
-    if (v0ok) xo.x = wrap_x(xo.x, a.lx);
-    if (v1ok) xo.y = wrap_x(xo.y, a.lx);
+  Shape sd[2];
+  bool od[2] = {false, false};
+  if (FULL) {  // both markers valid: 2-wide interleaved code
+    const double ax[2] = {x.x, x.y}, av[2] = {v.x, v.y}, aw[2] = {w.x, w.y}, ap[2] = {p.x, p.y};
+    const double axb[2] = {xb.x, xb.y}, avb[2] = {vb.x, vb.y}, awb[2] = {wb.x, wb.y};
+    double axo[2], avo[2], awo[2];
+    push_n<DIST, CFG, 2>(a, sE, ax, av, aw, ap, axb, avb, awb, axo, avo, awo);
+    if (FUSED) {
+      wrap_n<2>(axo, a.lx);
+      shape_n<2>(axo, a.lx, a.rlx, a.rnx, a.nx, right_frac, sd, od);
+    }
+    xo = make_double2(axo[0], axo[1]);
+    vo = make_double2(avo[0], avo[1]);
+    wo = make_double2(awo[0], awo[1]);
+  } else {
+    if (v0ok) push_one<DIST, CFG>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
+    if (v1ok) push_one<DIST, CFG>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
+    if (FUSED) {
+      if (v0ok) xo.x = wrap_x(xo.x, a.lx);
+      if (v1ok) xo.y = wrap_x(xo.y, a.lx);
+      sd[0] = shape_of(xo.x, a.lx, a.rlx, a.rnx, a.nx, right_frac, od[0]);
+      sd[1] = shape_of(xo.y, a.lx, a.rlx, a.rnx, a.nx, right_frac, od[1]);
+    }
   }
   if (v1ok) {
     st2(a.x_out + i, xo);
@@ -483,17 +728,14 @@ __device__ __forceinline__ void push_pair(const ParticleArgs &a, const double *s
   if (FUSED) {
     // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
     const double q0 = deltaf ? wo.x : p.x, q1 = deltaf ? wo.y : p.y;
-    bool o0 = false, o1 = false;
-    const Shape s0 = shape_of(xo.x, a.lx, a.rlx, a.rnx, a.nx, right_frac, o0);
-    dep.add(s0.ix, s0.ixr, dmul(s0.sl, q0), dmul(s0.sr, q0), v0ok);  // :110, :113
-    const Shape s1 = shape_of(xo.y, a.lx, a.rlx, a.rnx, a.nx, right_frac, o1);
-    dep.add(s1.ix, s1.ixr, dmul(s1.sl, q1), dmul(s1.sr, q1), v1ok);
-    noob += (v0ok && o0) + (v1ok && o1);
+    dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0), v0ok);  // :110, :113
+    dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), v1ok);
+    noob += (v0ok && od[0]) + (v1ok && od[1]);
   }
 }
 
 template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
-__global__ void __launch_bounds__(1024, 1) k_push(const ParticleArgs a) {
+__global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArgs a) {
   extern __shared__ __align__(16) double smem[];
   double *sE = smem;
   for (int j = threadIdx.x; j < a.nx; j += blockDim.x) sE[j] = a.E[j];

@@ -373,7 +373,7 @@ static int create_impl(pic1dp_gpu_t *h) {
   auto smem_need = [&](int d, int thr) { return (size_t)8 * (((nx + 1) & ~1) + (size_t)nx * dep_grids(d, thr)); };
   auto warp_private_threads = [&]() {
     int w = (int)((max_smem - 8) / ((size_t)nx * 8)) - 1;
-    if (w > 32) w = 32;
+    if (w > PIC1DP_MAXTHREADS / 32) w = PIC1DP_MAXTHREADS / 32;
     if (w >= 4) w &= ~3;
     return w * 32;
   };
@@ -392,7 +392,7 @@ static int create_impl(pic1dp_gpu_t *h) {
     h->err = "WARP_PRIVATE deposit needs one nx-sized shared-memory grid per warp: fewer than 8 warps fit for this nx";
     return PIC1DP_EUNSUPPORTED;
   }
-  h->threads = (dep == DEP_WARP_PRIVATE) ? warp_private_threads() : 512;
+  h->threads = (dep == DEP_WARP_PRIVATE) ? warp_private_threads() : PIC1DP_MAXTHREADS / 2;
   if (h->threads < 32 || smem_need(dep, h->threads) > max_smem) {
     h->err = "shared-memory grid does not fit for this nx with the requested deposit_mode";
     return PIC1DP_EUNSUPPORTED;
