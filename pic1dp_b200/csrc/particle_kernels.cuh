@@ -17,6 +17,10 @@
 #ifndef PIC1DP_MAXTHREADS
 #define PIC1DP_MAXTHREADS 1024
 #endif
+// which fused-kernel variants issue L2 prefetches: bit 0/1 = atomic deposits irk 1/2, bit 2/3 = warp-private irk 1/2
+#ifndef PIC1DP_PF_MASK
+#define PIC1DP_PF_MASK 8
+#endif
 
 namespace pic1dp {
 
@@ -612,6 +616,8 @@ __device__ __forceinline__ double2 ld2(const double *p) { return __ldcs(reinterp
 __device__ __forceinline__ double ld1(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
 __device__ __forceinline__ void st1(double *p, double v) { __stcs(p, v); }
+// pull the line a later tile step will read into L2 (no destination register, no scoreboard wait)
+__device__ __forceinline__ void prefetch_l2(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Shared-memory layout of the particle kernels: [E : nx rounded up to even] [deposit grid(s) : nx * ngrids]
 // (16-byte alignment of the pair grid for the 128-bit CAS)
@@ -746,8 +752,26 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
 
   const int64_t tile = (int64_t)blockDim.x * 2;
   unsigned long long noob = 0;
+  const bool deltaf_pf = Cfg<CFG>::deltaf(a.deltaf);
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
+    // L2 prefetch of this thread's markers of the next tile step: the loads then hit L2 instead of HBM.
+    // Measured on B200 at 1e8 markers (profiles/r01_ab_experiments.md): helps where fewer warps are resident
+    // (warp-private deposit, irk=2: 1.60 -> 1.35 ms) and hurts with 32 resident warps, so it is enabled per variant.
+    if (PIC1DP_PF_MASK & ((DEP == DEP_WARP_PRIVATE ? 4 : 1) << (IRK2 ? 1 : 0))) {
+      const int64_t inext = i + (int64_t)gridDim.x * tile;
+      if (inext + 1 < a.np) {
+        prefetch_l2(a.x_cur + inext);
+        prefetch_l2(a.v_cur + inext);
+        if (deltaf_pf) prefetch_l2(a.w_cur + inext);
+        if (deltaf_pf || FUSED) prefetch_l2(a.p + inext);
+        if (IRK2) {
+          prefetch_l2(a.x_bak + inext);
+          prefetch_l2(a.v_bak + inext);
+          if (deltaf_pf) prefetch_l2(a.w_bak + inext);
+        }
+      }
+    }
     if (base + tile <= a.np)
       push_pair<DIST, IRK2, DEP, FUSED, CFG, true>(a, sE, dep, i, noob);
     else
