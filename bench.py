@@ -76,7 +76,7 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
@@ -96,12 +96,23 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        time.sleep(0.05)
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
         for ts, line in self.rows:
-            if ts < t0 or ts > t1 + 0.1:
-                continue
             f = [t.strip() for t in line.split(",")]
+            try:  # nvidia-smi's own timestamp (its stdout is block-buffered when piped, so arrival time is late)
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                pass
+            f = f[1:]
+            if ts < t0 - 0.02 or ts > t1 + 0.05:
+                continue
             try:
                 sm.append(float(f[0]))
                 smax = float(f[1])
@@ -235,15 +246,14 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ("value") ----
+    sampler = ClockSampler(local)
+    sampler.start()   # started well before the timed region: nvidia-smi needs a few hundred ms to deliver samples
     g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])
     g.collect_charge()
     g.solve_field()
     g.step(args.warmup)
     barrier()
     c0 = g.counters()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
     t0 = time.time()
     g.timer_start()
     g.step(args.steps)

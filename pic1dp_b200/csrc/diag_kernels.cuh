@@ -100,6 +100,56 @@ __global__ void __launch_bounds__(512) k_diag(const DiagArgs a) {
   }
 }
 
+// Shared-memory form of the histogram: the CTA accumulates {g, f} pairs with one ATOMS.CAS.128 per bilinear corner and
+// delta f with a 64-bit CAS loop in a private ncell*24-byte grid, then flushes it to one of the ncopies L2-resident
+// grids with RED.ADD.F64.  4x faster than 12 REDs per marker when the grid fits (64 x 64: 96 KB).
+__global__ void __launch_bounds__(512) k_diag_hist_smem(const DiagArgs a) {
+  extern __shared__ __align__(16) double sh[];
+  const int ncell = a.nx_opd * a.nv_opd;
+  double2 *s_mt = reinterpret_cast<double2 *>(sh);  // {markr, total}
+  double *s_p = sh + 2 * (size_t)ncell;             // pertb
+  for (int j = threadIdx.x; j < 3 * ncell; j += blockDim.x) sh[j] = 0.0;
+  __syncthreads();
+  const double rnx = (double)a.nx_opd, rnv = (double)(a.nv_opd - 1), two_vmax = dmul(a.v_max, 2.0);
+  Depositor<DEP_SMEM_ATOMIC> pairs;
+  pairs.g = sh;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.np; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = __ldcs(a.v + i);
+    if (fabs(v) >= a.v_max) continue;  // :241
+    const double p = __ldcs(a.p + i), x = __ldcs(a.x + i);
+    const double w = a.deltaf ? __ldcs(a.w + i) : 0.0;
+    double sx = dmul(ddiv(x, a.lx), rnx);
+    int ix = __double2int_rd(sx);
+    sx = dsub(1.0, dsub(sx, (double)ix));
+    double sv = dmul(ddiv(dadd(v, a.v_max), two_vmax), rnv);
+    const int iv = __double2int_rd(sv);
+    sv = dsub(1.0, dsub(sv, (double)iv));
+    if ((unsigned)ix >= (unsigned)a.nx_opd) {
+      ix = 0;
+      sx = 1.0;
+    }
+    int ix2 = ix + 1;
+    if (ix2 > a.nx_opd - 1) ix2 = 0;
+    const double sx2 = dsub(1.0, sx), sv2 = dsub(1.0, sv);
+    const int c[4] = {iv * a.nx_opd + ix, (iv + 1) * a.nx_opd + ix, iv * a.nx_opd + ix2, (iv + 1) * a.nx_opd + ix2};
+    const double wt[4] = {dmul(sx, sv), dmul(sx, sv2), dmul(sx2, sv), dmul(sx2, sv2)};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      pairs.add(c[q], 0, wt[q], dmul(wt[q], p), true);
+      if (a.deltaf) atomicAdd(s_p + c[q], dmul(wt[q], w));
+    }
+  }
+  __syncthreads();
+  double *hm = a.hist + (size_t)(blockIdx.x % a.ncopies) * 3 * ncell;
+  for (int j = threadIdx.x; j < ncell; j += blockDim.x) {
+    const double2 mt = s_mt[j];
+    if (mt.x != 0.0) atomicAdd(hm + j, mt.x);
+    if (mt.y != 0.0) atomicAdd(hm + ncell + j, mt.y);
+    const double pp = s_p[j];
+    if (pp != 0.0) atomicAdd(hm + 2 * ncell + j, pp);
+  }
+}
+
 // out[3] = sum over CTAs in CTA order
 __global__ void k_diag_sums_final(const double *partial, int nparts, double *out) {
   if (threadIdx.x < 3) {

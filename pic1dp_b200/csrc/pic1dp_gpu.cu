@@ -93,7 +93,8 @@ struct pic1dp_gpu {
   std::vector<double> h_Fre, h_Fim, h_ginv;
   // diagnostics scratch (allocated on first use)
   double *d_diag_part = nullptr, *d_diag_sums = nullptr, *d_hist = nullptr, *d_hist_out = nullptr;
-  int diag_grid = 0, hist_cells = 0, hist_copies = 16;
+  int diag_grid = 0, hist_cells = 0, hist_copies = 16, hist_smem_set = -1, hist_per_sm = 1;
+  size_t max_smem = 0;
   int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0, cfg = -1;
   bool use_tma = false;
   int tma_smem[2] = {0, 0};  // dynamic shared memory of the TMA kernels, irk = 1, 2
@@ -365,6 +366,7 @@ static int create_impl(pic1dp_gpu_t *h) {
 
   const int nx = p.nx, M = p.nmode;
   const size_t max_smem = prop.sharedMemPerBlockOptin;
+  h->max_smem = max_smem;
   // ---- deposit strategy and launch geometry ----
   // Kernels are compiled for <= 64 registers (launch bound 1024 threads), so an SM holds up to 1024 threads =
   // 32 warps.  Shared/global-atomic deposits run 2 CTAs x 512 threads; the warp-private deposit needs one grid
@@ -997,8 +999,22 @@ int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int
   a.nx_opd = nx_opd;
   a.nv_opd = nv_opd;
   a.v_max = v_max;
-  k_diag<false, true><<<h->diag_grid, 512, 0, h->stream>>>(a);
-  CKL(h);
+  {
+    const size_t hs = (size_t)3 * ncell * 8;
+    if (hs <= h->max_smem) {  // private shared-memory histogram per CTA, flushed with REDs
+      if (h->hist_smem_set != (int)hs) {
+        CK(cudaFuncSetAttribute(k_diag_hist_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+        int per_sm = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diag_hist_smem, 512, hs));
+        h->hist_per_sm = per_sm < 1 ? 1 : per_sm;
+        h->hist_smem_set = (int)hs;
+      }
+      k_diag_hist_smem<<<h->nsm * h->hist_per_sm, 512, hs, h->stream>>>(a);
+    } else {
+      k_diag<false, true><<<h->diag_grid, 512, 0, h->stream>>>(a);
+    }
+    CKL(h);
+  }
   // the private copies are laid out for hist_cells; only the first 3*ncell entries of each copy are used
   // (stride between copies is 3*ncell of THIS call, see k_diag), so reduce with the same stride
   k_diag_hist_final<<<(3 * ncell + 255) / 256, 256, 0, h->stream>>>(h->d_hist, h->hist_copies, 3 * ncell, h->d_hist_out);
