@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--markers", type=float, default=1e8, help="markers per GPU")
     ap.add_argument("--nx", type=int, default=1024)
     ap.add_argument("--deposit", type=int, default=0, help="PIC1DP_DEPOSIT_* (0 = auto)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="density all-reduce: NCCL or peer-memory exchange (auto = p2p when it can be set up)")
     ap.add_argument("--load-path", type=int, default=0, help="PIC1DP_LOAD_* (0 auto, 1 direct, 2 TMA ring)")
     ap.add_argument("--cpu-markers", type=float, default=2e7, help="markers of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -184,7 +186,8 @@ def workload_config(args, n_gpus):
             "markers_per_gpu": n, "markers_total": n * n_gpus, "nx": args.nx, "nmode": 1,
             "bytes_per_particle_step": BYTES_STEP,
             "l2": "inputs larger than L2: %.1f GB of marker state streamed per step per GPU" % (n * BYTES_STEP / 1e9),
-            "parallelism": f"particle-decomposition x{n_gpus}, replicated grid, ncclAllReduce(rho) per substep"}
+            "parallelism": f"particle-decomposition x{n_gpus}, replicated grid, density all-reduce per substep "
+                           "(peer-memory exchange over NVLink, NCCL fallback)"}
 
 
 def main():
@@ -223,6 +226,15 @@ def main():
         uid = [g.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         g.comm_init(uid[0])
+        if args.allreduce in ("auto", "p2p") and world <= 8:
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, g.p2p_export())
+                g.p2p_import(handles)
+            except Exception as e:  # keep NCCL
+                if args.allreduce == "p2p":
+                    raise
+                print(f"[rank {rank}] peer-memory all-reduce unavailable, using NCCL: {e}", file=sys.stderr)
 
     # ---- synthetic markers in pinned host memory ----
     host = {k: torch.empty(n, dtype=torch.float64, pin_memory=True) for k in ("x", "v", "p", "w")}
@@ -349,9 +361,10 @@ def main():
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         ncpu = int(args.cpu_markers)
-        val, secs = cpu_reference_run(args.nx, ncpu, 5, 1, cores)
+        csteps = max(5, int(round(10.0 * 2e8 * cores / 16 / max(ncpu, 1))))  # ~10 s at ~1.2e7 particle-steps/s/core
+        val, secs = cpu_reference_run(args.nx, ncpu, csteps, 1, cores)
         cpu = {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{ncpu} markers x 5 steps (+1 warm-up), nx={args.nx}, {cores} emulated MPI ranks; {secs:.1f} s",
+               "sample": f"{ncpu} markers x {csteps} steps (+1 warm-up), nx={args.nx}, {cores} emulated MPI ranks; {secs:.1f} s",
                "note": "CPU restatement of the reference loops (oracle/), not the PETSc binary"}
 
     if rank == 0:
@@ -362,6 +375,7 @@ def main():
             "config": workload_config(args, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
             "nccl_calls": int(c1.nccl_calls - c0.nccl_calls),
+            "p2p_allreduces": int(c1.p2p_allreduces - c0.p2p_allreduces), "p2p_timeouts": int(c1.p2p_timeouts),
             "roofline": roofline, "roofline_detail": roofline_detail, "cpu_baseline": cpu,
             "deposit_mode": int(c1.deposit_mode), "grid_ctas": int(c1.grid_ctas), "cta_threads": int(c1.cta_threads),
             "smem_bytes": int(c1.smem_bytes), "oob_markers": int(c1.oob_markers), "field_energy": energy,

@@ -145,6 +145,19 @@ int pic1dp_gpu_comm_unique_id(uint8_t id[PIC1DP_UNIQUE_ID_BYTES]);
 int pic1dp_gpu_comm_init(pic1dp_gpu_t *h, const uint8_t id[PIC1DP_UNIQUE_ID_BYTES]);
 
 /*
+ * Optional peer-memory all-reduce (one process per GPU, NVLink/NVSwitch): instead of ncclAllReduce, the reduce kernel
+ * of every rank stores its partial density straight into an exchange buffer on every peer GPU and raises a flag; the
+ * next kernel waits for all flags and sums the nranks partial grids in rank order, so the density is bitwise
+ * identical on every rank and run-to-run.  Each rank exports a 64-byte IPC handle of its exchange buffer, the host
+ * all-gathers the handles (MPI_Allgather / torch.distributed), every rank imports all nranks*64 bytes.
+ * comm_init is still required (it is the fallback and is used by the diagnostics).  Processes only: IPC handles cannot
+ * be opened by the process that exported them.
+ */
+#define PIC1DP_IPC_HANDLE_BYTES 64
+int pic1dp_gpu_p2p_export(pic1dp_gpu_t *h, uint8_t handle[PIC1DP_IPC_HANDLE_BYTES]);
+int pic1dp_gpu_p2p_import(pic1dp_gpu_t *h, const uint8_t *all_handles /* nranks * PIC1DP_IPC_HANDLE_BYTES */);
+
+/*
  * set_markers: H2D of one species after particle_load (src/pic1dp_particle.F90:145-269 fills x,v,p,w through
  * VecGetArrayF90).  np = particle_np(ispecies) (:248).  isp is 0-based.
  */
@@ -247,6 +260,8 @@ int pic1dp_gpu_timer_stop(pic1dp_gpu_t *h, float *milliseconds); /* synchronises
 typedef struct pic1dp_counters {
   int64_t kernel_launches;   /* kernels of this library launched on this handle so far */
   int64_t nccl_calls;        /* ncclAllReduce calls issued */
+  int64_t p2p_allreduces;    /* density all-reduces done through peer memory instead of NCCL */
+  int64_t p2p_timeouts;      /* peer flags that never arrived (bounded spin): results are invalid when non-zero */
   int64_t oob_markers;       /* markers whose wrapped x was exactly lx (ix == nx; the reference writes out of
                                 bounds there, src/pic1dp_interaction.F90:104-113); deposited as ix=0, s=1 */
   int64_t h2d_bytes;         /* bytes copied host->device by this handle */

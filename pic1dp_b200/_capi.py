@@ -11,6 +11,7 @@ import os
 MAX_SPECIES = 4
 MAX_MODES = 64
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 OK, EINVAL, ECUDA, ENCCL, ENOMEM, ESTATE, ECAPACITY, ENODEVICE, EUNSUPPORTED = range(9)
 DEPOSIT_AUTO, DEPOSIT_SMEM_ATOMIC, DEPOSIT_GLOBAL_RED, DEPOSIT_WARP_PRIVATE = range(4)
@@ -58,6 +59,8 @@ class Counters(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_int64),
         ("nccl_calls", C.c_int64),
+        ("p2p_allreduces", C.c_int64),
+        ("p2p_timeouts", C.c_int64),
         ("oob_markers", C.c_int64),
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
@@ -72,6 +75,7 @@ class Counters(C.Structure):
 EXPORTS = [
     "pic1dp_gpu_params_default", "pic1dp_gpu_abi_version", "pic1dp_gpu_strerror", "pic1dp_gpu_last_error",
     "pic1dp_gpu_create", "pic1dp_gpu_destroy", "pic1dp_gpu_comm_unique_id", "pic1dp_gpu_comm_init",
+    "pic1dp_gpu_p2p_export", "pic1dp_gpu_p2p_import",
     "pic1dp_gpu_set_markers", "pic1dp_gpu_get_markers", "pic1dp_gpu_compute_shape_x", "pic1dp_gpu_get_shape_x",
     "pic1dp_gpu_collect_charge", "pic1dp_gpu_solve_field", "pic1dp_gpu_push", "pic1dp_gpu_step",
     "pic1dp_gpu_get_field", "pic1dp_gpu_set_field", "pic1dp_gpu_get_operators", "pic1dp_gpu_field_energy",
@@ -110,6 +114,8 @@ def load() -> C.CDLL:
     L.pic1dp_gpu_destroy.argtypes = [vp]
     L.pic1dp_gpu_comm_unique_id.argtypes = [u8p]
     L.pic1dp_gpu_comm_init.argtypes = [vp, u8p]
+    L.pic1dp_gpu_p2p_export.argtypes = [vp, u8p]
+    L.pic1dp_gpu_p2p_import.argtypes = [vp, u8p]
     L.pic1dp_gpu_set_markers.argtypes = [vp, i32, i64, dp, dp, dp, dp]
     L.pic1dp_gpu_get_markers.argtypes = [vp, i32, dp, dp, dp, dp, C.POINTER(i64)]
     L.pic1dp_gpu_compute_shape_x.argtypes = [vp]

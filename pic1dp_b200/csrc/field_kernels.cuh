@@ -28,7 +28,75 @@ struct GridArgs {
   double a_im, a_re;      // -1.0/nx, 1.0/nx  (src/pic1dp_field.F90:234, :239)
   double nx_over_lx;      // input_nx / input_lx (src/pic1dp_interaction.F90:77)
   double *energy;
+  // peer-memory all-reduce of `red` fused into the reduce kernel (scatter) and the finalize / solve kernels (gather);
+  // p2p_nranks == 0: off (single rank, or ncclAllReduce between the kernels)
+  int p2p_nranks, p2p_rank, p2p_parity;
+  unsigned long long p2p_epoch;
+  unsigned long long *p2p_peer[8];  // exchange buffer of every rank: flags[2][nranks] (padded to 256 B) | data[2][nranks][count]
+  unsigned int *p2p_counter;        // local: CTAs of the reduce kernel that have stored their part
+  unsigned long long *p2p_timeouts; // local error counter
 };
+
+__device__ __forceinline__ double *p2p_data(unsigned long long *base, int nranks, int count, int parity, int r) {
+  const size_t flag_bytes = ((size_t)2 * nranks * 8 + 255) & ~(size_t)255;
+  return reinterpret_cast<double *>(reinterpret_cast<char *>(base) + flag_bytes) + ((size_t)parity * nranks + r) * count;
+}
+
+// scatter side: store one reduced value into slot [parity][my rank] of every rank's exchange buffer (NVLink stores)
+__device__ __forceinline__ void p2p_store(const GridArgs &g, int idx, double v) {
+  const int count = (g.matrix_path ? g.nspecies : 1) * g.nx;
+  for (int r = 0; r < g.p2p_nranks; r++) p2p_data(g.p2p_peer[r], g.p2p_nranks, count, g.p2p_parity, g.p2p_rank)[idx] = v;
+}
+
+// scatter side, end of the kernel: the last CTA publishes this rank's epoch flag in every rank's buffer
+__device__ __forceinline__ void p2p_publish(const GridArgs &g) {
+  __threadfence_system();  // my stores are visible system-wide before the counter / flag
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(g.p2p_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *g.p2p_counter = 0;
+      __threadfence_system();
+      for (int r = 0; r < g.p2p_nranks; r++) {
+        unsigned long long *flag = g.p2p_peer[r] + (size_t)g.p2p_parity * g.p2p_nranks + g.p2p_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(g.p2p_epoch) : "memory");
+      }
+    }
+  }
+}
+
+// gather side, start of the kernel: wait (bounded) until every rank's flag shows this epoch; returns false on timeout
+__device__ __forceinline__ bool p2p_wait(const GridArgs &g) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if ((int)threadIdx.x < g.p2p_nranks) {
+    const unsigned long long *flag = g.p2p_peer[g.p2p_rank] + (size_t)g.p2p_parity * g.p2p_nranks + threadIdx.x;
+    unsigned long long seen = 0;
+    long long spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+      if (seen >= g.p2p_epoch) break;
+      if (++spins > 200000000LL) {  // seconds: a peer died; report instead of hanging the GPU
+        s_ok = 0;
+        if (blockIdx.x == 0) atomicAdd(g.p2p_timeouts, 1ULL);
+        break;
+      }
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+// gather side: the all-reduced value = sum over ranks in rank order (bitwise identical on every rank)
+__device__ __forceinline__ double p2p_sum(const GridArgs &g, int idx) {
+  const int count = (g.matrix_path ? g.nspecies : 1) * g.nx;
+  double t = p2p_data(g.p2p_peer[g.p2p_rank], g.p2p_nranks, count, g.p2p_parity, 0)[idx];
+  for (int r = 1; r < g.p2p_nranks; r++)
+    t = dadd(t, p2p_data(g.p2p_peer[g.p2p_rank], g.p2p_nranks, count, g.p2p_parity, r)[idx]);
+  return t;
+}
 
 // CTA = 32 cells x 8 warps.  Warp q sums the private grids q, q+8, q+16, ... of its 32 cells in that order (4 loads
 // in flight), then warp 0 adds the 8 partial sums in warp order: a fixed summation tree, hence deterministic.
@@ -57,27 +125,40 @@ __global__ void __launch_bounds__(256) k_reduce_charge(const GridArgs g) {
       double t = s_part[0][lane];
 #pragma unroll
       for (int q = 1; q < 8; q++) t = dadd(t, s_part[q][lane]);
-      if (g.matrix_path)
-        g.red[(size_t)s * g.nx + j] = t;  // field_tmp = S^T w per species (:52-59)
-      else
+      if (g.matrix_path) {  // field_tmp = S^T w per species (:52-59)
+        if (g.p2p_nranks) p2p_store(g, s * g.nx + j, t);
+        else g.red[(size_t)s * g.nx + j] = t;
+      } else {
         c2 = dadd(c2, dmul(t, g.Z[s]));   // charge2 += charge1 * Z (:126-127)
+      }
     }
     __syncthreads();
   }
-  if (wq == 0 && j < g.nx && !g.matrix_path) g.red[j] = c2;
+  if (wq == 0 && j < g.nx && !g.matrix_path) {
+    if (g.p2p_nranks) p2p_store(g, j, c2);
+    else g.red[j] = c2;
+  }
+  if (g.p2p_nranks) p2p_publish(g);  // MPI_Allreduce (:132-133), scatter half
 }
 
 // rho from the (all-)reduced grid: charge1 * nx / lx and the full-f offset (:140-148); matrix path :64-78
+__device__ __forceinline__ double red_value(const GridArgs &g, int idx) {
+  if (!g.p2p_nranks) return g.red[idx];
+  const double t = p2p_sum(g, idx);  // MPI_Allreduce (:132-133), gather half
+  g.red[idx] = t;
+  return t;
+}
+
 __device__ __forceinline__ double finalize_rho(const GridArgs &g, int j) {
   double rho;
   if (!g.matrix_path) {
-    rho = ddiv(dmul(g.red[j], g.rnx), g.lx);  // :140-141
+    rho = ddiv(dmul(red_value(g, j), g.rnx), g.lx);  // :140-141
     if (!g.deltaf)
       for (int s = 0; s < g.nspecies; s++) rho = dsub(rho, dmul(g.Z[s], g.n[s]));  // :142-148
   } else {
     rho = 0.0;  // :47
     for (int s = 0; s < g.nspecies; s++) {
-      double t = g.red[(size_t)s * g.nx + j];
+      double t = red_value(g, s * g.nx + j);
       if (!g.deltaf) t = dsub(t, ddiv(dmul(g.n[s], g.lx), g.rnx));  // :67
       rho = dadd(rho, dmul(g.Z[s], t));                              // VecAXPY :71
     }
@@ -87,8 +168,9 @@ __device__ __forceinline__ double finalize_rho(const GridArgs &g, int j) {
 }
 
 __global__ void __launch_bounds__(128) k_finalize_rho(const GridArgs g) {
+  const bool ok = g.p2p_nranks ? p2p_wait(g) : true;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < g.nx) g.rho[j] = finalize_rho(g, j);
+  if (j < g.nx) g.rho[j] = ok ? finalize_rho(g, j) : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // Single CTA, 1024 threads.  smem: rho[nx] + 2*nmode mode values.
@@ -102,10 +184,11 @@ __global__ void __launch_bounds__(1024) k_field_solve(const GridArgs g) {
   double *s_re = smem + g.nx;
   double *s_im = s_re + g.nmode;
   const int M = g.nmode, nx = g.nx;
+  const bool p2p_ok = (FINALIZE && g.p2p_nranks) ? p2p_wait(g) : true;
   for (int j = threadIdx.x; j < nx; j += blockDim.x) {
     double r;
     if (FINALIZE) {
-      r = finalize_rho(g, j);
+      r = p2p_ok ? finalize_rho(g, j) : __longlong_as_double(0x7ff8000000000000LL);
       g.rho[j] = r;
     } else {
       r = g.rho[j];

@@ -101,6 +101,14 @@ struct pic1dp_gpu {
   bool partial_valid = false;  // a fused push has already deposited into d_partial
   int nred = 1;
   ncclComm_t comm = nullptr;
+  // peer-memory all-reduce
+  unsigned long long *d_xchg = nullptr;       // my exchange buffer (flags + data), exported over IPC
+  unsigned long long *peer_base[8] = {};      // mapped buffers of all ranks (peer_base[rank] == d_xchg)
+  unsigned int *d_p2p_counter = nullptr;
+  unsigned long long *d_p2p_timeouts = nullptr;
+  bool p2p_ready = false;
+  unsigned long long p2p_epoch = 0;
+  int64_t p2p_calls = 0;
   int64_t launches = 0, nccl_calls = 0, h2d = 0, d2h = 0;
   std::string err;
 };
@@ -334,6 +342,11 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
   for (double *b : bufs)
     if (b) cudaFree(b);
   if (h->d_noob) cudaFree(h->d_noob);
+  for (int r = 0; r < 8; r++)
+    if (h->peer_base[r] && h->peer_base[r] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
+  if (h->d_xchg) cudaFree(h->d_xchg);
+  if (h->d_p2p_counter) cudaFree(h->d_p2p_counter);
+  if (h->d_p2p_timeouts) cudaFree(h->d_p2p_timeouts);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t e : h->pev)
@@ -545,6 +558,49 @@ int pic1dp_gpu_comm_init(pic1dp_gpu_t *h, const uint8_t id[PIC1DP_UNIQUE_ID_BYTE
   return PIC1DP_OK;
 }
 
+static size_t xchg_bytes(const pic1dp_gpu_t *h) {
+  const size_t flag_bytes = ((size_t)2 * h->p.nranks * 8 + 255) & ~(size_t)255;
+  return flag_bytes + (size_t)2 * h->p.nranks * h->nred * h->p.nx * 8;
+}
+
+int pic1dp_gpu_p2p_export(pic1dp_gpu_t *h, uint8_t handle[PIC1DP_IPC_HANDLE_BYTES]) {
+  if (!h || !handle) return PIC1DP_EINVAL;
+  if (h->p.nranks < 2 || h->p.nranks > 8) { h->err = "p2p all-reduce needs 2..8 ranks"; return PIC1DP_EUNSUPPORTED; }
+  CK(cudaSetDevice(h->p.device));
+  if (!h->d_xchg) {
+    CK(cudaMalloc(&h->d_xchg, xchg_bytes(h)));
+    CK(cudaMemset(h->d_xchg, 0, xchg_bytes(h)));
+    CK(cudaMalloc(&h->d_p2p_counter, 4));
+    CK(cudaMemset(h->d_p2p_counter, 0, 4));
+    CK(cudaMalloc(&h->d_p2p_timeouts, 8));
+    CK(cudaMemset(h->d_p2p_timeouts, 0, 8));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == PIC1DP_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  cudaIpcMemHandle_t ipc;
+  CK(cudaIpcGetMemHandle(&ipc, h->d_xchg));
+  memcpy(handle, &ipc, sizeof(ipc));
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_p2p_import(pic1dp_gpu_t *h, const uint8_t *all_handles) {
+  if (!h || !all_handles) return PIC1DP_EINVAL;
+  if (!h->d_xchg) { h->err = "p2p_import before p2p_export"; return PIC1DP_ESTATE; }
+  CK(cudaSetDevice(h->p.device));
+  for (int r = 0; r < h->p.nranks; r++) {
+    if (r == h->p.rank) {
+      h->peer_base[r] = h->d_xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, all_handles + (size_t)r * PIC1DP_IPC_HANDLE_BYTES, sizeof(ipc));
+    void *ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_base[r] = (unsigned long long *)ptr;
+  }
+  h->p2p_ready = true;
+  return PIC1DP_OK;
+}
+
 int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const double *x, const double *v,
                            const double *p, const double *w) {
   if (!h || isp < 0 || isp >= h->p.nspecies || np < 0 || !x || !v || !p || !w) {
@@ -613,6 +669,15 @@ static void fill_grid_args(pic1dp_gpu_t *h, GridArgs &g) {
   g.a_re = 1.0 / (double)p.nx;
   g.nx_over_lx = (double)p.nx / p.lx;
   g.energy = h->d_energy;
+  if (p.nranks > 1 && h->p2p_ready) {  // current all-reduce epoch (advanced by reduce_charge)
+    g.p2p_nranks = p.nranks;
+    g.p2p_rank = p.rank;
+    g.p2p_epoch = h->p2p_epoch;
+    g.p2p_parity = (int)(h->p2p_epoch & 1);
+    for (int r = 0; r < p.nranks; r++) g.p2p_peer[r] = h->peer_base[r];
+    g.p2p_counter = h->d_p2p_counter;
+    g.p2p_timeouts = h->d_p2p_timeouts;
+  }
 }
 
 static void fill_particle_args(pic1dp_gpu_t *h, int s, ParticleArgs &a) {
@@ -703,11 +768,16 @@ int pic1dp_gpu_get_shape_x(pic1dp_gpu_t *h, int32_t isp, int32_t *indexes, doubl
 
 // sum of the private grids (+ species charge), all-reduce over ranks, optionally rho = ... (k_finalize_rho)
 static int reduce_charge(pic1dp_gpu_t *h, bool finalize) {
+  if (h->p.nranks > 1 && h->p2p_ready) h->p2p_epoch++;  // a new all-reduce
   GridArgs g;
   fill_grid_args(h, g);
   k_reduce_charge<<<(h->p.nx + 31) / 32, 256, 0, h->stream>>>(g);
   CKL(h);
-  if (h->p.nranks > 1) {
+  if (h->p.nranks > 1 && h->p2p_ready) {
+    // all-reduce through peer memory: the reduce kernel above already scattered (it was launched with the p2p
+    // arguments), the finalize / solve kernel gathers
+    h->p2p_calls++;
+  } else if (h->p.nranks > 1) {
     if (!h->comm) { h->err = "collect_charge: nranks > 1 but comm_init was not called"; return PIC1DP_ESTATE; }
     ncclResult_t r = g_nccl.AllReduce(h->d_red, h->d_red, (size_t)h->nred * h->p.nx, ncclDouble, ncclSum, h->comm,
                                       h->stream);  // MPI_Allreduce, src/pic1dp_interaction.F90:132-133
@@ -1110,6 +1180,13 @@ int pic1dp_gpu_get_counters(pic1dp_gpu_t *h, pic1dp_counters *c) {
   CK(cudaStreamSynchronize(h->stream));
   c->kernel_launches = h->launches;
   c->nccl_calls = h->nccl_calls;
+  c->p2p_allreduces = h->p2p_calls;
+  c->p2p_timeouts = 0;
+  if (h->d_p2p_timeouts) {
+    unsigned long long t = 0;
+    CK(cudaMemcpy(&t, h->d_p2p_timeouts, 8, cudaMemcpyDeviceToHost));
+    c->p2p_timeouts = (int64_t)t;
+  }
   c->oob_markers = (int64_t)noob;
   c->h2d_bytes = h->h2d;
   c->d2h_bytes = h->d2h;

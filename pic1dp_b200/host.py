@@ -97,6 +97,17 @@ class Pic1dGpu:
         buf = (C.c_uint8 * _capi.UNIQUE_ID_BYTES).from_buffer_copy(uid)
         self._ck(self.L.pic1dp_gpu_comm_init(self._h, buf), "pic1dp_gpu_comm_init")
 
+    def p2p_export(self) -> bytes:
+        buf = (C.c_uint8 * _capi.IPC_HANDLE_BYTES)()
+        self._ck(self.L.pic1dp_gpu_p2p_export(self._h, buf), "pic1dp_gpu_p2p_export")
+        return bytes(buf)
+
+    def p2p_import(self, handles):
+        """handles: list of nranks 64-byte IPC handles in rank order (all-gathered by the host)."""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._ck(self.L.pic1dp_gpu_p2p_import(self._h, buf), "pic1dp_gpu_p2p_import")
+
     # ---- markers ----
     def set_markers(self, isp: int, x, v, p, w):
         n = x.size

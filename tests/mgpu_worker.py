@@ -21,6 +21,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     dep = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    p2p = len(sys.argv) > 2 and sys.argv[2] == "p2p"
     n, nx, nsteps = 400003, 256, 5
     op, gp = make_params(nx=nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=dep)
     st = synth_markers(op, n, seed=99)
@@ -29,6 +30,10 @@ def main():
     uid = [g.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     g.comm_init(uid[0])
+    if p2p:  # density all-reduce through peer memory instead of NCCL
+        handles = [None] * world
+        dist.all_gather_object(handles, g.p2p_export())
+        g.p2p_import(handles)
     g.set_markers(0, *(np.ascontiguousarray(st[k][lo:hi]) for k in ("x", "v", "p", "w")))
     g.collect_charge()
     g.solve_field()
@@ -53,9 +58,11 @@ def main():
         e_rho, e_E = rel_err(f["chargeden"], ref.rho), rel_err(f["electric"], ref.E)
         e_mk = max(rel_err(parts[r][k], ref.st[0][r][k]) for r in range(world) for k in ("x", "v", "w"))
         c = g.counters()
-        good = ok and e_rho < 1e-12 and e_E < 1e-12 and e_mk < 1e-12 and c.nccl_calls == 2 * nsteps + 1
+        ncoll = 2 * nsteps + 1
+        coll_ok = (c.p2p_allreduces == ncoll and c.p2p_timeouts == 0 and c.nccl_calls == 0) if p2p else c.nccl_calls == ncoll
+        good = ok and e_rho < 1e-12 and e_E < 1e-12 and e_mk < 1e-12 and coll_ok
         print(("MGPU_OK" if good else "MGPU_FAIL"), f"world={world} rho={e_rho:.2e} E={e_E:.2e} markers={e_mk:.2e} "
-              f"replicated_equal={ok} nccl_calls={c.nccl_calls}", flush=True)
+              f"replicated_equal={ok} nccl_calls={c.nccl_calls} p2p={c.p2p_allreduces} timeouts={c.p2p_timeouts}", flush=True)
     g.close()
     dist.destroy_process_group()
 
