@@ -46,7 +46,8 @@ type, bind(c), public :: pic1dp_params
   integer(c_int32_t) :: deposit_mode
   integer(c_int32_t) :: field_mode
   integer(c_int32_t) :: fuse
-  integer(c_int32_t) :: reserved(8)
+  integer(c_int32_t) :: load_path
+  integer(c_int32_t) :: reserved(7)
 end type pic1dp_params
 
 interface
@@ -109,6 +110,29 @@ interface
     type(c_ptr), value :: handle
     real(c_double), intent(out) :: electric(*), chargeden(*), mode_re(*), mode_im(*)
   end function
+  integer(c_int) function pic1dp_gpu_p2p_export(handle, ipc) bind(c, name = 'pic1dp_gpu_p2p_export')
+    import :: c_ptr, c_int8_t, c_int
+    type(c_ptr), value :: handle
+    integer(c_int8_t), intent(out) :: ipc(64)
+  end function
+  integer(c_int) function pic1dp_gpu_p2p_import(handle, all_ipc) bind(c, name = 'pic1dp_gpu_p2p_import')
+    import :: c_ptr, c_int8_t, c_int
+    type(c_ptr), value :: handle
+    integer(c_int8_t), intent(in) :: all_ipc(*)
+  end function
+  integer(c_int) function pic1dp_gpu_output_field(handle, scalars) bind(c, name = 'pic1dp_gpu_output_field')
+    import :: c_ptr, c_int, c_double
+    type(c_ptr), value :: handle
+    real(c_double), intent(out) :: scalars(*)
+  end function
+  integer(c_int) function pic1dp_gpu_output_ptcldist(handle, isp, nx_opd, nv_opd, v_max, markr_xv, total_xv, &
+      pertb_xv, markr_v, total_v, pertb_v) bind(c, name = 'pic1dp_gpu_output_ptcldist')
+    import :: c_ptr, c_int, c_int32_t, c_double
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: isp, nx_opd, nv_opd
+    real(c_double), value :: v_max
+    real(c_double), intent(out) :: markr_xv(*), total_xv(*), pertb_xv(*), markr_v(*), total_v(*), pertb_v(*)
+  end function
   integer(c_int) function pic1dp_gpu_sync(handle) bind(c, name = 'pic1dp_gpu_sync')
     import :: c_ptr, c_int
     type(c_ptr), value :: handle
@@ -122,6 +146,7 @@ public :: pic1dp_gpu_comm_unique_id, pic1dp_gpu_comm_init
 public :: pic1dp_gpu_set_markers, pic1dp_gpu_get_markers, pic1dp_gpu_compute_shape_x
 public :: pic1dp_gpu_collect_charge, pic1dp_gpu_solve_field, pic1dp_gpu_push
 public :: pic1dp_gpu_get_field, pic1dp_gpu_sync
+public :: pic1dp_gpu_p2p_export, pic1dp_gpu_p2p_import, pic1dp_gpu_output_field, pic1dp_gpu_output_ptcldist
 
 end module pic1dp_gpu
 
@@ -148,7 +173,7 @@ implicit none
 #include "finclude/petsc.h90"
 PetscInt, intent(in) :: local_capacity   ! particle_ip_high - particle_ip_low
 type(pic1dp_params) :: p
-integer(c_int8_t) :: id(128)
+integer(c_int8_t) :: id(128), ipc_mine(64), ipc_all(64 * 8)
 integer :: imode
 
 call pic1dp_gpu_params_default(p)
@@ -188,6 +213,15 @@ if (global_npe > 1) then
   CHKERRQ(global_ierr)
   global_ierr = pic1dp_gpu_comm_init(gpu_handle, id)
   CHKERRQ(global_ierr)
+  ! optional: density all-reduce through peer memory (NVLink) instead of ncclAllReduce
+  if (global_npe <= 8) then
+    global_ierr = pic1dp_gpu_p2p_export(gpu_handle, ipc_mine)
+    CHKERRQ(global_ierr)
+    call MPI_Allgather(ipc_mine, 64, MPI_BYTE, ipc_all, 64, MPI_BYTE, MPI_COMM_WORLD, global_ierr)
+    CHKERRQ(global_ierr)
+    global_ierr = pic1dp_gpu_p2p_import(gpu_handle, ipc_all)
+    CHKERRQ(global_ierr)
+  end if
 end if
 end subroutine gpu_init
 
@@ -316,6 +350,30 @@ if (im_high > im_low) then
   CHKERRQ(global_ierr)
 end if
 end subroutine gpu_field_refresh_host
+
+! scalar part of output_field (src/pic1dp_output.F90:117-172) from device-side reductions: realbuf(2:) of the
+! reference = scalars(1:1+3*nspecies); no marker array crosses PCIe
+subroutine gpu_output_field_scalars(realbuf)
+implicit none
+#include "finclude/petsc.h90"
+PetscReal, dimension(2 + input_nspecies * 3), intent(inout) :: realbuf
+real(c_double) :: scalars(1 + 3 * input_nspecies)
+global_ierr = pic1dp_gpu_output_field(gpu_handle, scalars)
+CHKERRQ(global_ierr)
+realbuf(2 : 2 + 3 * input_nspecies) = scalars(1 : 1 + 3 * input_nspecies)
+end subroutine gpu_output_field_scalars
+
+! the six arrays of output_ptcldist (src/pic1dp_output.F90:196-477) for one species, binned on the device
+subroutine gpu_output_ptcldist(ispecies, markr_xv, total_xv, pertb_xv, markr_v, total_v, pertb_v)
+implicit none
+#include "finclude/petsc.h90"
+PetscInt, intent(in) :: ispecies
+PetscScalar, dimension(0 : input_nx_opd * input_nv_opd - 1), intent(out) :: markr_xv, total_xv, pertb_xv
+PetscScalar, dimension(0 : input_nv_opd - 1), intent(out) :: markr_v, total_v, pertb_v
+global_ierr = pic1dp_gpu_output_ptcldist(gpu_handle, int(ispecies - 1, c_int32_t), int(input_nx_opd, c_int32_t), &
+  int(input_nv_opd, c_int32_t), real(input_v_max, c_double), markr_xv, total_xv, pertb_xv, markr_v, total_v, pertb_v)
+CHKERRQ(global_ierr)
+end subroutine gpu_output_ptcldist
 
 ! particle_final + field_final (src/pic1dp_particle.F90:819-858, src/pic1dp_field.F90:315-348)
 subroutine gpu_final

@@ -413,3 +413,51 @@ def test_tma_ring_path_against_oracle(dep, case):
         assert rel_err(f["chargeden"], ref.rho, scale) < TOL_SUM, n
         for k in ("x", "v", "w"):
             assert rel_err(out[k], ref.st[0][0][k]) < 1e-12, (n, k)
+
+
+@pytest.mark.parametrize("dep", DEPOSITS)
+@pytest.mark.parametrize("nx,nmode", [(2, 1), (3, 1), (193, 2), (1001, 3), (64, 32)])
+def test_odd_and_extreme_grid_sizes(dep, nx, nmode):
+    """nx = 2 (both neighbours are the only other cell), odd nx (16-byte alignment of the pair grid after the E copy),
+    many kept modes."""
+    modes = list(range(1, nmode + 1)) if nmode < nx else [1]
+    op, gp = make_params(nx=nx, nmode=len(modes), modes=modes, capacity=30011, deposit_mode=dep)
+    st = synth_markers(op, 30011, seed=90 + nx, spread=0.6)
+    ref = OracleRun(op, [[copy_state(st)]])
+    ref.init_field()
+    for _ in range(3):
+        ref.step()
+    with _gpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        g.collect_charge()
+        g.solve_field()
+        g.step(3)
+        f = g.get_field()
+        out = g.get_markers(0)
+    assert rel_err(f["chargeden"], ref.rho) < TOL_SUM
+    assert rel_err(f["electric"], ref.E, max(np.abs(ref.E).max(), 1e-300)) < 1e-11
+    for k in ("x", "v", "w"):
+        assert rel_err(out[k], ref.st[0][0][k]) < 1e-12, k
+
+
+def test_max_species_and_modes_limits():
+    op, gp = make_params(nx=128, nspecies=4, charge=[-1.0, 1.0, -1.0, 2.0], mass=[1.0, 4.0, 1.0, 8.0],
+                         temperature=[1.0, 0.5, 2.0, 1.0], temperature2=[1.0, 0.5, 1.0, 1.0],
+                         density=[0.9, 1.0, 0.5, 0.25], v0=[5.0, 0.0, 3.0, 1.0], nmode=4, modes=[1, 2, 3, 4], capacity=20000)
+    sts = [synth_markers(op, 20000 - 3 * s, seed=100 + s, isp=s) for s in range(4)]
+    ref = OracleRun(op, [[copy_state(s)] for s in sts])
+    ref.init_field()
+    ref.step()
+    ref.step()
+    with _gpu(gp) as g:
+        for s, st in enumerate(sts):
+            g.set_markers(s, st["x"], st["v"], st["p"], st["w"])
+        g.collect_charge()
+        g.solve_field()
+        g.step(2)
+        f = g.get_field()
+        assert rel_err(f["chargeden"], ref.rho) < TOL_SUM and rel_err(f["electric"], ref.E) < TOL_SUM
+        for s in range(4):
+            out = g.get_markers(s)
+            for k in ("x", "v", "w"):
+                assert rel_err(out[k], ref.st[s][0][k]) < 1e-12, (s, k)
