@@ -408,6 +408,10 @@ static int create_impl(pic1dp_gpu_t *h) {
     return PIC1DP_EUNSUPPORTED;
   }
   h->threads = (dep == DEP_WARP_PRIVATE) ? warp_private_threads() : PIC1DP_MAXTHREADS / 2;
+  // large grids: when only one CTA's shared memory fits per SM, make that CTA as large as the SM allows
+  if (dep != DEP_WARP_PRIVATE &&
+      2 * (smem_need(dep, h->threads) + 1024) > (size_t)prop.sharedMemPerMultiprocessor)
+    h->threads = PIC1DP_MAXTHREADS;
   if (h->threads < 32 || smem_need(dep, h->threads) > max_smem) {
     h->err = "shared-memory grid does not fit for this nx with the requested deposit_mode";
     return PIC1DP_EUNSUPPORTED;
