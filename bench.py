@@ -106,6 +106,23 @@ class ClockSampler:
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         import datetime
+        parsed = []
+        for ts, line in self.rows:
+            f = [t.strip() for t in line.split(",")]
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                pass
+            parsed.append((ts, line))
+        inside = [r for r in parsed if t0 - 0.02 <= r[0] <= t1 + 0.05]
+        note = None
+        if not inside and parsed:  # sampling period stretched beyond the timed region: use the closest samples
+            mid = 0.5 * (t0 + t1)
+            inside = sorted(parsed, key=lambda r: abs(r[0] - mid))[:3]
+            note = "no sample fell inside the %.0f ms timed region; nearest samples used (%.2f s away)" % (
+                1e3 * (t1 - t0), min(abs(r[0] - mid) for r in inside))
+            t0, t1 = min(r[0] for r in inside), max(r[0] for r in inside)
+        self.rows = inside
         for ts, line in self.rows:
             f = [t.strip() for t in line.split(",")]
             try:  # nvidia-smi's own timestamp (its stdout is block-buffered when piped, so arrival time is late)
@@ -123,8 +140,11 @@ class ClockSampler:
             for name, val in zip(names, f[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def measured_peak():
@@ -256,6 +276,25 @@ def main():
         t = torch.tensor([val], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---- peer-memory all-reduce sanity: one step, then every rank must report no timeout and a finite field ----
+    if world > 1 and args.allreduce != "nccl":
+        g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])
+        g.collect_charge()
+        g.solve_field()
+        g.step(1)
+        bad = float(g.counters().p2p_timeouts > 0 or not np.isfinite(g.field_energy()))
+        bad = max_over_ranks(bad)
+        if bad > 0:
+            if args.allreduce == "p2p":
+                raise SystemExit("peer-memory all-reduce failed (timeouts or non-finite field)")
+            if rank == 0:
+                print("peer-memory all-reduce failed its sanity step; falling back to NCCL", file=sys.stderr)
+            g.close()
+            g = P.Pic1dGpu(gp)
+            uid = [g.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            g.comm_init(uid[0])
 
     # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local)
