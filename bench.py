@@ -320,10 +320,19 @@ def main():
     # ---- roofline of the dominant kernel, CUDA events around each launch ----
     prof = np.array([g.profile_step() for _ in range(5)])[1:].mean(axis=0)  # ms: push1, collect1, field1, push2, ...
     peak, peak_src = measured_peak()
+    # dram__bytes_read + dram__bytes_write of this kernel from the committed `ncu --set full` capture, scaled per marker
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if int(c1.deposit_mode) == 1 and args.nx == 1024:
+            traffic = tj["irk2"]["dram_bytes_per_marker"] * n
+            traffic_src = tj["source"] + "; per-marker DRAM bytes x markers of this launch"
+    except Exception:
+        pass
     ach2 = n * BYTES_IRK2 / (prof[3] * 1e-3) / 1e9
     ach1 = n * BYTES_IRK1 / (prof[0] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_push<bump-on-tail, irk=2, fused push+wrap+deposit>",
-                "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "traffic": None,
+                "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "ms_per_launch": float(prof[3]),
                 "algorithmic_bytes_per_launch": n * BYTES_IRK2}
     roofline_detail = {
