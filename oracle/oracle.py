@@ -53,10 +53,15 @@ class OrcRankState(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc -O3 -ffp-contract=off)."""
+    import hashlib
     srcs = [os.path.join(_HERE, f) for f in ("pic1dp_oracle.c", "multirand_oracle.c", "pic1dp_oracle.h", "Makefile")]
-    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    hh = hashlib.sha256(b"".join(open(s, "rb").read() for s in srcs)).hexdigest()  # mtimes do not survive gpurun
+    hpath = _LIB_PATH + ".hash"
+    stale = (not os.path.exists(_LIB_PATH)) or (not os.path.exists(hpath)) or open(hpath).read().strip() != hh
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+        with open(hpath, "w") as f:
+            f.write(hh)
     return _LIB_PATH
 
 
