@@ -569,16 +569,16 @@ struct Depositor<DEP_GLOBAL_RED> {
   }
 };
 
-// per-warp private shared grid, no atomics.  Lanes of one instruction that hit the same cell are merged with
-// MATCH.ANY: every lane sums its peers' contributions in ascending lane order, the lowest lane does the
-// read-modify-write.  Fixed marker->lane mapping + fixed order => bitwise run-to-run deterministic.
-// Must be called by all 32 lanes (invalid lanes pass valid=false).
+// per-warp private shared grid, no atomics.  Lanes of one instruction that hit the same cell are found with
+// MATCH.ANY and take turns in ascending lane order (round r: the r-th lane of every group does its
+// read-modify-write), so each cell receives its contributions in marker order.  Fixed marker->lane mapping + fixed
+// order => bitwise run-to-run deterministic.  Must be called by all 32 lanes (invalid lanes pass valid=false).
 template <>
 struct Depositor<DEP_WARP_PRIVATE> {
   double *g;  // this warp's grid
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const unsigned lane = threadIdx.x & 31;
     if (!valid) {  // joins the ix == 0 group with zero contributions; ixr must agree with that group's (nx >= 2)
       ix = 0;
       ixr = 1;
@@ -586,28 +586,16 @@ struct Depositor<DEP_WARP_PRIVATE> {
       b = 0.0;
     }
     const unsigned peers = __match_any_sync(full, ix);
-    const bool leader = (__ffs(peers) - 1) == lane;
-    double A = a, B = b;
-    if (__any_sync(full, peers != (1u << lane))) {
-      const int maxc = __reduce_max_sync(full, (unsigned)__popc(peers));
-      unsigned rem = peers;
-      A = 0.0;
-      B = 0.0;
-      for (int k = 0; k < maxc; k++) {
-        const int src = rem ? (__ffs(rem) - 1) : lane;
-        const double ta = __shfl_sync(full, a, src);
-        const double tb = __shfl_sync(full, b, src);
-        if (rem) {
-          A = (k == 0) ? ta : dadd(A, ta);
-          B = (k == 0) ? tb : dadd(B, tb);
-          rem &= rem - 1;
-        }
-      }
+    const int myturn = __popc(peers & ((1u << lane) - 1u));
+    const int rounds = (int)__reduce_max_sync(full, (unsigned)__popc(peers));  // warp-uniform, 1 when no lane collides
+    for (int r = 0; r < rounds; r++) {
+      if (myturn == r) g[ix] = dadd(g[ix], a);
+      __syncwarp();
     }
-    if (leader) g[ix] = dadd(g[ix], A);
-    __syncwarp();
-    if (leader) g[ixr] = dadd(g[ixr], B);
-    __syncwarp();
+    for (int r = 0; r < rounds; r++) {  // same groups: equal ix means equal ixr
+      if (myturn == r) g[ixr] = dadd(g[ixr], b);
+      __syncwarp();
+    }
   }
 };
 
