@@ -599,11 +599,27 @@ struct Depositor<DEP_WARP_PRIVATE> {
   }
 };
 
-// streaming (evict-first) global accesses: marker arrays are touched once per substep
+// Marker arrays are touched once per substep.  Measured on B200 (profiles/r01_ab_experiments.md): the default cache
+// policy beats the streaming hints (.cs evict-first loads/stores cost ~3% of the step; .cg is on par with default).
+#ifndef PIC1DP_EXP_MEMPOLICY
+#define PIC1DP_EXP_MEMPOLICY 0
+#endif
+#if PIC1DP_EXP_MEMPOLICY == 1  // experiment: streaming (evict-first) loads and stores
 __device__ __forceinline__ double2 ld2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
 __device__ __forceinline__ double ld1(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void st2(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
 __device__ __forceinline__ void st1(double *p, double v) { __stcs(p, v); }
+#elif PIC1DP_EXP_MEMPOLICY == 3  // experiment: L2-only (cg) loads and stores
+__device__ __forceinline__ double2 ld2(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ double ld1(const double *p) { return __ldcg(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { __stcg(reinterpret_cast<double2 *>(p), v); }
+__device__ __forceinline__ void st1(double *p, double v) { __stcg(p, v); }
+#else
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double ld1(const double *p) { return *p; }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+__device__ __forceinline__ void st1(double *p, double v) { *p = v; }
+#endif
 // pull the line a later tile step will read into L2 (no destination register, no scoreboard wait)
 __device__ __forceinline__ void prefetch_l2(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -771,12 +787,17 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
 
 // ------------------------------------------------------------------------------------------------------------
 // TMA-pipelined variant of the fused substep kernel (delta-f, nonlinear; the flagship path).
-// Marker tiles of TILE markers are streamed into a STAGES-deep shared-memory ring with 1-D bulk copies
-// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) issued by one thread STAGES-1 tiles ahead; consumers wait on
-// the stage's "full" mbarrier, pull their marker into registers, release the stage ("empty" mbarrier, one arrival per
-// warp) and compute.  Loads never occupy registers or stall a warp on the scoreboard, and warps may drift up to
-// STAGES-1 tiles apart.  One marker per thread per tile; outputs go straight to global memory.
+// Marker tiles of 2*blockDim markers are streamed into a 2-stage shared-memory ring with 1-D bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) issued by one thread one tile ahead; consumers wait on the
+// stage's "full" mbarrier, pull their 2 markers into registers with 128-bit shared loads, release the stage ("empty"
+// mbarrier, one arrival per warp) and run the same 2-wide code as the direct kernel.  The next tile is in flight
+// while the current one is computed, which supplies the memory-level parallelism the direct kernel lacks (its
+// loads are only outstanding at the top of an iteration).  Outputs go straight to global memory.
 // ------------------------------------------------------------------------------------------------------------
+struct PairIn2 {
+  double2 x, v, w, p, xb, vb, wb;
+};
+
 namespace tma {
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -805,9 +826,9 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 
 template <int DIST, bool IRK2, int DEP, int CFG>
 __global__ void __launch_bounds__(1024, 1) k_push_tma(const ParticleArgs a) {
-  constexpr int TILE = 512;                 // == blockDim.x
   constexpr int NARR = IRK2 ? 7 : 4;        // x v w p [xb vb wb]
-  constexpr int STAGES = IRK2 ? 3 : 4;
+  constexpr int STAGES = 2;
+  const int TILE = 2 * blockDim.x;          // 2 markers per thread, one 128-bit shared load per array
   extern __shared__ __align__(16) double smem[];
   double *sE = smem;
   for (int j = threadIdx.x; j < a.nx; j += blockDim.x) sE[j] = a.E[j];
@@ -845,35 +866,55 @@ __global__ void __launch_bounds__(1024, 1) k_push_tma(const ParticleArgs a) {
   if (threadIdx.x == 0)
     for (int64_t k = 0; k < STAGES - 1 && k < my_tiles; k++) issue(k);
 
+  const int right_frac = Cfg<CFG>::right_frac(a.right_frac);
   unsigned long long noob = 0;
   for (int64_t k = 0; k < my_tiles; k++) {
     if (threadIdx.x == 0 && k + STAGES - 1 < my_tiles) issue(k + STAGES - 1);
     const int st = (int)(k % STAGES);
     tma::mbar_wait(full0 + 8 * st, (unsigned)((k / STAGES) & 1));
-    const double *rs = ring + (size_t)st * NARR * TILE + threadIdx.x;
-    const double x = rs[0], v = rs[TILE], w = rs[2 * TILE], p = rs[3 * TILE];
-    double xb = x, vb = v, wb = w;
+    const double2 *rs = reinterpret_cast<const double2 *>(ring + (size_t)st * NARR * TILE) + threadIdx.x;
+    const int T2 = TILE / 2;
+    PairIn2 in;
+    in.x = rs[0];
+    in.v = rs[T2];
+    in.w = rs[2 * T2];
+    in.p = rs[3 * T2];
     if (IRK2) {
-      xb = rs[4 * TILE];
-      vb = rs[5 * TILE];
-      wb = rs[6 * TILE];
+      in.xb = rs[4 * T2];
+      in.vb = rs[5 * T2];
+      in.wb = rs[6 * T2];
+    } else {
+      in.xb = in.x;
+      in.vb = in.v;
+      in.wb = in.w;
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) tma::mbar_arrive(empty0 + 8 * st);
-    const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * TILE + threadIdx.x;
-    const bool ok = i < a.np;
-    double xo = 0.0, vo = 0.0, wo = 0.0;
-    if (ok) {
-      push_one<DIST, CFG>(a, sE, x, v, w, p, xb, vb, wb, xo, vo, wo);
-      xo = wrap_x(xo, a.lx);
-      st1(a.x_out + i, xo);
-      st1(a.v_out + i, vo);
-      st1(a.w_out + i, wo);
+    const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * TILE + (int64_t)threadIdx.x * 2;
+    const bool ok0 = i < a.np, ok1 = i + 1 < a.np;
+    // invalid lanes of the last tile compute on harmless dummies (v = 1 keeps two-stream1's 2/v finite)
+    const double ax[2] = {ok0 ? in.x.x : 0.0, ok1 ? in.x.y : 0.0}, av[2] = {ok0 ? in.v.x : 1.0, ok1 ? in.v.y : 1.0};
+    const double aw[2] = {ok0 ? in.w.x : 0.0, ok1 ? in.w.y : 0.0}, ap[2] = {ok0 ? in.p.x : 0.0, ok1 ? in.p.y : 0.0};
+    const double axb[2] = {ok0 ? in.xb.x : 0.0, ok1 ? in.xb.y : 0.0}, avb[2] = {ok0 ? in.vb.x : 1.0, ok1 ? in.vb.y : 1.0};
+    const double awb[2] = {ok0 ? in.wb.x : 0.0, ok1 ? in.wb.y : 0.0};
+    double axo[2], avo[2], awo[2];
+    push_n<DIST, CFG, 2>(a, sE, ax, av, aw, ap, axb, avb, awb, axo, avo, awo);
+    wrap_n<2>(axo, a.lx);
+    Shape sd[2];
+    bool od[2];
+    shape_n<2>(axo, a.lx, a.rlx, a.rnx, a.nx, right_frac, sd, od);
+    if (ok1) {
+      st2(a.x_out + i, make_double2(axo[0], axo[1]));
+      st2(a.v_out + i, make_double2(avo[0], avo[1]));
+      st2(a.w_out + i, make_double2(awo[0], awo[1]));
+    } else if (ok0) {
+      st1(a.x_out + i, axo[0]);
+      st1(a.v_out + i, avo[0]);
+      st1(a.w_out + i, awo[0]);
     }
-    bool o0 = false;
-    const Shape s0 = shape_of(xo, a.lx, a.rlx, a.rnx, a.nx, Cfg<CFG>::right_frac(a.right_frac), o0);
-    dep.add(s0.ix, s0.ixr, dmul(s0.sl, wo), dmul(s0.sr, wo), ok);
-    noob += (ok && o0);
+    dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, awo[0]), dmul(sd[0].sr, awo[0]), ok0);
+    dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, awo[1]), dmul(sd[1].sr, awo[1]), ok1);
+    noob += (ok0 && od[0]) + (ok1 && od[1]);
   }
   dep_flush<DEP>(dep_base, a.nx, my_partial);
   if (noob) atomicAdd(a.noob, noob);

@@ -26,6 +26,15 @@
 
 using namespace pic1dp;
 
+// LOAD_AUTO: which substeps use the TMA ring (measured, see profiles/r01_ab_experiments.md)
+#ifndef PIC1DP_TMA_AUTO_IRK1
+#define PIC1DP_TMA_AUTO_IRK1 0
+#endif
+#ifndef PIC1DP_TMA_AUTO_IRK2
+#define PIC1DP_TMA_AUTO_IRK2 0
+#endif
+static const bool PIC1DP_TMA_AUTO_IRK[2] = {PIC1DP_TMA_AUTO_IRK1 != 0, PIC1DP_TMA_AUTO_IRK2 != 0};
+
 // ------------------------------------------------------------------------------------------------------------
 // NCCL is bound at run time (dlopen) and only when nranks > 1, so a single-GPU process never needs it and a
 // process that already loaded torch's bundled libnccl.so.2 reuses that copy.
@@ -96,7 +105,7 @@ struct pic1dp_gpu {
   int diag_grid = 0, hist_cells = 0, hist_copies = 16, hist_smem_set = -1, hist_per_sm = 1;
   size_t max_smem = 0;
   int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0, cfg = -1;
-  bool use_tma = false;
+  bool use_tma[2] = {false, false};  // per substep (irk = 1, 2)
   int tma_smem[2] = {0, 0};  // dynamic shared memory of the TMA kernels, irk = 1, 2
   bool partial_valid = false;  // a fused push has already deposited into d_partial
   int nred = 1;
@@ -433,32 +442,34 @@ static int create_impl(pic1dp_gpu_t *h) {
           if (fused && per_sm < per_sm_min) per_sm_min = per_sm;
         }
     if (per_sm_min < 1) per_sm_min = 1;
-    // TMA-pipelined variant (512 threads, ring of 3-4 stages): usable when it reaches the same residency
-    h->use_tma = false;
-    if (h->cfg == 1 && p.load_path != PIC1DP_LOAD_DIRECT && (dep != DEP_WARP_PRIVATE || h->threads >= 512)) {
+    // TMA-pipelined variant (2-stage ring of 2*threads markers): usable when it reaches the same residency.
+    // load_path TMA uses it for both substeps, AUTO only where it measured faster (profiles/r01_ab_experiments.md).
+    h->use_tma[0] = h->use_tma[1] = false;
+    if (h->cfg == 1 && p.load_path != PIC1DP_LOAD_DIRECT && dep != DEP_WARP_PRIVATE && h->threads == 512) {
       const int tthr = 512;
-      bool ok = true;
-      for (int irk2 = 0; irk2 < 2 && ok; irk2++) {
-        const size_t ring = (size_t)(irk2 ? 3 * 7 : 4 * 4) * 512 * 8 + 64;
+      for (int irk2 = 0; irk2 < 2; irk2++) {
+        const size_t ring = (size_t)2 * (irk2 ? 7 : 4) * (2 * tthr) * 8 + 64;
         const size_t need = 8 * (((size_t)(nx + 1) & ~(size_t)1) + (((size_t)nx * dep_grids(dep, tthr) + 1) & ~(size_t)1)) + ring;
         h->tma_smem[irk2] = (int)need;
-        if (need > max_smem) { ok = false; break; }
+        bool ok = need <= max_smem;
         const int cfgs3[3] = {1, 9, 25};
-        for (int ci = 0; ci < 3; ci++) {
+        for (int ci = 0; ci < 3 && ok; ci++) {
           PushKernel k = pick_tma(p.iptcldist, dep, irk2 == 1, cfgs3[ci]);
           CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
           int per_sm = 0;
           CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, tthr, need));
-          if (per_sm * tthr < per_sm_min * h->threads) ok = false;  // fewer resident threads than the direct kernel
-          if (ok && per_sm < per_sm_min) per_sm_min = per_sm;
+          if (per_sm < per_sm_min) ok = false;  // fewer resident CTAs than the direct kernel: not worth it
         }
+        const bool want = (p.load_path == PIC1DP_LOAD_TMA) || (p.load_path == PIC1DP_LOAD_AUTO && PIC1DP_TMA_AUTO_IRK[irk2]);
+        h->use_tma[irk2] = ok && want;
       }
-      // AUTO: measured faster only ... (decided from profiles/r01_tma_ab.md); explicit request always honoured
-      h->use_tma = ok && (p.load_path == PIC1DP_LOAD_TMA);
-      if (p.load_path == PIC1DP_LOAD_TMA && !ok) {
+      if (p.load_path == PIC1DP_LOAD_TMA && !h->use_tma[0] && !h->use_tma[1]) {
         h->err = "load_path = TMA: the shared-memory ring does not fit beside the deposit grids for this nx";
         return PIC1DP_EUNSUPPORTED;
       }
+    } else if (p.load_path == PIC1DP_LOAD_TMA) {
+      h->err = "load_path = TMA needs a delta-f nonlinear run with an atomic deposit mode";
+      return PIC1DP_EUNSUPPORTED;
     }
     h->grid = h->nsm * per_sm_min;  // persistent grid: every CTA resident, private grid per CTA
   }
@@ -864,7 +875,7 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
     a.v_out = S.v[out];
     a.w_out = S.w[out];
     const int cfg = (h->cfg == 1) ? (S.c.unit ? 25 : S.c.pow2 ? 9 : 1) : -1;
-    if (fused && h->use_tma && cfg > 0) {
+    if (fused && h->use_tma[irk - 1] && cfg > 0) {
       PushKernel k = pick_tma(p.iptcldist, h->dep, irk == 2, cfg);
       k<<<h->grid, 512, h->tma_smem[irk - 1], h->stream>>>(a);
     } else {
