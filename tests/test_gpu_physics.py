@@ -93,3 +93,55 @@ def test_cpp_host_driver_reproduces_oracle_loader_and_trace(tmp_path):
             en.append(o.field_energy(ref.E))
     assert np.max(np.abs(rows[:, 1] / np.array(en) - 1.0)) < 1e-9
     assert abs(rows[-1, 2] - ref.mode_re[0]) < 1e-9 * abs(ref.mode_im[0]) + 1e-20
+
+
+def test_landau_damping_from_a_ptcldist_file(tmp_path):
+    """BASELINE.json configs[2]: thermal plasma, k = 0.5, nx = 4096, markers sampled from a ptcldist_xv file.
+    A short Maxwellian run writes pic1dp.out; tools_py3/ptcldist.py exports the binned f like the reference's
+    tools/ptcldist.py; markers are re-sampled from that file and the delta-f run must show Landau damping at the
+    textbook rate gamma = -0.1533 (omega = 1.4156 - 0.1533 i at k lambda_D = 0.5)."""
+    from pic1dp_b200.output import OutputWriter
+    from tools_py3.output_data import OutputData
+    from tools_py3 import ptcldist
+    lx = 4.0 * np.pi
+    kw = dict(nx=4096, lx=lx, iptcldist=0, density=[1.0], v0=[0.0], capacity=4_000_000)
+    op, gp = make_params(**kw)
+    n = 4_000_000
+    # 1) a Maxwellian population, binned on the device and written in the reference's file format
+    rng = np.random.default_rng(5)
+    x = rng.random(n) * lx
+    v = (rng.random(n) - 0.5) * 16.0
+    p = lx * 16.0 / n * np.exp(-v * v / 2) / np.sqrt(2 * np.pi)
+    w = np.zeros(n)
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, x, v, p, w)
+        g.collect_charge()
+        g.solve_field()
+        with OutputWriter(tmp_path / "pic1dp.out", g) as out:
+            out.output_all(0.0)
+    od = OutputData(str(tmp_path / "pic1dp.out"))
+    paths = ptcldist.export_xv(od, 0, 0, 1, outdir=str(tmp_path))     # total distribution f
+    pd, xg, vg = ptcldist.load_xv(paths)
+    assert pd.shape == (64, 65) and abs(xg[-1] - lx) < 1e-12 and vg[0] == -8.0 and vg[-1] == 8.0
+    # 2) markers sampled from the file, cosine density perturbation, Landau damping
+    xs, vs, ps = ptcldist.sample_markers(pd, xg, vg, n, seed=6)
+    assert abs(np.sum(ps) / lx - 1.0) < 0.02                           # int f dv = n0 = 1
+    ws = 0.01 * np.cos(2 * np.pi / lx * xs) * ps
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, xs, vs, ps + ws, ws)
+        g.collect_charge()
+        g.solve_field()
+        t, en = [0.0], [g.field_energy()]
+        for k in range(1, 161):
+            g.step(2)
+            t.append(0.1 * k)
+            en.append(g.field_energy())
+        assert g.counters().oob_markers == 0
+    t, en = np.array(t), np.array(en)
+    pk = [i for i in range(1, len(en) - 1) if en[i] > en[i - 1] and en[i] > en[i + 1] and 1.0 < t[i] < 14.0]
+    assert len(pk) >= 4
+    slope = np.polyfit(t[pk], np.log(en[pk]), 1)[0]                    # energy envelope ~ exp(2 gamma t)
+    gamma = slope / 2.0
+    period = np.mean(np.diff(t[pk]))                                   # energy oscillates at 2 omega_r
+    assert abs(gamma / -0.1533 - 1.0) < 0.08, gamma
+    assert abs((np.pi / period) / 1.4156 - 1.0) < 0.05, period
