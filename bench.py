@@ -69,6 +69,15 @@ def fill_markers(x, v, p, w, lx, seed, chunk=1 << 24):
         x[lo:hi], v[lo:hi], w[lo:hi], p[lo:hi] = xs, vs, ww, pp + ww
 
 
+def fill_uniforms(u_v, u_x, seed, chunk=1 << 24):
+    """The two uniform [0, 1) streams particle_load draws (v first, then x), in place (numpy PCG64)."""
+    rng = np.random.default_rng(seed)
+    for arr in (u_v, u_x):
+        for lo in range(0, arr.size, chunk):
+            hi = min(arr.size, lo + chunk)
+            arr[lo:hi] = rng.random(hi - lo)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
 
@@ -256,11 +265,15 @@ def main():
                     raise
                 print(f"[rank {rank}] peer-memory all-reduce unavailable, using NCCL: {e}", file=sys.stderr)
 
-    # ---- synthetic markers in pinned host memory ----
-    host = {k: torch.empty(n, dtype=torch.float64, pin_memory=True) for k in ("x", "v", "p", "w")}
+    # ---- synthetic inputs in pinned host memory: the two uniform streams particle_load draws (RNG stays on the
+    # host, like multirand); x, v, p, w host buffers receive the loaded markers for the host-refresh variants ----
+    host = {k: torch.empty(n, dtype=torch.float64, pin_memory=True) for k in ("x", "v", "p", "w", "u_v", "u_x")}
     hv = {k: t.numpy() for k, t in host.items()}
-    fill_markers(hv["x"], hv["v"], hv["p"], hv["w"], gp.lx, seed=1234 + rank)
+    fill_uniforms(hv["u_v"], hv["u_x"], seed=1234 + rank)
     ptr = {k: t.data_ptr() for k, t in host.items()}
+
+    def load_from_host():  # particle_load through the C ABI: 16 B/marker H2D + the loader arithmetic on the device
+        g.load_markers(0, (ptr["u_v"], n), (ptr["u_x"], n), n * world, v_max=8.0)
     nx = args.nx
     hf = {k: torch.empty(m, dtype=torch.float64, pin_memory=True) for k, m in (("E", nx), ("rho", nx), ("re", 1), ("im", 1))}
 
@@ -279,7 +292,7 @@ def main():
 
     # ---- peer-memory all-reduce sanity: one step, then every rank must report no timeout and a finite field ----
     if world > 1 and args.allreduce != "nccl":
-        g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])
+        load_from_host()
         g.collect_charge()
         g.solve_field()
         g.step(1)
@@ -299,7 +312,8 @@ def main():
     # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local)
     sampler.start()   # started well before the timed region: nvidia-smi needs a few hundred ms to deliver samples
-    g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])
+    load_from_host()
+    g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], p=ptr["p"], w=ptr["w"])   # host copies for the host-refresh variants
     g.collect_charge()
     g.solve_field()
     g.step(args.warmup)
@@ -354,7 +368,10 @@ def main():
             barrier()
             cc0 = g.counters()
             t_0 = time.perf_counter()
-            g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])   # H2D (particle_load -> device)
+            if mode == "device":
+                load_from_host()   # particle_load: uniform streams H2D (16 B/marker), loader arithmetic on the device
+            else:
+                g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])   # host-loaded markers, 32 B/marker
             g.collect_charge()
             g.solve_field()
             for it in range(1, k + 1):
@@ -374,13 +391,15 @@ def main():
                     "d2h_bytes_per_step": (cc.d2h_bytes - cc0.d2h_bytes) / k}
 
         e2e = e2e_run("device", args.steps)
-        e2e["definition"] = ("reference driver loop through the C ABI, host wall clock, max over ranks: set_markers "
-                             "(pinned host -> device, 32 B/marker) + K steps, get_field (E, rho, modes) to the host "
+        e2e["definition"] = ("reference driver loop through the C ABI, host wall clock, max over ranks: particle_load as "
+                             "pic1dp_gpu_load_markers (the two uniform RNG streams from pinned host memory, 16 B/marker "
+                             "H2D, loader arithmetic on the device) + K steps, get_field (E, rho, modes) to the host "
                              f"after every step, output_all every {OUTPUT_EVERY} steps and at the end (reference "
                              "cadence, src/pic1dp.F90:98-108) as pic1dp_gpu_output_field + pic1dp_gpu_output_ptcldist "
                              "(device-side reductions, results to the host)")
         e2e["host_refresh_outputs"] = e2e_run("host", args.steps)
-        e2e["host_refresh_outputs"]["definition"] = "same, but each output step is get_markers(x, v, w) to pinned host memory"
+        e2e["host_refresh_outputs"]["definition"] = ("same with host-loaded markers (set_markers, 32 B/marker H2D) and each "
+                                                     "output step done as get_markers(x, v, w) to pinned host memory")
         # worst case: markers live on the host and make the round trip every step
         k2 = min(args.steps, 3)
         barrier()

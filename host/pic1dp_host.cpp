@@ -289,7 +289,7 @@ struct Rank {
   const pic1dp_input::Input *in = nullptr;
   pic1dp_gpu_t *h = nullptr;
   int64_t particle_ip_low = 0, particle_ip_high = 0, particle_np = 0;
-  std::vector<double> x, v, p, w;  // host copies of particle_x, _v, _p, _w (src/pic1dp_particle.F90:34-36)
+  std::vector<double> x, v;        // host scratch for the two uniform streams of particle_load
   std::vector<double> field_electric, field_chargeden, field_mode_re, field_mode_im;
 };
 
@@ -337,55 +337,28 @@ static void particle_init(Rank &r, const uint8_t *uid) {
   r.field_mode_im.resize(in.input_nmode);
 }
 
-// particle_load (src/pic1dp_particle.F90:145-269), uniform-v markers (input_imarker = 2), then host -> device
+// particle_load (src/pic1dp_particle.F90:145-269), uniform-v markers (input_imarker = 2): the RNG (multirand, a
+// sequential generator) runs on the host exactly as in the reference -- rand_v is drawn first (:180), then rand_x
+// (:222) -- and the loader arithmetic (:181-237, :260-263) runs on the device (pic1dp_gpu_load_markers), so only the
+// two uniform streams cross PCIe.
 static void particle_load(Rank &r) {
   const pic1dp_input::Input &in = *r.in;
-  using pic1dp_global::PETSC_PI;
   multirand::Generator rng;
   if (in.input_multirand_selftest && !rng.selftest(in.input_multirand_al_int))
     fprintf(stderr, "[%d][multirand_selftest] Warning: unexpected head sequence.\n", r.g.global_mype);
   rng.init(in.input_multirand_al_int, in.input_multirand_seed_type, r.g.global_mype, in.input_multirand_warmup);
   const int64_t n = r.particle_ip_high - r.particle_ip_low;
-  r.x.resize(n);
   r.v.resize(n);
-  r.p.resize(n);
-  r.w.resize(n);
-  const double T = in.input_species_temperature, T2 = in.input_species_temperature2, m = in.input_species_mass;
-  const double dens = in.input_species_density, v0 = in.input_species_v0, lx = in.input_lx, vmax = in.input_v_max;
-  const double ninit = (double)in.input_nparticle_max;
+  r.x.resize(n);
   rng.real_array(r.v.data(), n);  // :180
-  for (int64_t i = 0; i < n; i++) r.v[i] = (r.v[i] - 0.5) * 2.0 * vmax;
-  for (int64_t i = 0; i < n; i++) {
-    const double pv = r.v[i];
-    double pp;
-    if (in.input_iptcldist == 1)
-      pp = dens * lx * 2.0 * vmax / ninit * (pv * pv) * exp(-(pv * pv) / 2.0) / sqrt(2.0 * PETSC_PI);
-    else if (in.input_iptcldist == 2)
-      pp = dens * lx * 2.0 * vmax / ninit *
-           (exp(-((pv + v0) * (pv + v0)) / (2.0 * T / m)) + exp(-((pv - v0) * (pv - v0)) / (2.0 * T / m))) /
-           sqrt(8.0 * PETSC_PI * T / m);
-    else if (in.input_iptcldist == 3)
-      pp = 1.0 * lx * 2.0 * vmax / ninit *
-           (dens * exp(-(pv * pv) / (2.0 * T / m)) / sqrt(2.0 * PETSC_PI * T / m) +
-            (1.0 - dens) * exp(-((pv - v0) * (pv - v0)) / (2.0 * T2 / m)) / sqrt(2.0 * PETSC_PI * T2 / m));
-    else
-      pp = dens * lx * 2.0 * vmax / ninit * exp(-((pv - v0) * (pv - v0)) / (2.0 * T / m)) / sqrt(2.0 * PETSC_PI * T / m);
-    r.p[i] = pp;
-  }
   rng.real_array(r.x.data(), n);  // :222
-  for (int64_t i = 0; i < n; i++) r.x[i] = r.x[i] * lx;
-  for (int64_t i = 0; i < n; i++) r.w[i] = 0.0;
-  for (int im = 0; im < in.input_init_nmode; im++)
-    for (int64_t i = 0; i < n; i++) {
-      const double k = 2.0 * PETSC_PI / lx * (double)in.input_init_mode[im];
-      r.w[i] = r.w[i] + in.input_init_mode_cos[im] * cos(k * r.x[i]) + in.input_init_mode_sin[im] * sin(k * r.x[i]);
-    }
-  for (int64_t i = 0; i < n; i++) r.w[i] = r.w[i] * r.p[i] * 1.0;  // input_pertb_shape == 1
-  if (in.input_linear == 0)
-    for (int64_t i = 0; i < n; i++) r.p[i] = r.p[i] + 1.0 * r.w[i];
   r.particle_np = n;  // input_species_nparticle_init == input_nparticle_max: nothing to unload (:240-248)
-  r.g.global_ierr = pic1dp_gpu_set_markers(r.h, 0, n, r.x.data(), r.v.data(), r.p.data(), r.w.data());
+  r.g.global_ierr = pic1dp_gpu_load_markers(r.h, 0, n, in.input_nparticle_max, r.v.data(), r.x.data(), in.input_v_max,
+                                            in.input_init_nmode, in.input_init_mode, in.input_init_mode_cos,
+                                            in.input_init_mode_sin);
   CHKERRQ(r.g, r.h);
+  r.v.clear();
+  r.x.clear();
 }
 
 static void particle_compute_shape_x(Rank &r) {  // :275-350

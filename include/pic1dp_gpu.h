@@ -165,6 +165,19 @@ int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const doubl
                            const double *p, const double *w);
 
 /*
+ * load_markers: the arithmetic of particle_load for uniform-v markers (input_imarker = 2,
+ * src/pic1dp_particle.F90:179-264) on the device.  The host keeps the RNG (multirand is sequential) and passes the
+ * two uniform [0, 1] streams in the order particle_load draws them: rand_v (multirand_real_array(pv), :180) and rand_x
+ * (:222).  On the device: v = (rand_v - 0.5) * 2 * v_max (:181), p = f0(v) * lx * 2 v_max / nparticle_init (:182-218),
+ * x = rand_x * lx (:223), w = sum over init modes of cos/sin (:225-232) * p * pertb_shape (= 1, :235-236), and
+ * p = p + w for nonlinear runs (:260-263).  Halves the host-to-device traffic of set_markers (16 instead of 32 B per
+ * marker).  np = markers of this rank, nparticle_init = input_species_nparticle_init (all ranks together).
+ */
+int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
+                            const double *rand_x, double v_max, int32_t init_nmode, const int32_t *init_mode,
+                            const double *init_mode_cos, const double *init_mode_sin);
+
+/*
  * get_markers: D2H refresh of the host Vecs before pic1dp_output reads them (src/pic1dp_output.F90:128-150,
  * :228-237) or before particle_optimize.  Any of x,v,p,w may be NULL.  *np receives particle_np.
  */

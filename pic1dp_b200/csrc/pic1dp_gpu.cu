@@ -640,6 +640,52 @@ int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const doubl
   return PIC1DP_OK;
 }
 
+int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
+                            const double *rand_x, double v_max, int32_t init_nmode, const int32_t *init_mode,
+                            const double *init_mode_cos, const double *init_mode_sin) {
+  if (!h || isp < 0 || isp >= h->p.nspecies || np < 0 || nparticle_init < 1 || !rand_v || !rand_x || !(v_max > 0.0) ||
+      init_nmode < 0 || init_nmode > 8 || (init_nmode > 0 && (!init_mode || !init_mode_cos || !init_mode_sin))) {
+    if (h) h->err = "load_markers: bad argument (at most 8 initial modes)";
+    return PIC1DP_EINVAL;
+  }
+  if (np > h->p.capacity) { h->err = "load_markers: np exceeds capacity"; return PIC1DP_ECAPACITY; }
+  CK(cudaSetDevice(h->p.device));
+  Species &S = h->sp[isp];
+  S.cur = 0;
+  S.bak = 0;
+  S.np = np;
+  const size_t b = (size_t)np * 8;
+  CK(cudaMemcpyAsync(S.v[0], rand_v, b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(S.x[0], rand_x, b, cudaMemcpyHostToDevice, h->stream));
+  h->h2d += 2 * (int64_t)b;
+  LoadArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = S.x[0];
+  a.v = S.v[0];
+  a.p = S.p;
+  a.w = S.w[0];
+  a.np = np;
+  a.lx = h->p.lx;
+  a.v_max = v_max;
+  a.ninit = (double)nparticle_init;
+  a.c = S.c;
+  a.T2 = h->p.temperature2[isp];
+  a.dist = h->p.iptcldist;
+  a.linear = h->p.linear;
+  a.init_nmode = init_nmode;
+  for (int i = 0; i < init_nmode; i++) {
+    a.init_mode[i] = init_mode[i];
+    a.init_cos[i] = init_mode_cos[i];
+    a.init_sin[i] = init_mode_sin[i];
+  }
+  k_load_markers<<<h->nsm * 8, 256, 0, h->stream>>>(a);
+  CKL(h);
+  CK(cudaStreamSynchronize(h->stream));  // host buffers are only borrowed for the call
+  S.loaded = true;
+  h->partial_valid = false;
+  return PIC1DP_OK;
+}
+
 int pic1dp_gpu_get_markers(pic1dp_gpu_t *h, int32_t isp, double *x, double *v, double *p, double *w, int64_t *np) {
   if (!h || isp < 0 || isp >= h->p.nspecies) return PIC1DP_EINVAL;
   Species &S = h->sp[isp];

@@ -118,6 +118,20 @@ class Pic1dGpu:
         """Raw host addresses (e.g. pinned torch tensors' data_ptr())."""
         self._ck(self.L.pic1dp_gpu_set_markers(self._h, isp, n, _ptr(x), _ptr(v), _ptr(p), _ptr(w)), "set_markers")
 
+    def load_markers(self, isp: int, rand_v, rand_x, nparticle_init: int, v_max: float = 8.0, init_mode=(1,),
+                     init_cos=(0.0,), init_sin=(1e-5,)):
+        """Device-side particle_load from the two uniform streams (arrays or raw host addresses)."""
+        nm = len(init_mode)
+        im = (C.c_int32 * nm)(*init_mode)
+        ic = (C.c_double * nm)(*init_cos)
+        isn = (C.c_double * nm)(*init_sin)
+        if isinstance(rand_v, np.ndarray):
+            n, pv, px = rand_v.size, _dp(rand_v), _dp(rand_x)
+        else:
+            n, pv, px = rand_v[1], _ptr(rand_v[0]), _ptr(rand_x[0])
+        self._ck(self.L.pic1dp_gpu_load_markers(self._h, isp, n, int(nparticle_init), pv, px, float(v_max), nm, im, ic, isn),
+                 "load_markers")
+
     def get_markers(self, isp: int, want=("x", "v", "p", "w")):
         n = C.c_int64()
         self._ck(self.L.pic1dp_gpu_get_markers(self._h, isp, None, None, None, None, C.byref(n)), "get_markers")

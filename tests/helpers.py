@@ -16,7 +16,8 @@ def make_params(**over):
     gpu_only = {k: over.pop(k) for k in list(over) if k in ("capacity", "device", "deposit_mode", "field_mode",
                                                             "fuse", "rank", "nranks", "load_path")}
     op = O.default_params(**over)
-    gp = P.default_params(**over, **gpu_only)
+    loader_only = ("init_nmode", "init_mode", "init_mode_cos", "init_mode_sin", "v_max", "imarker")
+    gp = P.default_params(**{k: v for k, v in over.items() if k not in loader_only}, **gpu_only)
     return op, gp
 
 

@@ -461,3 +461,28 @@ def test_max_species_and_modes_limits():
             out = g.get_markers(s)
             for k in ("x", "v", "w"):
                 assert rel_err(out[k], ref.st[s][0][k]) < 1e-12, (s, k)
+
+
+@pytest.mark.parametrize("dist", [0, 1, 2, 3])
+@pytest.mark.parametrize("linear", [0, 1])
+def test_device_side_particle_load_matches_oracle_loader(dist, linear):
+    """pic1dp_gpu_load_markers given the two multirand streams (SuperKISS64, constant seeds, rank 1) against the oracle's
+    restated particle_load: x, v bit-exact; p, w within a few ulp (device exp / sin / cos vs glibc)."""
+    from oracle import oracle as O
+    n, ntot = 100003, 400012
+    op, gp = make_params(nx=192, iptcldist=dist, linear=linear, capacity=n, temperature=[1.3], temperature2=[0.8],
+                         mass=[1.1], density=[0.85], v0=[2.5], init_nmode=2, init_mode=[1, 3],
+                         init_mode_cos=[2e-6, 0.0], init_mode_sin=[1e-5, 3e-6])
+    o = O.Oracle(op)
+    x, v, p, w = o.particle_load(0, 3, 1, 5, n, ntot)
+    rng = O.MultiRand()
+    rng.init_const(3, 1, 5)
+    rand_v = rng.real_array(n)   # drawn first (src/pic1dp_particle.F90:180), then x (:222)
+    rand_x = rng.real_array(n)
+    with _gpu(gp) as g:
+        g.load_markers(0, rand_v, rand_x, ntot, v_max=8.0, init_mode=(1, 3), init_cos=(2e-6, 0.0), init_sin=(1e-5, 3e-6))
+        out = g.get_markers(0)
+        assert g.counters().h2d_bytes == 16 * n
+    assert np.array_equal(out["x"], x) and np.array_equal(out["v"], v)
+    assert rel_err(out["p"], p) < 1e-14
+    assert rel_err(out["w"], w) < 1e-13
