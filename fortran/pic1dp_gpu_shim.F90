@@ -80,6 +80,16 @@ interface
     integer(c_int64_t), value :: np
     real(c_double), intent(in) :: x(*), v(*), p(*), w(*)
   end function
+  integer(c_int) function pic1dp_gpu_load_markers(handle, isp, np, nparticle_init, rand_v, rand_x, v_max, init_nmode, &
+      init_mode, init_mode_cos, init_mode_sin) bind(c, name = 'pic1dp_gpu_load_markers')
+    import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: isp, init_nmode
+    integer(c_int64_t), value :: np, nparticle_init
+    real(c_double), intent(in) :: rand_v(*), rand_x(*), init_mode_cos(*), init_mode_sin(*)
+    real(c_double), value :: v_max
+    integer(c_int32_t), intent(in) :: init_mode(*)
+  end function
   integer(c_int) function pic1dp_gpu_get_markers(handle, isp, x, v, p, w, np) bind(c, name = 'pic1dp_gpu_get_markers')
     import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
     type(c_ptr), value :: handle
@@ -143,7 +153,7 @@ type(c_ptr), save, public :: gpu_handle = c_null_ptr
 
 public :: pic1dp_gpu_params_default, pic1dp_gpu_create, pic1dp_gpu_destroy
 public :: pic1dp_gpu_comm_unique_id, pic1dp_gpu_comm_init
-public :: pic1dp_gpu_set_markers, pic1dp_gpu_get_markers, pic1dp_gpu_compute_shape_x
+public :: pic1dp_gpu_set_markers, pic1dp_gpu_load_markers, pic1dp_gpu_get_markers, pic1dp_gpu_compute_shape_x
 public :: pic1dp_gpu_collect_charge, pic1dp_gpu_solve_field, pic1dp_gpu_push
 public :: pic1dp_gpu_get_field, pic1dp_gpu_sync
 public :: pic1dp_gpu_p2p_export, pic1dp_gpu_p2p_import, pic1dp_gpu_output_field, pic1dp_gpu_output_ptcldist
@@ -252,6 +262,21 @@ CHKERRQ(global_ierr)
 call VecRestoreArrayF90(vw, pw, global_ierr)
 CHKERRQ(global_ierr)
 end subroutine gpu_particle_upload
+
+! alternative to gpu_particle_upload: particle_load keeps only its two multirand_real_array calls
+! (src/pic1dp_particle.F90:180, :222) and hands the raw uniform streams over; the loader arithmetic (:181-237,
+! :260-263) runs on the device, so 16 instead of 32 bytes per marker cross PCIe
+subroutine gpu_particle_load(ispecies, np, rand_v, rand_x)
+implicit none
+#include "finclude/petsc.h90"
+PetscInt, intent(in) :: ispecies, np
+PetscScalar, dimension(:), intent(in) :: rand_v, rand_x
+global_ierr = pic1dp_gpu_load_markers(gpu_handle, int(ispecies - 1, c_int32_t), int(np, c_int64_t), &
+  int(input_species_nparticle_init(ispecies), c_int64_t), rand_v, rand_x, real(input_v_max, c_double), &
+  int(input_init_nmode, c_int32_t), int(input_init_mode, c_int32_t), real(input_init_mode_cos, c_double), &
+  real(input_init_mode_sin, c_double))
+CHKERRQ(global_ierr)
+end subroutine gpu_particle_load
 
 ! before output_all / particle_optimize (src/pic1dp_output.F90:128-150, :228-237): device -> host Vecs
 subroutine gpu_particle_refresh_host(ispecies, vx, vv, vp, vw)

@@ -486,3 +486,49 @@ def test_device_side_particle_load_matches_oracle_loader(dist, linear):
     assert np.array_equal(out["x"], x) and np.array_equal(out["v"], v)
     assert rel_err(out["p"], p) < 1e-14
     assert rel_err(out["w"], w) < 1e-13
+
+
+def test_randomized_configurations_two_steps():
+    """24 pseudo-random parameter sets (fixed seed): equilibrium, delta-f / full-f, linear, weight rounding, deposit
+    mode, fuse, species constants, grid size, mode set, ragged marker counts -- two full steps against the oracle."""
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        dist = int(rng.integers(0, 4))
+        deltaf = int(rng.integers(0, 2)) if dist in (0, 1) else 1
+        linear = int(rng.integers(0, 2)) if deltaf else 0
+        nx = int(rng.choice([2, 7, 64, 192, 333, 1024, 2048]))
+        nmode = int(rng.integers(1, 4)) if nx >= 16 else 1
+        modes = sorted(rng.choice(np.arange(1, max(2, min(9, nx // 2 + 1))), size=nmode, replace=False).tolist())
+        dep = int(rng.choice([P.DEPOSIT_AUTO, P.DEPOSIT_SMEM_ATOMIC, P.DEPOSIT_GLOBAL_RED, P.DEPOSIT_WARP_PRIVATE]))
+        n = int(rng.choice([1, 33, 1000, 4097, 20001]))
+        kw = dict(nx=nx, nmode=nmode, modes=modes, iptcldist=dist, deltaf=deltaf, linear=linear,
+                  iptclshape=int(rng.choice([1, 2, 3, 4])), deposit_mode=dep, fuse=int(rng.integers(0, 2)),
+                  temperature=[float(rng.choice([1.0, 2.0, 1.3]))], temperature2=[float(rng.choice([1.0, 0.5, 0.7]))],
+                  mass=[float(rng.choice([1.0, 0.5, 1.7]))], density=[float(rng.choice([0.9, 1.0, 0.6]))],
+                  v0=[float(rng.choice([5.0, 0.0, 2.0]))], charge=[float(rng.choice([-1.0, 1.0, 2.0]))],
+                  dt=float(rng.choice([0.05, 0.1])), capacity=max(n, 1))
+        op, gp = make_params(**kw)
+        st = synth_markers(op, n, seed=1000 + trial, spread=float(rng.choice([0.0, 0.4])))
+        if dist == 1:
+            st["v"][np.abs(st["v"]) < 1e-2] = 0.7
+        ref = OracleRun(op, [[copy_state(st)]])
+        ref.init_field()
+        ref.step()
+        ref.step()
+        with _gpu(gp) as g:
+            g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+            if gp.iptclshape < 4:
+                g.compute_shape_x()
+            g.collect_charge()
+            g.solve_field()
+            g.step(2)
+            f = g.get_field()
+            out = g.get_markers(0)
+            noob = g.counters().oob_markers
+        tag = (trial, kw)
+        scale = max(np.abs(ref.rho).max(), 1e-300)
+        assert rel_err(f["chargeden"], ref.rho, scale) < 1e-11, tag
+        assert rel_err(f["electric"], ref.E, max(np.abs(ref.E).max(), 1e-300)) < 1e-10, tag
+        for k in ("x", "v", "w", "p"):
+            assert rel_err(out[k], ref.st[0][0][k]) < 1e-11, (k, tag)
+        assert noob == ref.noob, tag
