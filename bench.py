@@ -330,6 +330,8 @@ def main():
     ms = max_over_ranks(ms)
     value = n * world * args.steps / (ms * 1e-3)
     energy = g.field_energy()
+    g.output_field()                     # one-time scratch allocations of the diagnostics happen here, untimed
+    g.output_ptcldist(0, 64, 64, 8.0)
 
     # ---- roofline of the dominant kernel, CUDA events around each launch ----
     prof = np.array([g.profile_step() for _ in range(5)])[1:].mean(axis=0)  # ms: push1, collect1, field1, push2, ...

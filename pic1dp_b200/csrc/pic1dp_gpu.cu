@@ -570,6 +570,10 @@ int pic1dp_gpu_comm_init(pic1dp_gpu_t *h, const uint8_t id[PIC1DP_UNIQUE_ID_BYTE
   memcpy(&u, id, sizeof(u));
   ncclResult_t r = g_nccl.CommInitRank(&h->comm, h->p.nranks, u, h->p.rank);
   if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return PIC1DP_ENCCL; }
+  // NCCL sets up its channels lazily on the first collective (hundreds of ms): do that here, not inside a timestep
+  r = g_nccl.AllReduce(h->d_energy, h->d_energy, 1, ncclDouble, ncclSum, h->comm, h->stream);
+  if (r != ncclSuccess) { h->err = std::string("ncclAllReduce (warm-up): ") + g_nccl.GetErrorString(r); return PIC1DP_ENCCL; }
+  CK(cudaStreamSynchronize(h->stream));
   return PIC1DP_OK;
 }
 
