@@ -532,3 +532,24 @@ def test_randomized_configurations_two_steps():
         for k in ("x", "v", "w", "p"):
             assert rel_err(out[k], ref.st[0][0][k]) < 1e-11, (k, tag)
         assert noob == ref.noob, tag
+
+
+def test_committed_hotpath_fixture():
+    """The GPU against the committed oracle-generated fixture tests/golden/hotpath_tiny.json (no oracle call)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hotpath_tiny.json")))
+    fh = lambda a: np.array([float.fromhex(t) for t in a])
+    _, gp = make_params(nx=g["nx"], capacity=g["n"], field_mode=P.FIELD_SEQUENTIAL)
+    with _gpu(gp) as gpu:
+        gpu.set_markers(0, *(fh(g["init"][k]) for k in ("x", "v", "p", "w")))
+        gpu.collect_charge()
+        gpu.solve_field()
+        f0 = gpu.get_field()
+        gpu.step(g["steps"])
+        f = gpu.get_field()
+        out = gpu.get_markers(0)
+    assert rel_err(f0["chargeden"], fh(g["after"]["rho0"])) < TOL_SUM and rel_err(f0["electric"], fh(g["after"]["E0"])) < TOL_SUM
+    assert rel_err(f["chargeden"], fh(g["after"]["rho"])) < TOL_SUM and rel_err(f["electric"], fh(g["after"]["E"])) < TOL_SUM
+    for k in ("x", "v", "w"):
+        assert rel_err(out[k], fh(g["after"][k])) < 1e-12, k

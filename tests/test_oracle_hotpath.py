@@ -186,3 +186,28 @@ def test_bump_on_tail_grows_at_the_analytic_rate():
     t = op.dt * (np.arange(nsteps) + 1)
     gamma = growthrate_energy_fit(t, res["energy"], 20.0, 50.0) / 2.0
     assert abs(gamma - 0.0838311) < 0.004, gamma
+
+
+def _golden():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hotpath_tiny.json")))
+
+
+def test_oracle_reproduces_committed_hotpath_fixture():
+    """tests/golden/hotpath_tiny.json (oracle-generated, see tests/golden/make_golden.py): 96 loader markers, nx = 16,
+    2 emulated ranks, 3 timesteps -- bit for bit."""
+    g = _golden()
+    fh = lambda a: np.array([float.fromhex(t) for t in a])
+    op, _ = make_params(nx=g["nx"])
+    ini = {k: fh(g["init"][k]) for k in ("x", "v", "p", "w")}
+    parts = [{k: a[:48].copy() for k, a in ini.items()}, {k: a[48:].copy() for k, a in ini.items()}]
+    run = OracleRun(op, [parts])
+    run.init_field()
+    assert np.array_equal(run.rho, fh(g["after"]["rho0"])) and np.array_equal(run.E, fh(g["after"]["E0"]))
+    for _ in range(g["steps"]):
+        run.step()
+    for k in ("rho", "E", "mode_re", "mode_im"):
+        assert np.array_equal(getattr(run, k), fh(g["after"][k])), k
+    for k in ("x", "v", "w"):
+        assert np.array_equal(np.concatenate([q[k] for q in run.st[0]]), fh(g["after"][k])), k
