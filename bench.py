@@ -79,78 +79,62 @@ def fill_uniforms(u_v, u_x, seed, chunk=1 << 24):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons during the timed region, sampled every 10 ms through NVML (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; a piped nvidia-smi block-buffers its output,
+    which loses samples of a ~100 ms region)."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
         self.index = index
         self.rows = []
-        self.proc = None
+        self.stop_flag = False
+        self.thread = None
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.index])
+                except Exception:
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.time(), sm, smax, rs))
+                time.sleep(0.01)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def start(self):
-        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
-        time.sleep(0.05)
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        import datetime
-        parsed = []
-        for ts, line in self.rows:
-            f = [t.strip() for t in line.split(",")]
-            try:
-                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-            except Exception:
-                pass
-            parsed.append((ts, line))
-        inside = [r for r in parsed if t0 - 0.02 <= r[0] <= t1 + 0.05]
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: %s" % self.err], "samples": 0}
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
         note = None
-        if not inside and parsed:  # sampling period stretched beyond the timed region: use the closest samples
+        if not inside:
             mid = 0.5 * (t0 + t1)
-            inside = sorted(parsed, key=lambda r: abs(r[0] - mid))[:3]
-            note = "no sample fell inside the %.0f ms timed region; nearest samples used (%.2f s away)" % (
-                1e3 * (t1 - t0), min(abs(r[0] - mid) for r in inside))
-            t0, t1 = min(r[0] for r in inside), max(r[0] for r in inside)
-        self.rows = inside
-        for ts, line in self.rows:
-            f = [t.strip() for t in line.split(",")]
-            try:  # nvidia-smi's own timestamp (its stdout is block-buffered when piped, so arrival time is late)
-                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-            except Exception:
-                pass
-            f = f[1:]
-            if ts < t0 - 0.02 or ts > t1 + 0.05:
-                continue
-            try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
-            except Exception:
-                continue
-            for name, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-               "samples": len(sm)}
+            inside = sorted(self.rows, key=lambda r: abs(r[0] - mid))[:3]
+            note = "no sample inside the %.0f ms timed region; nearest samples used" % (1e3 * (t1 - t0))
+        reasons = sorted(k for k, bit in self.REASONS.items() if any(r[3] & bit for r in inside))
+        out = {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(inside[0][2]),
+               "reasons": reasons, "samples": len(inside)}
         if note:
             out["note"] = note
         return out
