@@ -80,6 +80,8 @@ struct Input {
   // placement / implementation (not in the reference)
   int ngpus = 1, deposit_mode = 0, field_mode = 0, fuse = 1;
   std::string out = "pic1dp_energy.txt";
+  std::string petsc_out;          // when set: also write the reference's binary output file (pic1dp.out layout)
+  int input_nv = 128, input_nx_opd = 64, input_nv_opd = 64;  // src/pic1dp_input.F90:131, :253-256
 };
 
 static bool parse(Input &in, int argc, char **argv) {
@@ -117,6 +119,7 @@ static bool parse(Input &in, int argc, char **argv) {
     else if (k == "field_mode") in.field_mode = (int)d;
     else if (k == "fuse") in.fuse = (int)d;
     else if (k == "out") in.out = v;
+    else if (k == "petsc_out") in.petsc_out = v;
     else return false;
   }
   return true;
@@ -390,6 +393,61 @@ static void interaction_push_particle(Rank &r) {  // :161-370, implicit input gl
 }  // namespace pic1dp_interaction
 
 namespace pic1dp_output {
+// big-endian writers of the PETSc binary viewer (PetscViewerBinaryWriteInt / WriteReal / VecView)
+static void put_i32(FILE *f, int32_t v) {
+  unsigned char b[4] = {(unsigned char)(v >> 24), (unsigned char)(v >> 16), (unsigned char)(v >> 8), (unsigned char)v};
+  fwrite(b, 1, 4, f);
+}
+static void put_f64(FILE *f, double d) {
+  uint64_t u;
+  memcpy(&u, &d, 8);
+  unsigned char b[8];
+  for (int i = 0; i < 8; i++) b[i] = (unsigned char)(u >> (56 - 8 * i));
+  fwrite(b, 1, 8, f);
+}
+static void put_vec(FILE *f, const std::vector<double> &v) {  // VecView: VEC_FILE_CLASSID, n, values
+  put_i32(f, 1211214);
+  put_i32(f, (int32_t)v.size());
+  for (double d : v) put_f64(f, d);
+}
+// output_init header (src/pic1dp_output.F90:74-92)
+static void output_init(const pic1dp_input::Input &in, FILE *f) {
+  put_i32(f, in.input_nspecies);
+  put_i32(f, in.input_nmode);
+  put_i32(f, in.input_nx);
+  put_i32(f, in.input_nv);
+  put_i32(f, in.input_nx_opd);
+  put_i32(f, in.input_nv_opd);
+  for (int m = 0; m < in.input_nmode; m++) put_i32(f, in.input_modes[m]);
+  put_f64(f, in.input_lx);
+  put_f64(f, in.input_v_max);
+}
+// output_all = output_field + output_ptcldist (src/pic1dp_output.F90:100-189, :196-477) from device-side reductions
+static void output_all(Rank &r, FILE *f) {
+  const pic1dp_input::Input &in = *r.in;
+  double sc[1 + 3 * PIC1DP_MAX_SPECIES];
+  r.g.global_ierr = pic1dp_gpu_output_field(r.h, sc);
+  CHKERRQ(r.g, r.h);
+  r.g.global_ierr = pic1dp_gpu_get_field(r.h, r.field_electric.data(), r.field_chargeden.data(), r.field_mode_re.data(),
+                                         r.field_mode_im.data());
+  CHKERRQ(r.g, r.h);
+  const int nc = in.input_nx_opd * in.input_nv_opd;
+  std::vector<double> mxv(nc), txv(nc), pxv(nc), mv(in.input_nv_opd), tv(in.input_nv_opd), pv(in.input_nv_opd);
+  r.g.global_ierr = pic1dp_gpu_output_ptcldist(r.h, 0, in.input_nx_opd, in.input_nv_opd, in.input_v_max, mxv.data(),
+                                               txv.data(), pxv.data(), mv.data(), tv.data(), pv.data());
+  CHKERRQ(r.g, r.h);
+  if (!f || r.g.global_mype != 0) return;  // only the root process writes (:457-474)
+  put_f64(f, r.g.global_time);
+  for (int i = 0; i < 1 + 3 * in.input_nspecies; i++) put_f64(f, sc[i]);
+  put_vec(f, r.field_mode_re);
+  put_vec(f, r.field_mode_im);
+  put_vec(f, r.field_electric);
+  put_vec(f, r.field_chargeden);
+  for (auto *a : {&mxv, &txv, &pxv, &mv, &tv, &pv})
+    for (double d : *a) put_f64(f, d);
+  fflush(f);
+}
+
 // scalar part of output_field (src/pic1dp_output.F90:117-124, :178-181): t, int E^2 dx, mode_re, mode_im
 static void output_field(Rank &r, FILE *f) {
   double energy = 0.0;
@@ -417,6 +475,9 @@ static void run_rank(const pic1dp_input::Input *in, int mype, int npe, const uin
   r.g.global_mype = mype;
   r.g.global_npe = npe;
   FILE *f = (mype == 0) ? fopen(in->out.c_str(), "w") : nullptr;
+  FILE *fb = (mype == 0 && !in->petsc_out.empty()) ? fopen(in->petsc_out.c_str(), "wb") : nullptr;
+  const bool binary = !in->petsc_out.empty();
+  if (fb) pic1dp_output::output_init(*in, fb);
   pic1dp_input::input_init(*in);
   pic1dp_particle::particle_init(r, uid);  // + field_init
   pic1dp_particle::particle_load(r);
@@ -426,6 +487,7 @@ static void run_rank(const pic1dp_input::Input *in, int mype, int npe, const uin
   pic1dp_interaction::interaction_collect_charge(r);  // :71
   pic1dp_field::field_solve_electric(r);              // :72
   pic1dp_output::output_field(r, f);                  // :74
+  if (binary) pic1dp_output::output_all(r, fb);
   pic1dp_gpu_timer_start(r.h);
   int itermination = check_termination(r);
   while (itermination == 0) {  // :78-109
@@ -442,8 +504,10 @@ static void run_rank(const pic1dp_input::Input *in, int mype, int npe, const uin
     const double eps = pic1dp_global::PETSC_SQRT_MACHINE_EPSILON;
     if (fmod(r.g.global_time + eps, in->input_output_interval) <
             fmod(r.g.global_time + eps - in->input_dt, in->input_output_interval) ||
-        itermination == 1)
+        itermination == 1) {
       pic1dp_output::output_field(r, f);  // :98-108
+      if (binary) pic1dp_output::output_all(r, fb);
+    }
   }
   float ms = 0.f;
   pic1dp_gpu_timer_stop(r.h, &ms);
@@ -456,6 +520,7 @@ static void run_rank(const pic1dp_input::Input *in, int mype, int npe, const uin
            (long long)c.oob_markers, c.deposit_mode, (double)r.particle_np * r.g.global_itime / (ms * 1e-3));
   pic1dp_particle::particle_final(r);
   if (f) fclose(f);
+  if (fb) fclose(fb);
 }
 
 int main(int argc, char **argv) {

@@ -145,3 +145,24 @@ def test_landau_damping_from_a_ptcldist_file(tmp_path):
     period = np.mean(np.diff(t[pk]))                                   # energy oscillates at 2 omega_r
     assert abs(gamma / -0.1533 - 1.0) < 0.08, gamma
     assert abs((np.pi / period) / 1.4156 - 1.0) < 0.05, period
+
+
+def test_cpp_host_driver_writes_reference_output_file(tmp_path):
+    """host/pic1dp_host petsc_out=...: the compiled host writes the reference's `pic1dp.out` (PETSc binary layout) from
+    device-side reductions; the py3 restatement of tools/OutputData.py reads it and the scalars agree with the text trace."""
+    from pic1dp_b200 import build
+    from tools_py3.output_data import OutputData
+    exe = build.build_host()
+    out, pout = tmp_path / "energy.txt", tmp_path / "pic1dp.out"
+    r = subprocess.run([exe, "nparticle_max=300000", "nx=192", "time_max=3", "seed_type=1", f"out={out}", f"petsc_out={pout}"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(out)
+    od = OutputData(str(pout))
+    assert (od.nspecies, od.nmode, od.nx, od.nv, od.nx_pd, od.nv_pd) == (1, 1, 192, 128, 64, 64) and od.ntime == 7
+    sc = od.get_scalar_t()
+    assert np.allclose(sc[0], rows[:, 0]) and np.array_equal(sc[1], rows[:, 1])
+    assert np.array_equal(od.get_mode_t()[1], rows[:, 3])
+    f = od.get_ptcldist_xv(6, 0, 1)
+    assert abs(np.sum(f) * (od.lx / 64) * (16.0 / 63) / od.lx - 1.0) < 0.03   # int f dx dv / lx = n0 = 1
+    assert sc[2, 0] > 0 and abs(sc[3, 0] / (od.lx * 3.4) - 1.0) < 0.1          # sum v^2 p ~ lx * <v^2> = lx * (0.9 + 0.1*26)
