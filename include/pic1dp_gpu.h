@@ -262,6 +262,52 @@ int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int
                                double *markr_xv, double *total_xv, double *pertb_xv, double *markr_v,
                                double *total_v, double *pertb_v);
 
+/*
+ * ---- marker optimisation: particle_optimize's workers (src/pic1dp_particle.F90:356-746) ----
+ * particle_optimize itself (:752-813) is schedule logic (input_tmerge / _tremove / _tsplit against global_time, only at
+ * global_irk == 2, delta-f only) and stays in the host; it is called between push and collect_charge
+ * (src/pic1dp.F90:82), so a host that optimises must drive that substep with the individual entry points
+ * (push, [optimise], collect_charge, solve_field) instead of step().
+ *
+ * compute_dist_pertb_abs_v: replaces particle_compute_dist_pertb_abs_v (:356-403): per species
+ * dist[iv] = sum over markers with |v| < v_max of |w| x linear weight on the nv-point v grid, reduced on the device and
+ * over ranks (MPI_Allreduce, :392-395).  dist (may be NULL) receives particle_dist_pertb_abs_v as [nspecies][nv]; the
+ * handle keeps a copy for the three routines below.  nv = input_nv, v_max = input_v_max.
+ */
+int pic1dp_gpu_compute_dist_pertb_abs_v(pic1dp_gpu_t *h, int32_t nv, double v_max, double *dist);
+
+/* RNG call-backs: the host owns the generator (multirand is sequential and rank-seeded, src/multirand.F90).
+ * real64 = multirand_real64() (:644-650); gaussian_array fills a[0..n) like multirand_gaussian_array (:838-872). */
+typedef double (*pic1dp_real64_fn)(void *rng_ctx);
+typedef void (*pic1dp_gaussian_array_fn)(void *rng_ctx, double *a, int32_t n);
+
+/*
+ * particle_merge / particle_remove / particle_split (src/pic1dp_particle.F90:411-522, :530-627, :635-746) for every
+ * species of this rank, thsh = thsh_frac_dist_pertb_abs_v.  The three algorithms are sequential by definition (a freed
+ * slot is refilled by the LAST marker and examined again; pairs form in visiting order; one RNG stream is consumed in
+ * visiting order), so each call stages x, v, p, w in pinned host memory, runs the reference's visiting order there and
+ * copies the survivors back (32 B/marker each way, a few events per run).  They use the dist of the last
+ * compute_dist_pertb_abs_v call (PIC1DP_ESTATE without one).  np_out (may be NULL) receives particle_np per species.
+ * remove: typeremove = input_typeremove (1 or 2), remove_frac = input_remove_frac.
+ * split: ngroup = input_split_ngroup, dv_sig_frac = input_split_dv_sig_frac; capacity given at create bounds growth.
+ */
+int pic1dp_gpu_particle_merge(pic1dp_gpu_t *h, double thsh, int64_t *np_out);
+int pic1dp_gpu_particle_remove(pic1dp_gpu_t *h, double thsh, int32_t typeremove, double remove_frac,
+                               pic1dp_real64_fn dice, void *rng_ctx, int64_t *np_out);
+int pic1dp_gpu_particle_split(pic1dp_gpu_t *h, double thsh, int32_t ngroup, double dv_sig_frac,
+                              pic1dp_gaussian_array_fn gauss, void *rng_ctx, int64_t *np_out);
+
+/* The same host halves on caller-owned arrays (no handle, no GPU): for a host that already holds fresh marker arrays,
+ * and for testing the visiting order without a device.  Return the new particle_np.  split: arrays hold `capacity`. */
+int64_t pic1dp_host_particle_merge(int64_t np, double *x, double *v, double *p, double *w, const double *dist,
+                                   int32_t nv, double v_max, double thsh, int32_t nx, double lx);
+int64_t pic1dp_host_particle_remove(int64_t np, double *x, double *v, double *p, double *w, const double *dist,
+                                    int32_t nv, double v_max, double thsh, int32_t typeremove, double remove_frac,
+                                    pic1dp_real64_fn dice, void *rng_ctx);
+int64_t pic1dp_host_particle_split(int64_t np, int64_t capacity, double *x, double *v, double *p, double *w,
+                                   const double *dist, int32_t nv, double v_max, double thsh, int32_t ngroup,
+                                   double dv_sig_frac, int32_t deltaf, pic1dp_gaussian_array_fn gauss, void *rng_ctx);
+
 /* block until all queued work of this handle is done; surfaces asynchronous CUDA errors */
 int pic1dp_gpu_sync(pic1dp_gpu_t *h);
 

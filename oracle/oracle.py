@@ -54,7 +54,7 @@ class OrcRankState(C.Structure):
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc -O3 -ffp-contract=off)."""
     import hashlib
-    srcs = [os.path.join(_HERE, f) for f in ("pic1dp_oracle.c", "multirand_oracle.c", "pic1dp_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("pic1dp_oracle.c", "multirand_oracle.c", "optimize_oracle.c", "pic1dp_oracle.h", "Makefile")]
     hh = hashlib.sha256(b"".join(open(s, "rb").read() for s in srcs)).hexdigest()  # mtimes do not survive gpurun
     hpath = _LIB_PATH + ".hash"
     stale = (not os.path.exists(_LIB_PATH)) or (not os.path.exists(hpath)) or open(hpath).read().strip() != hh
@@ -105,6 +105,15 @@ def lib() -> C.CDLL:
         L.orc_multirand_real64.restype = C.c_double
         L.orc_multirand_real_array.argtypes = [C.c_void_p, dp, C.c_int64]
         L.orc_multirand_gaussian_array.argtypes = [C.c_void_p, dp, C.c_int64]
+        L.orc_dist_pertb_abs_v.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(dp), C.POINTER(dp), C.c_int, C.c_double, dp]
+        L.orc_particle_merge.argtypes = [pp, C.c_int64, dp, dp, dp, dp, dp, C.c_int, C.c_double, C.c_double]
+        L.orc_particle_merge.restype = C.c_int64
+        L.orc_particle_remove.argtypes = [C.c_int64, dp, dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int,
+                                          C.c_double, C.c_void_p]
+        L.orc_particle_remove.restype = C.c_int64
+        L.orc_particle_split.argtypes = [pp, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, C.c_int, C.c_double, C.c_double,
+                                         C.c_int, C.c_double, C.c_void_p]
+        L.orc_particle_split.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -213,6 +222,31 @@ class Oracle:
         self.L.orc_particle_load(C.byref(self.p), isp, al_int, mype, warmup, nlocal, ninit_total, _dp(x), _dp(v),
                                  _dp(pp), _dp(w))
         return x, v, pp, w
+
+    # ---- marker optimisation (src/pic1dp_particle.F90:356-746); arrays are updated in place, new np returned ----
+    def dist_pertb_abs_v(self, vs, ws, nv=128, v_max=8.0):
+        """vs, ws: per-rank arrays of one species.  Returns particle_dist_pertb_abs_v(ispecies, :)."""
+        R = len(vs)
+        dpt = C.POINTER(C.c_double)
+        npa = (C.c_int64 * R)(*[a.size for a in vs])
+        dist = np.zeros(nv)
+        self.L.orc_dist_pertb_abs_v(R, npa, (dpt * R)(*[_dp(a) for a in vs]), (dpt * R)(*[_dp(a) for a in ws]), nv,
+                                    float(v_max), _dp(dist))
+        return dist
+
+    def particle_merge(self, st, n, dist, thsh, v_max=8.0):
+        return self.L.orc_particle_merge(C.byref(self.p), n, _dp(st["x"]), _dp(st["v"]), _dp(st["p"]), _dp(st["w"]),
+                                         _dp(dist), dist.size, float(v_max), float(thsh))
+
+    def particle_remove(self, st, n, dist, thsh, typeremove, remove_frac, rng, v_max=8.0):
+        return self.L.orc_particle_remove(n, _dp(st["x"]), _dp(st["v"]), _dp(st["p"]), _dp(st["w"]), _dp(dist),
+                                          dist.size, float(v_max), float(thsh), typeremove, float(remove_frac), rng.g)
+
+    def particle_split(self, st, n, dist, thsh, ngroup, dv_sig_frac, rng, v_max=8.0):
+        """st arrays are sized to the capacity (particle_ip_high - particle_ip_low)."""
+        return self.L.orc_particle_split(C.byref(self.p), n, st["x"].size, _dp(st["x"]), _dp(st["v"]), _dp(st["p"]),
+                                         _dp(st["w"]), _dp(dist), dist.size, float(v_max), float(thsh), ngroup,
+                                         float(dv_sig_frac), rng.g)
 
     def run(self, states, nsteps, E0, nthreads=0):
         """states: list[species][rank] of dict(x,v,p,w) (updated in place).  Returns dict with rho,E,modes,

@@ -140,6 +140,19 @@ double orc_multirand_real64(orc_multirand *g);            /* INT2REAL64, :49 */
 void orc_multirand_real_array(orc_multirand *g, double *a, int64_t n);      /* :664-690 */
 void orc_multirand_gaussian_array(orc_multirand *g, double *a, int64_t n);  /* :838-872 */
 
+/* ---- marker optimisation (optimize_oracle.c): src/pic1dp_particle.F90:356-746 ----
+ * dist = particle_dist_pertb_abs_v(ispecies, 0:nv-1) of one species; merge / remove / split act on the marker
+ * arrays of one species on one rank (1-based visiting order of the reference) and return the new particle_np. */
+void orc_dist_pertb_abs_v_rank(int64_t np, const double *v, const double *w, int nv, double v_max, double *dist);
+void orc_dist_pertb_abs_v(int nranks, const int64_t *np, double **v, double **w, int nv, double v_max, double *dist);
+int64_t orc_particle_merge(const orc_params *p, int64_t np, double *x, double *v, double *pp, double *w,
+                           const double *dist, int nv, double v_max, double thsh);
+int64_t orc_particle_remove(int64_t np, double *x, double *v, double *pp, double *w, const double *dist, int nv,
+                            double v_max, double thsh, int typeremove, double remove_frac, orc_multirand *rng);
+int64_t orc_particle_split(const orc_params *p, int64_t np, int64_t capacity, double *x, double *v, double *pp,
+                           double *w, const double *dist, int nv, double v_max, double thsh, int ngroup,
+                           double dv_sig_frac, orc_multirand *rng);
+
 #ifdef __cplusplus
 }
 #endif

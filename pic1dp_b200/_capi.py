@@ -82,7 +82,14 @@ EXPORTS = [
     "pic1dp_gpu_output_field", "pic1dp_gpu_output_ptcldist",
     "pic1dp_gpu_sync", "pic1dp_gpu_timer_start", "pic1dp_gpu_timer_stop", "pic1dp_gpu_get_counters",
     "pic1dp_gpu_profile_step",
+    "pic1dp_gpu_compute_dist_pertb_abs_v", "pic1dp_gpu_particle_merge", "pic1dp_gpu_particle_remove",
+    "pic1dp_gpu_particle_split",
+    "pic1dp_host_particle_merge", "pic1dp_host_particle_remove", "pic1dp_host_particle_split",
 ]
+
+# RNG call-backs of particle_remove / particle_split (pic1dp_real64_fn, pic1dp_gaussian_array_fn)
+REAL64_FN = C.CFUNCTYPE(C.c_double, C.c_void_p)
+GAUSSIAN_ARRAY_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_int32)
 
 _lib = None
 
@@ -136,6 +143,18 @@ def load() -> C.CDLL:
     L.pic1dp_gpu_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.pic1dp_gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.pic1dp_gpu_profile_step.argtypes = [vp, C.POINTER(C.c_float)]
+    i64p, dbl = C.POINTER(i64), C.c_double
+    L.pic1dp_gpu_compute_dist_pertb_abs_v.argtypes = [vp, i32, dbl, dp]
+    L.pic1dp_gpu_particle_merge.argtypes = [vp, dbl, i64p]
+    L.pic1dp_gpu_particle_remove.argtypes = [vp, dbl, i32, dbl, REAL64_FN, vp, i64p]
+    L.pic1dp_gpu_particle_split.argtypes = [vp, dbl, i32, dbl, GAUSSIAN_ARRAY_FN, vp, i64p]
+    L.pic1dp_host_particle_merge.argtypes = [i64, dp, dp, dp, dp, dp, i32, dbl, dbl, i32, dbl]
+    L.pic1dp_host_particle_merge.restype = i64
+    L.pic1dp_host_particle_remove.argtypes = [i64, dp, dp, dp, dp, dp, i32, dbl, dbl, i32, dbl, REAL64_FN, vp]
+    L.pic1dp_host_particle_remove.restype = i64
+    L.pic1dp_host_particle_split.argtypes = [i64, i64, dp, dp, dp, dp, dp, i32, dbl, dbl, i32, dbl, i32,
+                                             GAUSSIAN_ARRAY_FN, vp]
+    L.pic1dp_host_particle_split.restype = i64
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("pic1dp_gpu_abi_version",):

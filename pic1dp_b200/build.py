@@ -11,11 +11,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpic1dp_b200.so")
 SOURCES = ["pic1dp_gpu.cu"]
-HEADERS = ["particle_kernels.cuh", "field_kernels.cuh", "diag_kernels.cuh"]
+HEADERS = ["particle_kernels.cuh", "field_kernels.cuh", "diag_kernels.cuh", "optimize_kernels.cuh", "optimize_host.hpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-ffp-contract=off",   # host-side arithmetic (marker optimisation) must not be contracted to FMA
 ]
 
 

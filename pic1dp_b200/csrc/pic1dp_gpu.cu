@@ -22,6 +22,8 @@
 
 #include "diag_kernels.cuh"
 #include "field_kernels.cuh"
+#include "optimize_host.hpp"
+#include "optimize_kernels.cuh"
 #include "particle_kernels.cuh"
 
 using namespace pic1dp;
@@ -103,6 +105,14 @@ struct pic1dp_gpu {
   // diagnostics scratch (allocated on first use)
   double *d_diag_part = nullptr, *d_diag_sums = nullptr, *d_hist = nullptr, *d_hist_out = nullptr;
   int diag_grid = 0, hist_cells = 0, hist_copies = 16, hist_smem_set = -1, hist_per_sm = 1;
+  // marker optimisation (allocated on first use): device scratch of compute_dist_pertb_abs_v, its host copy
+  // particle_dist_pertb_abs_v(ispecies, 0:nv-1), and the pinned staging arrays of merge / remove / split
+  double *d_dist_part = nullptr;
+  int dist_grid = 0, dist_threads = 0, dist_smem_set = -1, dist_cap = 0;
+  std::vector<double> h_dist;
+  int opt_nv = 0;
+  double opt_vmax = 0.0;
+  double *stage[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t max_smem = 0;
   int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0, cfg = -1;
   bool use_tma[2] = {false, false};  // per substep (irk = 1, 2)
@@ -347,9 +357,11 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
     if (S.p) cudaFree(S.p);
   }
   double *bufs[] = {h->d_E, h->d_rho, h->d_mre, h->d_mim, h->d_Fre, h->d_Fim, h->d_ginv, h->d_partial, h->d_red, h->d_energy,
-                    h->d_diag_part, h->d_diag_sums, h->d_hist, h->d_hist_out};
+                    h->d_diag_part, h->d_diag_sums, h->d_hist, h->d_hist_out, h->d_dist_part};
   for (double *b : bufs)
     if (b) cudaFree(b);
+  for (double *b : h->stage)
+    if (b) cudaFreeHost(b);
   if (h->d_noob) cudaFree(h->d_noob);
   for (int r = 0; r < 8; r++)
     if (h->peer_base[r] && h->peer_base[r] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
@@ -629,13 +641,9 @@ int pic1dp_gpu_p2p_import(pic1dp_gpu_t *h, const uint8_t *all_handles) {
   return PIC1DP_OK;
 }
 
-int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const double *x, const double *v,
-                           const double *p, const double *w) {
-  if (!h || isp < 0 || isp >= h->p.nspecies || np < 0 || !x || !v || !p || !w) {
-    if (h) h->err = "set_markers: bad argument";
-    return PIC1DP_EINVAL;
-  }
-  if (np > h->p.capacity) { h->err = "set_markers: np exceeds capacity"; return PIC1DP_ECAPACITY; }
+// H2D of one species into buffer set 0; the marker count becomes np
+static int upload_species(pic1dp_gpu_t *h, int isp, int64_t np, const double *x, const double *v, const double *p,
+                          const double *w) {
   CK(cudaSetDevice(h->p.device));
   Species &S = h->sp[isp];
   S.cur = 0;
@@ -651,6 +659,16 @@ int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const doubl
   S.loaded = true;
   h->partial_valid = false;
   return PIC1DP_OK;
+}
+
+int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const double *x, const double *v,
+                           const double *p, const double *w) {
+  if (!h || isp < 0 || isp >= h->p.nspecies || np < 0 || !x || !v || !p || !w) {
+    if (h) h->err = "set_markers: bad argument";
+    return PIC1DP_EINVAL;
+  }
+  if (np > h->p.capacity) { h->err = "set_markers: np exceeds capacity"; return PIC1DP_ECAPACITY; }
+  return upload_species(h, isp, np, x, v, p, w);
 }
 
 int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
@@ -1221,6 +1239,147 @@ int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int
   if (total_v) memcpy(total_v, t_v.data(), (size_t)nv_opd * 8);
   if (pertb_v) memcpy(pertb_v, p_v.data(), (size_t)nv_opd * 8);
   return PIC1DP_OK;
+}
+
+// ---- marker optimisation (src/pic1dp_particle.F90:356-813) ----
+
+int pic1dp_gpu_compute_dist_pertb_abs_v(pic1dp_gpu_t *h, int32_t nv, double v_max, double *dist) {
+  if (!h || nv < 2 || nv > (1 << 20) || !(v_max > 0.0)) {
+    if (h) h->err = "compute_dist_pertb_abs_v: bad argument";
+    return PIC1DP_EINVAL;
+  }
+  int rc = check_loaded(h, "compute_dist_pertb_abs_v");
+  if (rc) return rc;
+  CK(cudaSetDevice(h->p.device));
+  const pic1dp_params &p = h->p;
+  // one private (nv + 1)-cell grid per warp in shared memory; fewer warps per CTA for large grids
+  int threads = 512;
+  while (threads > 32 && (size_t)(threads / 32) * (nv + 1) * 8 > h->max_smem) threads >>= 1;
+  const size_t smem = (size_t)(threads / 32) * (nv + 1) * 8;
+  if (smem > h->max_smem) { h->err = "compute_dist_pertb_abs_v: nv too large for a shared-memory grid"; return PIC1DP_EUNSUPPORTED; }
+  if (h->dist_smem_set != (int)smem || h->dist_threads != threads) {
+    CK(cudaFuncSetAttribute(k_dist_pertb_abs_v, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dist_pertb_abs_v, threads, smem));
+    h->dist_grid = h->nsm * (per_sm < 1 ? 1 : per_sm);
+    h->dist_threads = threads;
+    h->dist_smem_set = (int)smem;
+  }
+  const int need = h->dist_grid * nv + p.nspecies * nv;
+  if (need > h->dist_cap) {
+    if (h->d_dist_part) cudaFree(h->d_dist_part);
+    h->d_dist_part = nullptr;
+    CK(cudaMalloc(&h->d_dist_part, (size_t)need * 8));
+    h->dist_cap = need;
+  }
+  double *d_out = h->d_dist_part + (size_t)h->dist_grid * nv;  // [nspecies][nv]
+  for (int s = 0; s < p.nspecies; s++) {
+    Species &S = h->sp[s];
+    DistArgs a;
+    a.v = S.v[S.cur];
+    a.w = S.w[S.cur];
+    a.np = S.np;
+    a.nv = nv;
+    a.v_max = v_max;
+    a.partial = h->d_dist_part;
+    k_dist_pertb_abs_v<<<h->dist_grid, threads, smem, h->stream>>>(a);
+    CKL(h);
+    k_dist_final<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->d_dist_part, h->dist_grid, nv, d_out + (size_t)s * nv);
+    CKL(h);
+  }
+  rc = allreduce_inplace(h, d_out, (size_t)p.nspecies * nv);  // MPI_Allreduce :392-395
+  if (rc) return rc;
+  h->h_dist.assign((size_t)p.nspecies * nv, 0.0);
+  CK(cudaMemcpyAsync(h->h_dist.data(), d_out, (size_t)p.nspecies * nv * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->d2h += (int64_t)p.nspecies * nv * 8;
+  h->opt_nv = nv;
+  h->opt_vmax = v_max;
+  if (dist) memcpy(dist, h->h_dist.data(), (size_t)p.nspecies * nv * 8);
+  return PIC1DP_OK;
+}
+
+// D2H of the current x, v, p, w of one species into the pinned staging arrays (allocated on first use)
+static int stage_species(pic1dp_gpu_t *h, int isp, const char *who) {
+  if (h->opt_nv == 0) { h->err = std::string(who) + ": compute_dist_pertb_abs_v must be called first"; return PIC1DP_ESTATE; }
+  CK(cudaSetDevice(h->p.device));
+  for (double *&b : h->stage)
+    if (!b) CK(cudaMallocHost(&b, (size_t)(h->p.capacity > 0 ? h->p.capacity : 1) * 8));
+  return pic1dp_gpu_get_markers(h, isp, h->stage[0], h->stage[1], h->stage[2], h->stage[3], nullptr);
+}
+
+int pic1dp_gpu_particle_merge(pic1dp_gpu_t *h, double thsh, int64_t *np_out) {
+  if (!h) return PIC1DP_EINVAL;
+  int rc = check_loaded(h, "particle_merge");
+  if (rc) return rc;
+  for (int s = 0; s < h->p.nspecies; s++) {
+    if ((rc = stage_species(h, s, "particle_merge"))) return rc;
+    const hostopt::Markers m = {h->stage[0], h->stage[1], h->stage[2], h->stage[3]};
+    const int64_t n = hostopt::merge(m, h->sp[s].np, h->h_dist.data() + (size_t)s * h->opt_nv, h->opt_nv, h->opt_vmax,
+                                     thsh, h->p.nx, h->p.lx);
+    if ((rc = upload_species(h, s, n, m.x, m.v, m.p, m.w))) return rc;
+    if (np_out) np_out[s] = n;
+  }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_particle_remove(pic1dp_gpu_t *h, double thsh, int32_t typeremove, double remove_frac,
+                               pic1dp_real64_fn dice, void *rng_ctx, int64_t *np_out) {
+  if (!h || !dice || (typeremove != 1 && typeremove != 2)) {
+    if (h) h->err = "particle_remove: bad argument";
+    return PIC1DP_EINVAL;
+  }
+  int rc = check_loaded(h, "particle_remove");
+  if (rc) return rc;
+  for (int s = 0; s < h->p.nspecies; s++) {
+    if ((rc = stage_species(h, s, "particle_remove"))) return rc;
+    const hostopt::Markers m = {h->stage[0], h->stage[1], h->stage[2], h->stage[3]};
+    const int64_t n = hostopt::remove(m, h->sp[s].np, h->h_dist.data() + (size_t)s * h->opt_nv, h->opt_nv, h->opt_vmax,
+                                      thsh, typeremove, remove_frac, dice, rng_ctx);
+    if ((rc = upload_species(h, s, n, m.x, m.v, m.p, m.w))) return rc;
+    if (np_out) np_out[s] = n;
+  }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_particle_split(pic1dp_gpu_t *h, double thsh, int32_t ngroup, double dv_sig_frac,
+                              pic1dp_gaussian_array_fn gauss, void *rng_ctx, int64_t *np_out) {
+  if (!h || !gauss || ngroup < 1) {
+    if (h) h->err = "particle_split: bad argument";
+    return PIC1DP_EINVAL;
+  }
+  int rc = check_loaded(h, "particle_split");
+  if (rc) return rc;
+  for (int s = 0; s < h->p.nspecies; s++) {
+    if ((rc = stage_species(h, s, "particle_split"))) return rc;
+    const hostopt::Markers m = {h->stage[0], h->stage[1], h->stage[2], h->stage[3]};
+    const int64_t n = hostopt::split(m, h->sp[s].np, h->p.capacity, h->h_dist.data() + (size_t)s * h->opt_nv, h->opt_nv,
+                                     h->opt_vmax, thsh, ngroup, dv_sig_frac, h->p.deltaf, gauss, rng_ctx);
+    if ((rc = upload_species(h, s, n, m.x, m.v, m.p, m.w))) return rc;
+    if (np_out) np_out[s] = n;
+  }
+  return PIC1DP_OK;
+}
+
+// host halves on caller-owned arrays (no GPU involved)
+int64_t pic1dp_host_particle_merge(int64_t np, double *x, double *v, double *p, double *w, const double *dist,
+                                   int32_t nv, double v_max, double thsh, int32_t nx, double lx) {
+  const hostopt::Markers m = {x, v, p, w};
+  return hostopt::merge(m, np, dist, nv, v_max, thsh, nx, lx);
+}
+
+int64_t pic1dp_host_particle_remove(int64_t np, double *x, double *v, double *p, double *w, const double *dist,
+                                    int32_t nv, double v_max, double thsh, int32_t typeremove, double remove_frac,
+                                    pic1dp_real64_fn dice, void *rng_ctx) {
+  const hostopt::Markers m = {x, v, p, w};
+  return hostopt::remove(m, np, dist, nv, v_max, thsh, typeremove, remove_frac, dice, rng_ctx);
+}
+
+int64_t pic1dp_host_particle_split(int64_t np, int64_t capacity, double *x, double *v, double *p, double *w,
+                                   const double *dist, int32_t nv, double v_max, double thsh, int32_t ngroup,
+                                   double dv_sig_frac, int32_t deltaf, pic1dp_gaussian_array_fn gauss, void *rng_ctx) {
+  const hostopt::Markers m = {x, v, p, w};
+  return hostopt::split(m, np, capacity, dist, nv, v_max, thsh, ngroup, dv_sig_frac, deltaf, gauss, rng_ctx);
 }
 
 int pic1dp_gpu_sync(pic1dp_gpu_t *h) {

@@ -213,6 +213,43 @@ class Pic1dGpu:
                  "output_ptcldist")
         return dict(zip(("markr_xv", "total_xv", "pertb_xv", "markr_v", "total_v", "pertb_v"), outs))
 
+    # ---- marker optimisation (src/pic1dp_particle.F90:356-746) ----
+    def compute_dist_pertb_abs_v(self, nv: int = 128, v_max: float = 8.0) -> np.ndarray:
+        """particle_dist_pertb_abs_v as [nspecies, nv], reduced on the device and over ranks."""
+        out = np.empty((self.params.nspecies, nv))
+        self._ck(self.L.pic1dp_gpu_compute_dist_pertb_abs_v(self._h, nv, float(v_max), _dp(out)),
+                 "compute_dist_pertb_abs_v")
+        return out
+
+    def _np_out(self):
+        return (C.c_int64 * self.params.nspecies)()
+
+    def particle_merge(self, thsh: float):
+        n = self._np_out()
+        self._ck(self.L.pic1dp_gpu_particle_merge(self._h, float(thsh), n), "particle_merge")
+        return list(n)
+
+    def particle_remove(self, thsh: float, typeremove: int, remove_frac: float, real64):
+        """real64: callable returning the next multirand_real64() of this rank's generator."""
+        n = self._np_out()
+        cb = _capi.REAL64_FN(lambda _ctx: float(real64()))
+        self._ck(self.L.pic1dp_gpu_particle_remove(self._h, float(thsh), typeremove, float(remove_frac), cb, None, n),
+                 "particle_remove")
+        return list(n)
+
+    def particle_split(self, thsh: float, ngroup: int, dv_sig_frac: float, gaussian_array):
+        """gaussian_array: callable n -> array of n draws, like multirand_gaussian_array."""
+        n = self._np_out()
+
+        def fill(_ctx, a, k):
+            g = gaussian_array(k)
+            for i in range(k):
+                a[i] = g[i]
+        cb = _capi.GAUSSIAN_ARRAY_FN(fill)
+        self._ck(self.L.pic1dp_gpu_particle_split(self._h, float(thsh), ngroup, float(dv_sig_frac), cb, None, n),
+                 "particle_split")
+        return list(n)
+
     # ---- instrumentation ----
     def sync(self):
         self._ck(self.L.pic1dp_gpu_sync(self._h), "sync")
@@ -291,6 +328,62 @@ class Pic1dpModules:
 
     def particle_compute_shape_x(self):
         self._call(self.gpu.compute_shape_x)
+
+    # marker optimisation: the schedule of particle_optimize (src/pic1dp_particle.F90:752-813) with run-time copies of
+    # input_nmerge/_tmerge/_thshmerge, ... (src/pic1dp_input.F90:146-206); `rng` supplies multirand draws
+    def particle_optimize_setup(self, tmerge=(), thshmerge=(), tremove=(), thshremove=(), typeremove=2, remove_frac=0.9,
+                                tsplit=(), thshsplit=(), split_ngroup=5, split_dv_sig_frac=0.1, nv=128, v_max=8.0,
+                                rng=None):
+        self.input_tmerge, self.input_thshmerge = list(tmerge), list(thshmerge)
+        self.input_tremove, self.input_thshremove = list(tremove), list(thshremove)
+        self.input_tsplit, self.input_thshsplit = list(tsplit), list(thshsplit)
+        self.input_typeremove, self.input_remove_frac = typeremove, remove_frac
+        self.input_split_ngroup, self.input_split_dv_sig_frac = split_ngroup, split_dv_sig_frac
+        self.input_nv, self.input_v_max = nv, v_max
+        self.particle_imerge = 1 if self.input_tmerge else 0    # :73-87
+        self.particle_iremove = 1 if self.input_tremove else 0
+        self.particle_isplit = 1 if self.input_tsplit else 0
+        self.multirand = rng
+
+    def particle_compute_dist_pertb_abs_v(self):
+        self.particle_dist_pertb_abs_v = self._call(self.gpu.compute_dist_pertb_abs_v, self.input_nv, self.input_v_max)
+
+    def particle_merge(self, thsh):
+        self.particle_np = self._call(self.gpu.particle_merge, thsh)
+
+    def particle_remove(self, thsh):
+        self.particle_np = self._call(self.gpu.particle_remove, thsh, self.input_typeremove, self.input_remove_frac,
+                                      self.multirand.real64)
+
+    def particle_split(self, thsh):
+        self.particle_np = self._call(self.gpu.particle_split, thsh, self.input_split_ngroup,
+                                      self.input_split_dv_sig_frac, self.multirand.gaussian_array)
+
+    def particle_optimize(self, global_time: float) -> bool:
+        """flag_optimized of particle_optimize; global_time is the time at the START of the current step."""
+        flag = False
+        if self.input.deltaf == 0:          # :762
+            return flag
+        dt = self.input.dt
+        if 0 < self.particle_imerge <= len(self.input_tmerge):
+            if global_time + dt >= self.input_tmerge[self.particle_imerge - 1] and self.global_irk == 2:
+                self.particle_compute_dist_pertb_abs_v()
+                self.particle_merge(self.input_thshmerge[self.particle_imerge - 1])
+                self.particle_imerge += 1
+                flag = True
+        if 0 < self.particle_iremove <= len(self.input_tremove):
+            if global_time + dt >= self.input_tremove[self.particle_iremove - 1] and self.global_irk == 2:
+                self.particle_compute_dist_pertb_abs_v()
+                self.particle_remove(self.input_thshremove[self.particle_iremove - 1])
+                self.particle_iremove += 1
+                flag = True
+        if 0 < self.particle_isplit <= len(self.input_tsplit):
+            if global_time + dt >= self.input_tsplit[self.particle_isplit - 1] and self.global_irk == 2:
+                self.particle_compute_dist_pertb_abs_v()
+                self.particle_split(self.input_thshsplit[self.particle_isplit - 1])
+                self.particle_isplit += 1
+                flag = True
+        return flag
 
     def particle_final(self):
         if self.gpu is not None:

@@ -15,7 +15,7 @@ HEADER = os.path.join(ROOT, "include", "pic1dp_gpu.h")
 def _declared_symbols():
     txt = open(HEADER).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(pic1dp_gpu_\w+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(pic1dp_(?:gpu|host)_\w+)\s*\(", txt)))
 
 
 def test_header_symbols_all_exported(capi):
