@@ -147,6 +147,41 @@ interface
     import :: c_ptr, c_int
     type(c_ptr), value :: handle
   end function
+  ! marker optimisation (src/pic1dp_particle.F90:356-746)
+  integer(c_int) function pic1dp_gpu_compute_dist_pertb_abs_v(handle, nv, v_max, dist) &
+      bind(c, name = 'pic1dp_gpu_compute_dist_pertb_abs_v')
+    import :: c_ptr, c_int, c_int32_t, c_double
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: nv
+    real(c_double), value :: v_max
+    real(c_double), intent(out) :: dist(*)   ! [nv, nspecies] in Fortran order
+  end function
+  integer(c_int) function pic1dp_gpu_particle_merge(handle, thsh, np_out) bind(c, name = 'pic1dp_gpu_particle_merge')
+    import :: c_ptr, c_int, c_int64_t, c_double
+    type(c_ptr), value :: handle
+    real(c_double), value :: thsh
+    integer(c_int64_t), intent(out) :: np_out(*)
+  end function
+  integer(c_int) function pic1dp_gpu_particle_remove(handle, thsh, typeremove, remove_frac, dice, rng_ctx, np_out) &
+      bind(c, name = 'pic1dp_gpu_particle_remove')
+    import :: c_ptr, c_funptr, c_int, c_int32_t, c_int64_t, c_double
+    type(c_ptr), value :: handle
+    real(c_double), value :: thsh, remove_frac
+    integer(c_int32_t), value :: typeremove
+    type(c_funptr), value :: dice
+    type(c_ptr), value :: rng_ctx
+    integer(c_int64_t), intent(out) :: np_out(*)
+  end function
+  integer(c_int) function pic1dp_gpu_particle_split(handle, thsh, ngroup, dv_sig_frac, gauss, rng_ctx, np_out) &
+      bind(c, name = 'pic1dp_gpu_particle_split')
+    import :: c_ptr, c_funptr, c_int, c_int32_t, c_int64_t, c_double
+    type(c_ptr), value :: handle
+    real(c_double), value :: thsh, dv_sig_frac
+    integer(c_int32_t), value :: ngroup
+    type(c_funptr), value :: gauss
+    type(c_ptr), value :: rng_ctx
+    integer(c_int64_t), intent(out) :: np_out(*)
+  end function
 end interface
 
 type(c_ptr), save, public :: gpu_handle = c_null_ptr
@@ -157,6 +192,8 @@ public :: pic1dp_gpu_set_markers, pic1dp_gpu_load_markers, pic1dp_gpu_get_marker
 public :: pic1dp_gpu_collect_charge, pic1dp_gpu_solve_field, pic1dp_gpu_push
 public :: pic1dp_gpu_get_field, pic1dp_gpu_sync
 public :: pic1dp_gpu_p2p_export, pic1dp_gpu_p2p_import, pic1dp_gpu_output_field, pic1dp_gpu_output_ptcldist
+public :: pic1dp_gpu_compute_dist_pertb_abs_v, pic1dp_gpu_particle_merge, pic1dp_gpu_particle_remove
+public :: pic1dp_gpu_particle_split
 
 end module pic1dp_gpu
 
@@ -399,6 +436,72 @@ global_ierr = pic1dp_gpu_output_ptcldist(gpu_handle, int(ispecies - 1, c_int32_t
   int(input_nv_opd, c_int32_t), real(input_v_max, c_double), markr_xv, total_xv, pertb_xv, markr_v, total_v, pertb_v)
 CHKERRQ(global_ierr)
 end subroutine gpu_output_ptcldist
+
+! ---- marker optimisation: bodies of particle_compute_dist_pertb_abs_v / particle_merge / particle_remove /
+! particle_split (src/pic1dp_particle.F90:356-746).  particle_optimize (:752-813) itself is unchanged: it still
+! decides WHEN, these decide HOW.  The RNG stays the host's multirand module; the library draws from it through two
+! bind(C) call-backs so that the stream is consumed in the reference's visiting order.
+function gpu_cb_real64(ctx) bind(c) result(r)
+use multirand
+implicit none
+type(c_ptr), value :: ctx
+real(c_double) :: r
+r = multirand_real64()
+end function gpu_cb_real64
+
+subroutine gpu_cb_gaussian_array(ctx, a, n) bind(c)
+use multirand
+implicit none
+type(c_ptr), value :: ctx
+integer(c_int32_t), value :: n
+real(c_double), intent(out) :: a(n)
+call multirand_gaussian_array(a)
+end subroutine gpu_cb_gaussian_array
+
+subroutine gpu_particle_compute_dist_pertb_abs_v(dist_pertb_abs_v)
+implicit none
+#include "finclude/petsc.h90"
+PetscScalar, dimension(input_nspecies, 0 : input_nv - 1), intent(out) :: dist_pertb_abs_v
+real(c_double) :: dist(0 : input_nv - 1, input_nspecies)   ! C layout [nspecies][nv]
+global_ierr = pic1dp_gpu_compute_dist_pertb_abs_v(gpu_handle, int(input_nv, c_int32_t), real(input_v_max, c_double), dist)
+CHKERRQ(global_ierr)
+dist_pertb_abs_v = transpose(dist)
+end subroutine gpu_particle_compute_dist_pertb_abs_v
+
+subroutine gpu_particle_merge(thsh, np)
+implicit none
+#include "finclude/petsc.h90"
+PetscReal, intent(in) :: thsh
+PetscInt, dimension(input_nspecies), intent(out) :: np   ! particle_np
+integer(c_int64_t) :: np64(input_nspecies)
+global_ierr = pic1dp_gpu_particle_merge(gpu_handle, real(thsh, c_double), np64)
+CHKERRQ(global_ierr)
+np = int(np64, kind(np))
+end subroutine gpu_particle_merge
+
+subroutine gpu_particle_remove(thsh, np)
+implicit none
+#include "finclude/petsc.h90"
+PetscReal, intent(in) :: thsh
+PetscInt, dimension(input_nspecies), intent(out) :: np
+integer(c_int64_t) :: np64(input_nspecies)
+global_ierr = pic1dp_gpu_particle_remove(gpu_handle, real(thsh, c_double), int(input_typeremove, c_int32_t), &
+  real(input_remove_frac, c_double), c_funloc(gpu_cb_real64), c_null_ptr, np64)
+CHKERRQ(global_ierr)
+np = int(np64, kind(np))
+end subroutine gpu_particle_remove
+
+subroutine gpu_particle_split(thsh, np)
+implicit none
+#include "finclude/petsc.h90"
+PetscReal, intent(in) :: thsh
+PetscInt, dimension(input_nspecies), intent(out) :: np
+integer(c_int64_t) :: np64(input_nspecies)
+global_ierr = pic1dp_gpu_particle_split(gpu_handle, real(thsh, c_double), int(input_split_ngroup, c_int32_t), &
+  real(input_split_dv_sig_frac, c_double), c_funloc(gpu_cb_gaussian_array), c_null_ptr, np64)
+CHKERRQ(global_ierr)
+np = int(np64, kind(np))
+end subroutine gpu_particle_split
 
 ! particle_final + field_final (src/pic1dp_particle.F90:819-858, src/pic1dp_field.F90:315-348)
 subroutine gpu_final

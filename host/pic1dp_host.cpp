@@ -82,6 +82,23 @@ struct Input {
   std::string out = "pic1dp_energy.txt";
   std::string petsc_out;          // when set: also write the reference's binary output file (pic1dp.out layout)
   int input_nv = 128, input_nx_opd = 64, input_nv_opd = 64;  // src/pic1dp_input.F90:131, :253-256
+  // marker optimisation (src/pic1dp_input.F90:117, :146-206).  The reference hard-codes the schedules as
+  // t_i = 50 + 0.5 i and the thresholds as 0.1 i / n (merge, remove) and 1 - 0.9 i / n (split); start and spacing of
+  // the schedule are run-time values here (opt_t0, opt_dt), the formulas are the reference's.
+  int64_t input_species_nparticle_init = -1;  // -1: input_nparticle_max (:117)
+  int input_nmerge = 0, input_nremove = 0, input_nsplit = 0;
+  double opt_t0 = 50.0, opt_dt = 0.5;
+  int input_typeremove = 2;
+  double input_remove_frac = 0.9;
+  int input_split_ngroup = 5;
+  double input_split_dv_sig_frac = 0.1;
+  std::string markers_out;  // when set: rank 0 dumps its final x, v, p, w (raw doubles) for inspection / tests
+  double input_tmerge(int i) const { return opt_t0 + i * opt_dt; }                                      // :150
+  double input_thshmerge(int i) const { return 0.1 / (input_nmerge > 1 ? input_nmerge : 1) * (double)i; }   // :157
+  double input_tremove(int i) const { return opt_t0 + i * opt_dt; }                                     // :166
+  double input_thshremove(int i) const { return 0.1 / (input_nremove > 1 ? input_nremove : 1) * (double)i; }  // :179
+  double input_tsplit(int i) const { return opt_t0 + i * opt_dt; }                                      // :192
+  double input_thshsplit(int i) const { return 1.0 - 0.9 / (input_nsplit > 1 ? input_nsplit : 1) * (double)i; }  // :199
 };
 
 static bool parse(Input &in, int argc, char **argv) {
@@ -120,6 +137,17 @@ static bool parse(Input &in, int argc, char **argv) {
     else if (k == "fuse") in.fuse = (int)d;
     else if (k == "out") in.out = v;
     else if (k == "petsc_out") in.petsc_out = v;
+    else if (k == "nparticle_init") in.input_species_nparticle_init = (int64_t)d;
+    else if (k == "nmerge") in.input_nmerge = (int)d;
+    else if (k == "nremove") in.input_nremove = (int)d;
+    else if (k == "nsplit") in.input_nsplit = (int)d;
+    else if (k == "opt_t0") in.opt_t0 = d;
+    else if (k == "opt_dt") in.opt_dt = d;
+    else if (k == "typeremove") in.input_typeremove = (int)d;
+    else if (k == "remove_frac") in.input_remove_frac = d;
+    else if (k == "split_ngroup") in.input_split_ngroup = (int)d;
+    else if (k == "split_dv_sig_frac") in.input_split_dv_sig_frac = d;
+    else if (k == "markers_out") in.markers_out = v;
     else return false;
   }
   return true;
@@ -133,6 +161,11 @@ static void input_init(const Input &in) {
   }
   if (in.input_linear == 1 && in.input_deltaf == 0) {
     fprintf(stderr, "Error: case of input_linear = 1 and input_deltaf = 0 not implemented yet.\n");
+    exit(1);
+  }
+  if (in.input_species_nparticle_init > in.input_nparticle_max || in.input_species_nparticle_init == 0 ||
+      (in.input_typeremove != 1 && in.input_typeremove != 2) || in.input_split_ngroup < 1) {
+    fprintf(stderr, "Error: bad marker-optimisation input.\n");
     exit(1);
   }
 }
@@ -283,6 +316,33 @@ struct Generator {
   void real_array(double *a, int64_t n) {
     for (int64_t i = 0; i < n; i++) a[i] = real64();
   }
+  // multirand_gaussian_array64 (:838-872): Marsaglia's polar method, two values per accepted point; an odd tail
+  // leaves the second value in the one-slot buffer that the next call consumes first
+  double spare = 0.0;
+  bool has_spare = false;
+  void gaussian_array(double *a, int64_t n) {
+    int64_t k = 0;
+    if (has_spare && n > 0) {
+      a[k++] = spare;
+      has_spare = false;
+    }
+    while (k < n) {
+      double gx, gy, r2;
+      do {
+        gx = (double)int64() / 9223372036854775807.0;
+        gy = (double)int64() / 9223372036854775807.0;
+        r2 = gx * gx + gy * gy;
+      } while (!(r2 > 0.0 && r2 < 1.0));
+      const double f = sqrt((-2.0 * log(r2)) / r2);
+      a[k++] = gx * f;
+      if (k < n) {
+        a[k++] = gy * f;
+      } else {
+        spare = gy * f;
+        has_spare = true;
+      }
+    }
+  }
 };
 }  // namespace multirand
 
@@ -293,6 +353,9 @@ struct Rank {
   pic1dp_gpu_t *h = nullptr;
   int64_t particle_ip_low = 0, particle_ip_high = 0, particle_np = 0;
   std::vector<double> x, v;        // host scratch for the two uniform streams of particle_load
+  multirand::Generator rng;        // module state of multirand (seeded in particle_load, drawn again by remove / split)
+  int particle_imerge = 0, particle_iremove = 0, particle_isplit = 0;  // src/pic1dp_particle.F90:26, :73-87
+  double marker_steps = 0.0;       // sum over timesteps of particle_np (throughput report)
   std::vector<double> field_electric, field_chargeden, field_mode_re, field_mode_im;
 };
 
@@ -334,6 +397,9 @@ static void particle_init(Rank &r, const uint8_t *uid) {
     r.g.global_ierr = pic1dp_gpu_comm_init(r.h, uid);
     CHKERRQ(r.g, r.h);
   }
+  r.particle_imerge = in.input_nmerge > 0 ? 1 : 0;    // :73-77
+  r.particle_iremove = in.input_nremove > 0 ? 1 : 0;  // :78-82
+  r.particle_isplit = in.input_nsplit > 0 ? 1 : 0;    // :83-87
   r.field_electric.resize(in.input_nx);
   r.field_chargeden.resize(in.input_nx);
   r.field_mode_re.resize(in.input_nmode);
@@ -346,17 +412,21 @@ static void particle_init(Rank &r, const uint8_t *uid) {
 // two uniform streams cross PCIe.
 static void particle_load(Rank &r) {
   const pic1dp_input::Input &in = *r.in;
-  multirand::Generator rng;
+  multirand::Generator &rng = r.rng;
   if (in.input_multirand_selftest && !rng.selftest(in.input_multirand_al_int))
     fprintf(stderr, "[%d][multirand_selftest] Warning: unexpected head sequence.\n", r.g.global_mype);
   rng.init(in.input_multirand_al_int, in.input_multirand_seed_type, r.g.global_mype, in.input_multirand_warmup);
   const int64_t n = r.particle_ip_high - r.particle_ip_low;
   r.v.resize(n);
   r.x.resize(n);
-  rng.real_array(r.v.data(), n);  // :180
+  rng.real_array(r.v.data(), n);  // :180  (the whole local array is drawn, used or not)
   rng.real_array(r.x.data(), n);  // :222
-  r.particle_np = n;  // input_species_nparticle_init == input_nparticle_max: nothing to unload (:240-248)
-  r.g.global_ierr = pic1dp_gpu_load_markers(r.h, 0, n, in.input_nparticle_max, r.v.data(), r.x.data(), in.input_v_max,
+  // unload not used particles (:240-248): the tail of the local array stays free for particle_split
+  const int64_t ninit = in.input_species_nparticle_init > 0 ? in.input_species_nparticle_init : in.input_nparticle_max;
+  int64_t nparticle_unload = (in.input_nparticle_max - ninit) / r.g.global_npe;
+  if (r.g.global_mype == 0) nparticle_unload += (in.input_nparticle_max - ninit) % r.g.global_npe;
+  r.particle_np = n - nparticle_unload;
+  r.g.global_ierr = pic1dp_gpu_load_markers(r.h, 0, r.particle_np, ninit, r.v.data(), r.x.data(), in.input_v_max,
                                             in.input_init_nmode, in.input_init_mode, in.input_init_mode_cos,
                                             in.input_init_mode_sin);
   CHKERRQ(r.g, r.h);
@@ -368,6 +438,59 @@ static void particle_compute_shape_x(Rank &r) {  // :275-350
   r.g.global_ierr = pic1dp_gpu_compute_shape_x(r.h);
   CHKERRQ(r.g, r.h);
 }
+// RNG call-backs handed through the C ABI (the generator is this rank's module state)
+static double cb_real64(void *ctx) { return static_cast<multirand::Generator *>(ctx)->real64(); }
+static void cb_gaussian_array(void *ctx, double *a, int32_t n) { static_cast<multirand::Generator *>(ctx)->gaussian_array(a, n); }
+
+static void particle_compute_dist_pertb_abs_v(Rank &r) {  // :356-403, reduced on the device
+  r.g.global_ierr = pic1dp_gpu_compute_dist_pertb_abs_v(r.h, r.in->input_nv, r.in->input_v_max, nullptr);
+  CHKERRQ(r.g, r.h);
+}
+static void particle_merge(Rank &r, double thsh_frac_dist_pertb_abs_v) {  // :411-522
+  r.g.global_ierr = pic1dp_gpu_particle_merge(r.h, thsh_frac_dist_pertb_abs_v, &r.particle_np);
+  CHKERRQ(r.g, r.h);
+}
+static void particle_remove(Rank &r, double thsh_frac_dist_pertb_abs_v) {  // :530-627
+  r.g.global_ierr = pic1dp_gpu_particle_remove(r.h, thsh_frac_dist_pertb_abs_v, r.in->input_typeremove,
+                                               r.in->input_remove_frac, cb_real64, &r.rng, &r.particle_np);
+  CHKERRQ(r.g, r.h);
+}
+static void particle_split(Rank &r, double thsh_frac_dist_pertb_abs_v) {  // :635-746
+  r.g.global_ierr = pic1dp_gpu_particle_split(r.h, thsh_frac_dist_pertb_abs_v, r.in->input_split_ngroup,
+                                              r.in->input_split_dv_sig_frac, cb_gaussian_array, &r.rng, &r.particle_np);
+  CHKERRQ(r.g, r.h);
+}
+// particle_optimize (:752-813): manages the calling of merge / remove / split
+static void particle_optimize(Rank &r, bool &flag_optimized) {
+  const pic1dp_input::Input &in = *r.in;
+  flag_optimized = false;
+  if (in.input_deltaf == 0) return;  // "now only support optimization for delta f"
+  if (r.particle_imerge > 0 && r.particle_imerge <= in.input_nmerge) {
+    if (r.g.global_time + in.input_dt >= in.input_tmerge(r.particle_imerge) && r.g.global_irk == 2) {
+      particle_compute_dist_pertb_abs_v(r);
+      particle_merge(r, in.input_thshmerge(r.particle_imerge));
+      r.particle_imerge++;
+      flag_optimized = true;
+    }
+  }
+  if (r.particle_iremove > 0 && r.particle_iremove <= in.input_nremove) {
+    if (r.g.global_time + in.input_dt >= in.input_tremove(r.particle_iremove) && r.g.global_irk == 2) {
+      particle_compute_dist_pertb_abs_v(r);
+      particle_remove(r, in.input_thshremove(r.particle_iremove));
+      r.particle_iremove++;
+      flag_optimized = true;
+    }
+  }
+  if (r.particle_isplit > 0 && r.particle_isplit <= in.input_nsplit) {
+    if (r.g.global_time + in.input_dt >= in.input_tsplit(r.particle_isplit) && r.g.global_irk == 2) {
+      particle_compute_dist_pertb_abs_v(r);
+      particle_split(r, in.input_thshsplit(r.particle_isplit));
+      r.particle_isplit++;
+      flag_optimized = true;
+    }
+  }
+}
+
 static void particle_final(Rank &r) {  // :819-858 (+ field_final)
   r.g.global_ierr = pic1dp_gpu_destroy(r.h);
   r.h = nullptr;
@@ -493,13 +616,17 @@ static void run_rank(const pic1dp_input::Input *in, int mype, int npe, const uin
   while (itermination == 0) {  // :78-109
     for (r.g.global_irk = 1; r.g.global_irk <= 2; r.g.global_irk++) {
       pic1dp_interaction::interaction_push_particle(r);
-      // particle_optimize: disabled in the default input (input_nmerge = nremove = nsplit = 0)
+      bool flag_optimized;
+      pic1dp_particle::particle_optimize(r, flag_optimized);  // src/pic1dp.F90:82 (off in the default input)
+      if (flag_optimized && mype == 0)                        // output_progress(2), :83
+        printf("t=%g: marker optimisation, %lld markers on rank 0\n", r.g.global_time + in->input_dt, (long long)r.particle_np);
       if (in->input_iptclshape < 4) pic1dp_particle::particle_compute_shape_x(r);
       pic1dp_interaction::interaction_collect_charge(r);
       pic1dp_field::field_solve_electric(r);
     }
     r.g.global_itime++;
     r.g.global_time += in->input_dt;
+    r.marker_steps += (double)r.particle_np;
     itermination = check_termination(r);
     const double eps = pic1dp_global::PETSC_SQRT_MACHINE_EPSILON;
     if (fmod(r.g.global_time + eps, in->input_output_interval) <
@@ -511,13 +638,25 @@ static void run_rank(const pic1dp_input::Input *in, int mype, int npe, const uin
   }
   float ms = 0.f;
   pic1dp_gpu_timer_stop(r.h, &ms);
-  if (steps_per_s) *steps_per_s = (double)r.particle_np * r.g.global_itime / (ms * 1e-3);
+  if (steps_per_s) *steps_per_s = r.marker_steps / (ms * 1e-3);
   pic1dp_counters c;
   pic1dp_gpu_get_counters(r.h, &c);
   if (mype == 0)
     printf("steps=%d markers/rank=%lld kernels=%lld nccl=%lld oob=%lld deposit_mode=%d  %.3e particle-steps/s/rank (wall incl. outputs)\n",
            r.g.global_itime, (long long)r.particle_np, (long long)c.kernel_launches, (long long)c.nccl_calls,
-           (long long)c.oob_markers, c.deposit_mode, (double)r.particle_np * r.g.global_itime / (ms * 1e-3));
+           (long long)c.oob_markers, c.deposit_mode, r.marker_steps / (ms * 1e-3));
+  if (mype == 0 && !in->markers_out.empty()) {  // final marker arrays of rank 0: int64 np, then x, v, p, w
+    std::vector<double> buf((size_t)r.particle_np * 4);
+    int64_t n = 0;
+    double *b = buf.data();
+    r.g.global_ierr = pic1dp_gpu_get_markers(r.h, 0, b, b + r.particle_np, b + 2 * r.particle_np, b + 3 * r.particle_np, &n);
+    CHKERRQ(r.g, r.h);
+    if (FILE *fm = fopen(in->markers_out.c_str(), "wb")) {
+      fwrite(&n, 8, 1, fm);
+      fwrite(b, 8, (size_t)n * 4, fm);
+      fclose(fm);
+    }
+  }
   pic1dp_particle::particle_final(r);
   if (f) fclose(f);
   if (fb) fclose(fb);
