@@ -63,7 +63,9 @@ enum {
 enum {
   PIC1DP_LOAD_AUTO = 0,
   PIC1DP_LOAD_DIRECT = 1, /* 128-bit streaming loads into registers, 2 markers per thread */
-  PIC1DP_LOAD_TMA = 2     /* cp.async.bulk tiles into a shared-memory ring (mbarrier pipeline), 1 marker per thread */
+  PIC1DP_LOAD_TMA = 2,    /* cp.async.bulk tiles into a shared-memory ring (mbarrier pipeline) */
+  PIC1DP_LOAD_CPASYNC = 3 /* per-thread cp.async (LDGSTS.128) into thread-private slots of a 2-stage shared-memory ring:
+                             next tile in flight during the current one, no barrier; used where the ring fits */
 };
 
 /* field-solve summation order for the partial-DFT projections */

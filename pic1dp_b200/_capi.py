@@ -16,7 +16,7 @@ IPC_HANDLE_BYTES = 64
 OK, EINVAL, ECUDA, ENCCL, ENOMEM, ESTATE, ECAPACITY, ENODEVICE, EUNSUPPORTED = range(9)
 DEPOSIT_AUTO, DEPOSIT_SMEM_ATOMIC, DEPOSIT_GLOBAL_RED, DEPOSIT_WARP_PRIVATE = range(4)
 FIELD_TREE, FIELD_SEQUENTIAL = range(2)
-LOAD_AUTO, LOAD_DIRECT, LOAD_TMA = range(3)
+LOAD_AUTO, LOAD_DIRECT, LOAD_TMA, LOAD_CPASYNC = range(4)
 
 # PIC1DP_B200_LIB overrides the library path (kernel A/B experiments under scratch/); the product default is in-tree
 _LIB_PATH = os.environ.get("PIC1DP_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)),

@@ -665,10 +665,15 @@ __device__ __forceinline__ void dep_flush(double *smem_after_E, int nx, double *
 // ------------------------------------------------------------------------------------------------------------
 // one tile step of one thread: markers i, i+1.  FULL: the whole CTA tile is inside [0, np) (no tail checks).
 template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG, bool FULL>
+__device__ __forceinline__ void push_pair_body(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep,
+                                               const int64_t i, unsigned long long &noob, double2 x, double2 v, double2 w,
+                                               double2 p, double2 xb, double2 vb, double2 wb);
+
+template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG, bool FULL>
 __device__ __forceinline__ void push_pair(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep, const int64_t i,
                                           unsigned long long &noob) {
   typedef Cfg<CFG> F;
-  const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
+  const bool deltaf = F::deltaf(a.deltaf);
   const bool need_p = deltaf || FUSED;  // full-f deposits p (src/pic1dp_interaction.F90:88-90)
   const bool v0ok = FULL || i < a.np, v1ok = FULL || i + 1 < a.np;
   double2 x = {0.0, 0.0}, v = {0.0, 0.0}, w = {0.0, 0.0}, p = {0.0, 0.0};
@@ -694,6 +699,17 @@ __device__ __forceinline__ void push_pair(const ParticleArgs &a, const double *s
       if (deltaf) wb.x = ld1(a.w_bak + i);
     }
   }
+  push_pair_body<DIST, IRK2, DEP, FUSED, CFG, FULL>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
+}
+
+// the arithmetic, stores and deposit of one tile step, given the loaded markers (xb, vb, wb are ignored at irk == 1)
+template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG, bool FULL>
+__device__ __forceinline__ void push_pair_body(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep,
+                                               const int64_t i, unsigned long long &noob, double2 x, double2 v, double2 w,
+                                               double2 p, double2 xb, double2 vb, double2 wb) {
+  typedef Cfg<CFG> F;
+  const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
+  const bool v0ok = FULL || i < a.np, v1ok = FULL || i + 1 < a.np;
   if (!IRK2) {
     xb = x;
     vb = v;
@@ -783,6 +799,82 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   }
   if (FUSED) dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
   if (FUSED && noob) atomicAdd(a.noob, noob);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// cp.async-staged variant of the fused substep kernel (delta-f nonlinear, fused; opt-in / AUTO where it measured
+// faster).  The direct kernel's loads are only outstanding at the top of an iteration and with 64 registers per
+// thread there is no room to hold the next tile in registers, so ~25 % of its stall samples are the first use of
+// the streamed x.  Here every thread copies ITS OWN 2 markers of the next tile step into a private 16-byte slot per
+// array of a 2-stage shared-memory ring with cp.async (LDGSTS.128, no registers, no L1), computes the current tile
+// step from the other stage, and waits with cp.async.wait_group: slots are thread-private, so there is no mbarrier,
+// no elected producer and no CTA-wide synchronisation in the loop (unlike the TMA ring below).  Tail tiles fall back
+// to direct loads.  Ring: STAGES x NARR x blockDim x 16 B (128 KB at irk = 1 with 1024 threads).
+// ------------------------------------------------------------------------------------------------------------
+namespace cpa {
+__device__ __forceinline__ void copy16(unsigned dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+}  // namespace cpa
+
+template <int DIST, bool IRK2, int DEP, int CFG>
+__global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push_cpa(const ParticleArgs a) {
+  constexpr int NARR = IRK2 ? 7 : 4;  // x v w p [xb vb wb]
+  extern __shared__ __align__(16) double smem[];
+  double *sE = smem;
+  for (int j = threadIdx.x; j < a.nx; j += blockDim.x) sE[j] = a.E[j];
+  double *my_partial = a.partial + (size_t)blockIdx.x * a.nx;
+  Depositor<DEP> dep;
+  double *dep_base = smem + ((a.nx + 1) & ~1);
+  dep.g = dep_setup<DEP>(dep_base, a.nx, my_partial);
+  const int ngr = (DEP == DEP_WARP_PRIVATE) ? (int)(blockDim.x >> 5) : (DEP == DEP_SMEM_ATOMIC ? 2 : 0);
+  double2 *ring = reinterpret_cast<double2 *>(dep_base + (((size_t)a.nx * ngr + 1) & ~(size_t)1));  // [2][NARR][blockDim]
+  __syncthreads();
+
+  const double *src[7] = {a.x_cur, a.v_cur, a.w_cur, a.p, a.x_bak, a.v_bak, a.w_bak};
+  const int64_t tile = (int64_t)blockDim.x * 2, stride = (int64_t)gridDim.x * tile;
+  const unsigned slot0 = (unsigned)__cvta_generic_to_shared(ring + threadIdx.x);
+  const unsigned arr_bytes = blockDim.x * 16u, stage_bytes = NARR * arr_bytes;
+  auto stage_in = [&](int64_t base, int st) {  // this thread's markers base + 2 tid, base + 2 tid + 1 of a full tile
+    const int64_t i = base + (int64_t)threadIdx.x * 2;
+#pragma unroll
+    for (int q = 0; q < NARR; q++) cpa::copy16(slot0 + st * stage_bytes + q * arr_bytes, src[q] + i);
+    cpa::commit();
+  };
+  unsigned long long noob = 0;
+  int64_t base = (int64_t)blockIdx.x * tile;
+  bool cur_staged = base + tile <= a.np;
+  if (cur_staged) stage_in(base, 0);
+  for (int st = 0; base < a.np; base += stride, st ^= 1) {
+    const int64_t next = base + stride;
+    const bool next_staged = next + tile <= a.np;
+    if (next_staged) stage_in(next, st ^ 1);
+    const int64_t i = base + (int64_t)threadIdx.x * 2;
+    if (cur_staged) {
+      if (next_staged)
+        cpa::wait<1>();
+      else
+        cpa::wait<0>();
+      const double2 *rs = ring + (size_t)st * NARR * blockDim.x + threadIdx.x;
+      const int B = blockDim.x;
+      const double2 x = rs[0], v = rs[B], w = rs[2 * B], p = rs[3 * B];
+      double2 xb = x, vb = v, wb = w;
+      if (IRK2) {
+        xb = rs[4 * B];
+        vb = rs[5 * B];
+        wb = rs[6 * B];
+      }
+      push_pair_body<DIST, IRK2, DEP, true, CFG, true>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
+    } else {
+      push_pair<DIST, IRK2, DEP, true, CFG, false>(a, sE, dep, i, noob);
+    }
+    cur_staged = next_staged;
+  }
+  dep_flush<DEP>(dep_base, a.nx, my_partial);
+  if (noob) atomicAdd(a.noob, noob);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -36,6 +36,14 @@ using namespace pic1dp;
 #define PIC1DP_TMA_AUTO_IRK2 0
 #endif
 static const bool PIC1DP_TMA_AUTO_IRK[2] = {PIC1DP_TMA_AUTO_IRK1 != 0, PIC1DP_TMA_AUTO_IRK2 != 0};
+// LOAD_AUTO: which substeps use the cp.async-staged kernel when its ring fits beside the deposit grids
+#ifndef PIC1DP_CPA_AUTO_IRK1
+#define PIC1DP_CPA_AUTO_IRK1 0
+#endif
+#ifndef PIC1DP_CPA_AUTO_IRK2
+#define PIC1DP_CPA_AUTO_IRK2 0
+#endif
+static const bool PIC1DP_CPA_AUTO_IRK[2] = {PIC1DP_CPA_AUTO_IRK1 != 0, PIC1DP_CPA_AUTO_IRK2 != 0};
 
 // ------------------------------------------------------------------------------------------------------------
 // NCCL is bound at run time (dlopen) and only when nranks > 1, so a single-GPU process never needs it and a
@@ -117,6 +125,8 @@ struct pic1dp_gpu {
   int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0, cfg = -1;
   bool use_tma[2] = {false, false};  // per substep (irk = 1, 2)
   int tma_smem[2] = {0, 0};  // dynamic shared memory of the TMA kernels, irk = 1, 2
+  bool use_cpa[2] = {false, false};  // cp.async-staged kernel per substep
+  int cpa_smem[2] = {0, 0};
   bool partial_valid = false;  // a fused push has already deposited into d_partial
   int nred = 1;
   ncclComm_t comm = nullptr;
@@ -254,6 +264,30 @@ static PushKernel pick_tma(int dist, int dep, bool irk2, int cfg) {
   }
 }
 
+// cp.async-staged flagship kernels (delta-f nonlinear, fused): cfg in {1, 9, 25}
+template <int DIST, bool IRK2, int CFG>
+static PushKernel pick_cpa_dep(int dep) {
+  switch (dep) {
+    case DEP_SMEM_ATOMIC: return k_push_cpa<DIST, IRK2, DEP_SMEM_ATOMIC, CFG>;
+    case DEP_GLOBAL_RED: return k_push_cpa<DIST, IRK2, DEP_GLOBAL_RED, CFG>;
+    default: return k_push_cpa<DIST, IRK2, DEP_WARP_PRIVATE, CFG>;
+  }
+}
+template <int DIST>
+static PushKernel pick_cpa_dist(int dep, bool irk2, int cfg) {
+  if (cfg == 25) return irk2 ? pick_cpa_dep<DIST, true, 25>(dep) : pick_cpa_dep<DIST, false, 25>(dep);
+  if (cfg == 9) return irk2 ? pick_cpa_dep<DIST, true, 9>(dep) : pick_cpa_dep<DIST, false, 9>(dep);
+  return irk2 ? pick_cpa_dep<DIST, true, 1>(dep) : pick_cpa_dep<DIST, false, 1>(dep);
+}
+static PushKernel pick_cpa(int dist, int dep, bool irk2, int cfg) {
+  switch (dist) {
+    case 1: return pick_cpa_dist<1>(dep, irk2, cfg);
+    case 2: return pick_cpa_dist<2>(dep, irk2, cfg);
+    case 3: return pick_cpa_dist<3>(dep, irk2, cfg);
+    default: return pick_cpa_dist<0>(dep, irk2, cfg);
+  }
+}
+
 static PushKernel pick_deposit(int dep, bool deposit) {
   if (!deposit) return k_deposit<DEP_SMEM_ATOMIC, false>;
   switch (dep) {
@@ -335,7 +369,7 @@ static int validate(const pic1dp_params *p, std::string &err) {
       return PIC1DP_EINVAL;
     }
   if (p->deposit_mode < 0 || p->deposit_mode > 3 || p->field_mode < 0 || p->field_mode > 1 || p->load_path < 0 ||
-      p->load_path > 2) {
+      p->load_path > 3) {
     err = "bad deposit_mode / field_mode / load_path";
     return PIC1DP_EINVAL;
   }
@@ -490,6 +524,33 @@ static int create_impl(pic1dp_gpu_t *h) {
       }
     } else if (p.load_path == PIC1DP_LOAD_TMA) {
       h->err = "load_path = TMA needs a delta-f nonlinear run with an atomic deposit mode";
+      return PIC1DP_EUNSUPPORTED;
+    }
+    // cp.async-staged variant: same CTA shape as the direct kernel plus a ring of 2 stages x NARR x threads x 16 B
+    h->use_cpa[0] = h->use_cpa[1] = false;
+    if (h->cfg == 1 && (p.load_path == PIC1DP_LOAD_CPASYNC || p.load_path == PIC1DP_LOAD_AUTO)) {
+      for (int irk2 = 0; irk2 < 2; irk2++) {
+        const size_t ring = (size_t)2 * (irk2 ? 7 : 4) * h->threads * 16;
+        const size_t need = 8 * (((size_t)(nx + 1) & ~(size_t)1) + (((size_t)nx * dep_grids(dep, h->threads) + 1) & ~(size_t)1)) + ring;
+        h->cpa_smem[irk2] = (int)need;
+        bool ok = need <= max_smem;
+        const int cfgs3[3] = {1, 9, 25};
+        for (int ci = 0; ci < 3 && ok; ci++) {
+          PushKernel k = pick_cpa(p.iptcldist, dep, irk2 == 1, cfgs3[ci]);
+          CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+          int per_sm = 0;
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, h->threads, need));
+          if (per_sm < per_sm_min) ok = false;
+        }
+        const bool want = (p.load_path == PIC1DP_LOAD_CPASYNC) || PIC1DP_CPA_AUTO_IRK[irk2];
+        h->use_cpa[irk2] = ok && want;
+      }
+      if (p.load_path == PIC1DP_LOAD_CPASYNC && !h->use_cpa[0] && !h->use_cpa[1]) {
+        h->err = "load_path = CPASYNC: the shared-memory ring does not fit beside the deposit grids for this nx";
+        return PIC1DP_EUNSUPPORTED;
+      }
+    } else if (p.load_path == PIC1DP_LOAD_CPASYNC) {
+      h->err = "load_path = CPASYNC needs a delta-f nonlinear run";
       return PIC1DP_EUNSUPPORTED;
     }
     h->grid = h->nsm * per_sm_min;  // persistent grid: every CTA resident, private grid per CTA
@@ -952,7 +1013,10 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
     a.v_out = S.v[out];
     a.w_out = S.w[out];
     const int cfg = (h->cfg == 1) ? (S.c.unit ? 25 : S.c.pow2 ? 9 : 1) : -1;
-    if (fused && h->use_tma[irk - 1] && cfg > 0) {
+    if (fused && h->use_cpa[irk - 1] && cfg > 0) {
+      PushKernel k = pick_cpa(p.iptcldist, h->dep, irk == 2, cfg);
+      k<<<h->grid, h->threads, h->cpa_smem[irk - 1], h->stream>>>(a);
+    } else if (fused && h->use_tma[irk - 1] && cfg > 0) {
       PushKernel k = pick_tma(p.iptcldist, h->dep, irk == 2, cfg);
       k<<<h->grid, 512, h->tma_smem[irk - 1], h->stream>>>(a);
     } else {

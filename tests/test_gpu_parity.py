@@ -365,12 +365,14 @@ def test_charge_conservation_and_linearity_at_scale():
     assert rel_err(r1 + r2, r12) < TOL_SUM
 
 
+@pytest.mark.parametrize("load_path", [P._capi.LOAD_TMA, P._capi.LOAD_CPASYNC])
 @pytest.mark.parametrize("dep", DEPOSITS)
 @pytest.mark.parametrize("case", ["unit", "pow2", "nonpow2", "maxwell"])
-def test_tma_ring_path_against_oracle(dep, case):
-    """load_path = TMA (cp.async.bulk tiles through a shared-memory ring): one substep with prescribed E is bit-exact
-    in x, v; five full steps stay within the summation-order tolerance; ragged sizes cover partial tiles."""
-    kw = dict(nx=256, capacity=70001, deposit_mode=dep, load_path=P._capi.LOAD_TMA)
+def test_staged_load_paths_against_oracle(dep, case, load_path):
+    """load_path = TMA (cp.async.bulk tiles through a shared-memory ring) and CPASYNC (per-thread cp.async into
+    thread-private ring slots): one substep with prescribed E is bit-exact in x, v; five full steps stay within the
+    summation-order tolerance; ragged sizes cover partial tiles."""
+    kw = dict(nx=256, capacity=1000003, deposit_mode=dep, load_path=load_path)
     if case == "pow2":
         kw.update(temperature=[2.0], mass=[0.5], temperature2=[0.5])
     elif case == "nonpow2":
@@ -382,8 +384,8 @@ def test_tma_ring_path_against_oracle(dep, case):
         _gpu(gp).close()
     except P.Pic1dpError as e:
         assert e.code == 8  # PIC1DP_EUNSUPPORTED: the ring does not reach the direct kernel's residency here
-        pytest.skip("TMA ring not available for this deposit mode / nx")
-    for n in (70001, 512, 513, 1, 1023):
+        pytest.skip("shared-memory ring not available for this deposit mode / nx")
+    for n in (1000003, 70001, 512, 513, 1, 1023):  # 1000003: several tile steps per CTA, so the ring wraps
         st = synth_markers(op, n, seed=80 + n % 7)
         E = 1e-3 * np.sin(2 * np.pi * np.arange(op.nx) / op.nx + 0.1)
         ref = OracleRun(op, [[copy_state(st)]])
