@@ -338,6 +338,13 @@ int pic1dp_gpu_get_counters(pic1dp_gpu_t *h, pic1dp_counters *c);
  * ms[0] push+deposit irk=1, ms[1] reduce+allreduce irk=1, ms[2] field irk=1, ms[3..5] same for irk=2 */
 int pic1dp_gpu_profile_step(pic1dp_gpu_t *h, float ms[6]);
 
+/* launch timing: between start and stop every fused particle-kernel launch of push() / step() is bracketed by a pair
+ * of CUDA events on the handle's stream (up to 8192 launches).  stop synchronises and returns, per substep
+ * (index 0: irk = 1, index 1: irk = 2), the summed device time in ms and the number of launches -- the per-launch
+ * average over a whole timed region rather than over one separately profiled step. */
+int pic1dp_gpu_launch_timing_start(pic1dp_gpu_t *h);
+int pic1dp_gpu_launch_timing_stop(pic1dp_gpu_t *h, double ms_sum[2], int64_t launches[2]);
+
 #ifdef __cplusplus
 }
 #endif

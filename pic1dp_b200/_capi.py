@@ -85,6 +85,7 @@ EXPORTS = [
     "pic1dp_gpu_compute_dist_pertb_abs_v", "pic1dp_gpu_particle_merge", "pic1dp_gpu_particle_remove",
     "pic1dp_gpu_particle_split",
     "pic1dp_host_particle_merge", "pic1dp_host_particle_remove", "pic1dp_host_particle_split",
+    "pic1dp_gpu_launch_timing_start", "pic1dp_gpu_launch_timing_stop",
 ]
 
 # RNG call-backs of particle_remove / particle_split (pic1dp_real64_fn, pic1dp_gaussian_array_fn)
@@ -144,6 +145,8 @@ def load() -> C.CDLL:
     L.pic1dp_gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.pic1dp_gpu_profile_step.argtypes = [vp, C.POINTER(C.c_float)]
     i64p, dbl = C.POINTER(i64), C.c_double
+    L.pic1dp_gpu_launch_timing_start.argtypes = [vp]
+    L.pic1dp_gpu_launch_timing_stop.argtypes = [vp, dp, i64p]
     L.pic1dp_gpu_compute_dist_pertb_abs_v.argtypes = [vp, i32, dbl, dp]
     L.pic1dp_gpu_particle_merge.argtypes = [vp, dbl, i64p]
     L.pic1dp_gpu_particle_remove.argtypes = [vp, dbl, i32, dbl, REAL64_FN, vp, i64p]

@@ -19,7 +19,12 @@
 #endif
 // which fused-kernel variants issue L2 prefetches: bit 0/1 = atomic deposits irk 1/2, bit 2/3 = warp-private irk 1/2
 #ifndef PIC1DP_PF_MASK
-#define PIC1DP_PF_MASK 8
+#define PIC1DP_PF_MASK 12
+#endif
+// which fused-kernel variants stage the next tile step's v in registers (same bit layout as PIC1DP_PF_MASK).
+// Measured on B200 at 1e8 markers, nx = 1024: warp-private irk=1 1.264 -> 1.158 ms; atomic deposits +0.5 % slower.
+#ifndef PIC1DP_PV_MASK
+#define PIC1DP_PV_MASK 4
 #endif
 
 namespace pic1dp {
@@ -294,31 +299,30 @@ __device__ __forceinline__ void push_one(const ParticleArgs &a, const double *sE
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// N-wide forms of the functions above.  The per-marker code is a chain of dependent fp64 operations (exact
+// N-wide fast forms of the functions above.  The per-marker code is a chain of dependent fp64 operations (exact
 // division, two exponentials, another division); processing the N = 2 markers of a thread as explicitly interleaved
-// straight-line code, with the rare-path tests of all lanes OR-ed into one branch, lets the scheduler overlap the
-// independent chains instead of stalling on fixed-latency dependencies.  Every lane performs exactly the scalar
-// sequence of operations, so results are bit-identical to the scalar functions.
+// straight-line code lets the scheduler overlap the independent chains instead of stalling on fixed-latency
+// dependencies.  These forms contain NO rare path at all: every operation that could need the IEEE routine (division
+// next to a rounding midpoint or out of range, |exp argument| > 700, x more than a box length away) only ORs a flag
+// into `rare`, and the caller redoes a flagged marker pair with the scalar functions above (push_one, wrap_x,
+// shape_of), which hold the rare paths.  Without call sites in the hot loop ptxas keeps the polynomial and kernel
+// constants in uniform registers and the body spill-free (measured: 420 -> ~360 issued instructions per tile step).
+// When no flag is raised every lane has performed exactly the scalar sequence of operations, so the results are
+// bit-identical to the scalar functions.
 // ------------------------------------------------------------------------------------------------------------
 template <int N>
-__device__ __forceinline__ void div_const_n(const double (&a)[N], double b, double y, double (&q)[N]) {
-  bool rare = false;
+__device__ __forceinline__ void div_const_n(const double (&a)[N], double b, double y, double (&q)[N], bool &rare) {
 #pragma unroll
   for (int k = 0; k < N; k++) {
     const double q0 = a[k] * y;
     const double r = fma(-q0, b, a[k]);
     q[k] = fma(r, y, q0);
-    rare |= !(a[k] >= 0x1p-800) || div_suspect(a[k], b, q[k]);
-  }
-  if (__builtin_expect(rare, 0)) {
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = div_slow(a[k], b);
+    rare = rare | !(a[k] >= 0x1p-800) | div_suspect(a[k], b, q[k]);  // no short-circuit: predicate logic, no branches
   }
 }
 
 template <int N>
-__device__ __forceinline__ void div_pos_n(const double (&a)[N], const double (&b)[N], double (&q)[N]) {
-  bool rare = false;
+__device__ __forceinline__ void div_pos_n(const double (&a)[N], const double (&b)[N], double (&q)[N], bool &rare) {
 #pragma unroll
   for (int k = 0; k < N; k++) {
     const unsigned eb = (unsigned)(__double2hiint(b[k]) & 0x7ff00000) - (523u << 20);
@@ -333,29 +337,26 @@ __device__ __forceinline__ void div_pos_n(const double (&a)[N], const double (&b
     const double q0 = a[k] * y;
     const double r = fma(-q0, b[k], a[k]);
     q[k] = fma(r, y, q0);
-    rare |= (eb | ea) >= (1000u << 20) || !(b[k] > 0.0) || div_suspect(a[k], b[k], q[k]);
-  }
-  if (__builtin_expect(rare, 0)) {
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = div_slow(a[k], b[k]);
+    rare = rare | ((eb | ea) >= (1000u << 20)) | !(b[k] > 0.0) | div_suspect(a[k], b[k], q[k]);
   }
 }
 
+// e[k] = exp(-na[k]): callers hold the positive quantity v^2/(2T/m); taking it un-negated keeps the negation inside the
+// FMA operand modifiers
 template <int M>
-__device__ __forceinline__ void exp_fast_n(const double (&a)[M], double (&e)[M]) {
+__device__ __forceinline__ void exp_fast_neg_n(const double (&na)[M], double (&e)[M], bool &rare) {
   const double magic = 6755399441055744.0;
   double r[M], q[M];
   int n[M];
-  bool rare = false;
 #pragma unroll
   for (int k = 0; k < M; k++) {
-    const double t = fma(a[k], c_exp_red[0], magic);
+    const double t = fma(-na[k], c_exp_red[0], magic);
     n[k] = __double2loint(t);
     const double f = t - magic;
-    r[k] = fma(f, -c_exp_red[1], a[k]);
+    r[k] = fma(f, -c_exp_red[1], -na[k]);
     r[k] = fma(f, -c_exp_red[2], r[k]);
     q[k] = c_exp_poly[0];
-    rare |= !(fabs(a[k]) <= 700.0);
+    rare = rare | !(fabs(na[k]) <= 700.0);
   }
 #pragma unroll
   for (int j = 1; j < 10; j++) {
@@ -367,36 +368,24 @@ __device__ __forceinline__ void exp_fast_n(const double (&a)[M], double (&e)[M])
     const double pr = fma(r[k] * r[k], q[k], r[k]) + 1.0;
     e[k] = __hiloint2double(__double2hiint(pr) + (n[k] << 20), __double2loint(pr));
   }
-  if (__builtin_expect(rare, 0)) {  // never reached by physical velocities
-#pragma unroll
-    for (int k = 0; k < M; k++) e[k] = exp_slow(a[k]);
-  }
 }
 
 template <int N>
-__device__ __forceinline__ void wrap_n(double (&x)[N], double lx) {
-  bool rare = false;
-  double xw[N];
+__device__ __forceinline__ void wrap_n(double (&x)[N], double lx, bool &rare) {
 #pragma unroll
   for (int k = 0; k < N; k++) {
-    xw[k] = (x[k] >= lx) ? dsub(x[k], lx) : x[k];
-    xw[k] = (x[k] < 0.0) ? dadd(x[k], lx) : xw[k];
-    rare |= !(x[k] > -lx && x[k] < dadd(lx, lx));
+    double xw = (x[k] >= lx) ? dsub(x[k], lx) : x[k];
+    xw = (x[k] < 0.0) ? dadd(x[k], lx) : xw;
+    rare = rare | !((x[k] > -lx) & (x[k] < dadd(lx, lx)));  // more than a box length away (or NaN): fmod
+    x[k] = xw;
   }
-  if (__builtin_expect(rare, 0)) {
-#pragma unroll
-    for (int k = 0; k < N; k++)
-      if (!(x[k] > -lx && x[k] < dadd(lx, lx))) xw[k] = wrap_slow(x[k], lx);
-  }
-#pragma unroll
-  for (int k = 0; k < N; k++) x[k] = xw[k];
 }
 
 template <int N>
 __device__ __forceinline__ void shape_n(const double (&x)[N], double lx, double rlx, double rnx, int nx, int right_frac,
-                                        Shape (&s)[N], bool (&oob)[N]) {
+                                        Shape (&s)[N], bool (&oob)[N], bool &rare) {
   double q[N];
-  div_const_n<N>(x, lx, rlx, q);
+  div_const_n<N>(x, lx, rlx, q, rare);
 #pragma unroll
   for (int k = 0; k < N; k++) {
     const double sx = dmul(q[k], rnx);
@@ -419,7 +408,7 @@ __device__ __forceinline__ void shape_n(const double (&x)[N], double lx, double 
 }
 
 template <int DIST, bool POW2, bool UNIT, int N>
-__device__ __forceinline__ void dlnf0_impl_n(const SpeciesConst &c, const double (&v)[N], double (&out)[N]) {
+__device__ __forceinline__ void dlnf0_impl_n(const SpeciesConst &c, const double (&v)[N], double (&out)[N], bool &rare) {
 #define DIVC(x, name) (UNIT && !DivIsTwo::name ? (x) : UNIT ? dmul((x), 0.5) : POW2 ? dmul((x), c.i_##name) : ddiv((x), c.name))
   if (DIST == 1) {
 #pragma unroll
@@ -429,17 +418,17 @@ __device__ __forceinline__ void dlnf0_impl_n(const SpeciesConst &c, const double
 #pragma unroll
     for (int k = 0; k < N; k++) {
       const double vp = dadd(v[k], c.v0), vm = dsub(v[k], c.v0);
-      arg[2 * k] = -DIVC(dmul(vp, vp), twoTm);
-      arg[2 * k + 1] = -DIVC(dmul(vm, vm), twoTm);
+      arg[2 * k] = DIVC(dmul(vp, vp), twoTm);
+      arg[2 * k + 1] = DIVC(dmul(vm, vm), twoTm);
     }
-    exp_fast_n<2 * N>(arg, e);
+    exp_fast_neg_n<2 * N>(arg, e, rare);
 #pragma unroll
     for (int k = 0; k < N; k++) {
       const double vp = dadd(v[k], c.v0), vm = dsub(v[k], c.v0);
       num[k] = dadd(dmul(vp, e[2 * k]), dmul(vm, e[2 * k + 1]));
       den[k] = dadd(e[2 * k], e[2 * k + 1]);
     }
-    div_pos_n<N>(num, den, r);
+    div_pos_n<N>(num, den, r, rare);
 #pragma unroll
     for (int k = 0; k < N; k++) {
       double t = r[k];
@@ -451,10 +440,10 @@ __device__ __forceinline__ void dlnf0_impl_n(const SpeciesConst &c, const double
 #pragma unroll
     for (int k = 0; k < N; k++) {
       const double vm = dsub(v[k], c.v0);
-      arg[2 * k] = -DIVC(dmul(v[k], v[k]), twoTm);
-      arg[2 * k + 1] = -DIVC(dmul(vm, vm), twoT2m);
+      arg[2 * k] = DIVC(dmul(v[k], v[k]), twoTm);
+      arg[2 * k + 1] = DIVC(dmul(vm, vm), twoT2m);
     }
-    exp_fast_n<2 * N>(arg, e);
+    exp_fast_neg_n<2 * N>(arg, e, rare);
 #pragma unroll
     for (int k = 0; k < N; k++) {
       const double vm = dsub(v[k], c.v0), e1 = e[2 * k], e2 = e[2 * k + 1];
@@ -463,7 +452,7 @@ __device__ __forceinline__ void dlnf0_impl_n(const SpeciesConst &c, const double
       num[k] = dadd(a, b);
       den[k] = dadd(DIVC(dmul(c.n, e1), sqTm), DIVC(dmul(c.omn, e2), sqT2m));
     }
-    div_pos_n<N>(num, den, out);
+    div_pos_n<N>(num, den, out, rare);
   } else {
 #pragma unroll
     for (int k = 0; k < N; k++) out[k] = DIVC(dsub(v[k], c.v0), Tm);
@@ -476,11 +465,11 @@ template <int DIST, int CFG, int N>
 __device__ __forceinline__ void push_n(const ParticleArgs &a, const double *sE, const double (&x)[N],
                                        const double (&v)[N], const double (&w)[N], const double (&p)[N],
                                        const double (&xb)[N], const double (&vb)[N], const double (&wb)[N],
-                                       double (&xo)[N], double (&vo)[N], double (&wo)[N]) {
+                                       double (&xo)[N], double (&vo)[N], double (&wo)[N], bool &rare) {
   typedef Cfg<CFG> F;
   Shape s[N];
   bool oob[N];
-  shape_n<N>(x, a.lx, a.rlx, a.rnx, a.nx, F::right_frac(a.right_frac), s, oob);
+  shape_n<N>(x, a.lx, a.rlx, a.rnx, a.nx, F::right_frac(a.right_frac), s, oob, rare);
   double electric[N];
 #pragma unroll
   for (int k = 0; k < N; k++) {
@@ -492,11 +481,11 @@ __device__ __forceinline__ void push_n(const ParticleArgs &a, const double *sE, 
   if (F::deltaf(a.deltaf)) {
     double tmp2[N];
     if (F::unit)
-      dlnf0_impl_n<DIST, true, true, N>(a.c, v, tmp2);
+      dlnf0_impl_n<DIST, true, true, N>(a.c, v, tmp2, rare);
     else if (F::pow2(a.c.pow2))
-      dlnf0_impl_n<DIST, true, false, N>(a.c, v, tmp2);
+      dlnf0_impl_n<DIST, true, false, N>(a.c, v, tmp2, rare);
     else
-      dlnf0_impl_n<DIST, false, false, N>(a.c, v, tmp2);
+      dlnf0_impl_n<DIST, false, false, N>(a.c, v, tmp2, rare);
 #pragma unroll
     for (int k = 0; k < N; k++) {
       const double tmp1 = F::linear(a.linear) ? dmul(p[k], electric[k]) : dmul(dsub(p[k], w[k]), electric[k]);  // :268-272
@@ -663,19 +652,56 @@ __device__ __forceinline__ void dep_flush(double *smem_after_E, int nx, double *
 // through 128-bit loads/stores.  IRK2 selects the second RK substep (reads midpoint + start-of-step state).
 // FUSED=false gives the reference's push-only side effects (x left unwrapped, no deposit).
 // ------------------------------------------------------------------------------------------------------------
-// one tile step of one thread: markers i, i+1.  FULL: the whole CTA tile is inside [0, np) (no tail checks).
-template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG, bool FULL>
-__device__ __forceinline__ void push_pair_body(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep,
+// One tile step of one thread (markers i, i+1) comes in two forms.  push_pair_fast: both markers valid, 2-wide
+// interleaved code without any rare path; when one of its operations raises the `rare` flag nothing is stored or
+// deposited and the caller redoes the pair with push_pair_slow.  push_pair_slow: scalar code with the IEEE fallbacks,
+// per-marker validity (tail of the arrays, or `ok` = this thread's pair needs the redo); loads its own inputs.
+template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
+__device__ __forceinline__ bool push_pair_fast(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep,
                                                const int64_t i, unsigned long long &noob, double2 x, double2 v, double2 w,
-                                               double2 p, double2 xb, double2 vb, double2 wb);
-
-template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG, bool FULL>
-__device__ __forceinline__ void push_pair(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep, const int64_t i,
-                                          unsigned long long &noob) {
+                                               double2 p, double2 xb, double2 vb, double2 wb) {
   typedef Cfg<CFG> F;
-  const bool deltaf = F::deltaf(a.deltaf);
+  const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
+  if (!IRK2) {  // xb, vb, wb are ignored at irk == 1
+    xb = x;
+    vb = v;
+    wb = w;
+  } else if (!deltaf) {
+    wb = w;
+  }
+  bool rare = false;
+  Shape sd[2];
+  bool od[2] = {false, false};
+  const double ax[2] = {x.x, x.y}, av[2] = {v.x, v.y}, aw[2] = {w.x, w.y}, ap[2] = {p.x, p.y};
+  const double axb[2] = {xb.x, xb.y}, avb[2] = {vb.x, vb.y}, awb[2] = {wb.x, wb.y};
+  double axo[2], avo[2], awo[2];
+  push_n<DIST, CFG, 2>(a, sE, ax, av, aw, ap, axb, avb, awb, axo, avo, awo, rare);
+  if (FUSED) {
+    wrap_n<2>(axo, a.lx, rare);
+    shape_n<2>(axo, a.lx, a.rlx, a.rnx, a.nx, right_frac, sd, od, rare);
+  }
+  if (!rare) {
+    st2(a.x_out + i, make_double2(axo[0], axo[1]));
+    if (!linear) st2(a.v_out + i, make_double2(avo[0], avo[1]));
+    if (deltaf) st2(a.w_out + i, make_double2(awo[0], awo[1]));
+  }
+  if (FUSED) {
+    // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
+    const double q0 = deltaf ? awo[0] : p.x, q1 = deltaf ? awo[1] : p.y;
+    dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0), !rare);  // :110, :113
+    dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
+    noob += (!rare && od[0]) + (!rare && od[1]);
+  }
+  return rare;
+}
+
+template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
+__device__ __forceinline__ void push_pair_slow(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep, const int64_t i,
+                                            unsigned long long &noob, const bool ok) {
+  typedef Cfg<CFG> F;
+  const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
   const bool need_p = deltaf || FUSED;  // full-f deposits p (src/pic1dp_interaction.F90:88-90)
-  const bool v0ok = FULL || i < a.np, v1ok = FULL || i + 1 < a.np;
+  const bool v0ok = ok && i < a.np, v1ok = ok && i + 1 < a.np;
   double2 x = {0.0, 0.0}, v = {0.0, 0.0}, w = {0.0, 0.0}, p = {0.0, 0.0};
   double2 xb = {0.0, 0.0}, vb = {0.0, 0.0}, wb = {0.0, 0.0};
   if (v1ok) {
@@ -699,17 +725,6 @@ __device__ __forceinline__ void push_pair(const ParticleArgs &a, const double *s
       if (deltaf) wb.x = ld1(a.w_bak + i);
     }
   }
-  push_pair_body<DIST, IRK2, DEP, FUSED, CFG, FULL>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
-}
-
-// the arithmetic, stores and deposit of one tile step, given the loaded markers (xb, vb, wb are ignored at irk == 1)
-template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG, bool FULL>
-__device__ __forceinline__ void push_pair_body(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep,
-                                               const int64_t i, unsigned long long &noob, double2 x, double2 v, double2 w,
-                                               double2 p, double2 xb, double2 vb, double2 wb) {
-  typedef Cfg<CFG> F;
-  const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
-  const bool v0ok = FULL || i < a.np, v1ok = FULL || i + 1 < a.np;
   if (!IRK2) {
     xb = x;
     vb = v;
@@ -720,27 +735,13 @@ __device__ __forceinline__ void push_pair_body(const ParticleArgs &a, const doub
   double2 xo = {0.0, 0.0}, vo = {0.0, 0.0}, wo = {0.0, 0.0};
   Shape sd[2];
   bool od[2] = {false, false};
-  if (FULL) {  // both markers valid: 2-wide interleaved code
-    const double ax[2] = {x.x, x.y}, av[2] = {v.x, v.y}, aw[2] = {w.x, w.y}, ap[2] = {p.x, p.y};
-    const double axb[2] = {xb.x, xb.y}, avb[2] = {vb.x, vb.y}, awb[2] = {wb.x, wb.y};
-    double axo[2], avo[2], awo[2];
-    push_n<DIST, CFG, 2>(a, sE, ax, av, aw, ap, axb, avb, awb, axo, avo, awo);
-    if (FUSED) {
-      wrap_n<2>(axo, a.lx);
-      shape_n<2>(axo, a.lx, a.rlx, a.rnx, a.nx, right_frac, sd, od);
-    }
-    xo = make_double2(axo[0], axo[1]);
-    vo = make_double2(avo[0], avo[1]);
-    wo = make_double2(awo[0], awo[1]);
-  } else {
-    if (v0ok) push_one<DIST, CFG>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
-    if (v1ok) push_one<DIST, CFG>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
-    if (FUSED) {
-      if (v0ok) xo.x = wrap_x(xo.x, a.lx);
-      if (v1ok) xo.y = wrap_x(xo.y, a.lx);
-      sd[0] = shape_of(xo.x, a.lx, a.rlx, a.rnx, a.nx, right_frac, od[0]);
-      sd[1] = shape_of(xo.y, a.lx, a.rlx, a.rnx, a.nx, right_frac, od[1]);
-    }
+  if (v0ok) push_one<DIST, CFG>(a, sE, x.x, v.x, w.x, p.x, xb.x, vb.x, wb.x, xo.x, vo.x, wo.x);
+  if (v1ok) push_one<DIST, CFG>(a, sE, x.y, v.y, w.y, p.y, xb.y, vb.y, wb.y, xo.y, vo.y, wo.y);
+  if (FUSED) {
+    if (v0ok) xo.x = wrap_x(xo.x, a.lx);
+    if (v1ok) xo.y = wrap_x(xo.y, a.lx);
+    sd[0] = shape_of(xo.x, a.lx, a.rlx, a.rnx, a.nx, right_frac, od[0]);
+    sd[1] = shape_of(xo.y, a.lx, a.rlx, a.rnx, a.nx, right_frac, od[1]);
   }
   if (v1ok) {
     st2(a.x_out + i, xo);
@@ -752,12 +753,37 @@ __device__ __forceinline__ void push_pair_body(const ParticleArgs &a, const doub
     if (deltaf) st1(a.w_out + i, wo.x);
   }
   if (FUSED) {
-    // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
     const double q0 = deltaf ? wo.x : p.x, q1 = deltaf ? wo.y : p.y;
     dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0), v0ok);  // :110, :113
     dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), v1ok);
     noob += (v0ok && od[0]) + (v1ok && od[1]);
   }
+}
+
+// direct 128-bit loads of a full tile step's markers
+template <bool IRK2, bool FUSED, int CFG>
+__device__ __forceinline__ void load_pair(const ParticleArgs &a, const int64_t i, double2 &x, double2 &v, double2 &w,
+                                          double2 &p, double2 &xb, double2 &vb, double2 &wb) {
+  const bool deltaf = Cfg<CFG>::deltaf(a.deltaf);
+  x = ld2(a.x_cur + i);
+  v = ld2(a.v_cur + i);
+  w = p = xb = vb = wb = make_double2(0.0, 0.0);
+  if (deltaf) w = ld2(a.w_cur + i);
+  if (deltaf || FUSED) p = ld2(a.p + i);
+  if (IRK2) {
+    xb = ld2(a.x_bak + i);
+    vb = ld2(a.v_bak + i);
+    if (deltaf) wb = ld2(a.w_bak + i);
+  }
+}
+
+// the redo / tail step shared by all fused kernels: threads whose pair was flagged (or every thread of a partial tile)
+// run the scalar code; the warp-private depositor needs all 32 lanes present
+template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
+__device__ __forceinline__ void push_pair_redo(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep,
+                                               const int64_t i, unsigned long long &noob, const bool redo) {
+  const bool enter = (FUSED && DEP == DEP_WARP_PRIVATE) ? __any_sync(0xffffffffu, redo) : redo;
+  if (__builtin_expect(enter, 0)) push_pair_slow<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, redo);
 }
 
 template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
@@ -773,6 +799,14 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   const int64_t tile = (int64_t)blockDim.x * 2;
   unsigned long long noob = 0;
   const bool deltaf_pf = Cfg<CFG>::deltaf(a.deltaf);
+  // register-staged v of the next tile step: the fast body starts with the v-only work (both exponentials), so v is
+  // the one load whose latency nothing hides; it is issued one iteration ahead (4 registers)
+  constexpr bool PV = (PIC1DP_PV_MASK & ((DEP == DEP_WARP_PRIVATE ? 4 : 1) << (IRK2 ? 1 : 0))) != 0;
+  double2 v_next = make_double2(0.0, 0.0);
+  if (PV) {
+    const int64_t b0 = (int64_t)blockIdx.x * tile;
+    if (b0 + tile <= a.np) v_next = ld2(a.v_cur + b0 + (int64_t)threadIdx.x * 2);
+  }
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
     // L2 prefetch of this thread's markers of the next tile step: the loads then hit L2 instead of HBM.
@@ -792,10 +826,18 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
         }
       }
     }
-    if (base + tile <= a.np)
-      push_pair<DIST, IRK2, DEP, FUSED, CFG, true>(a, sE, dep, i, noob);
-    else
-      push_pair<DIST, IRK2, DEP, FUSED, CFG, false>(a, sE, dep, i, noob);
+    bool redo = true;  // partial tile: every thread takes the scalar path (validity per marker)
+    if (base + tile <= a.np) {
+      double2 x, v, w, p, xb, vb, wb;
+      load_pair<IRK2, FUSED, CFG>(a, i, x, v, w, p, xb, vb, wb);
+      if (PV) {
+        v = v_next;
+        const int64_t nb = base + (int64_t)gridDim.x * tile;
+        if (nb + tile <= a.np) v_next = ld2(a.v_cur + nb + (int64_t)threadIdx.x * 2);
+      }
+      redo = push_pair_fast<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
+    }
+    push_pair_redo<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, redo);
   }
   if (FUSED) dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
   if (FUSED && noob) atomicAdd(a.noob, noob);
@@ -853,6 +895,7 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push_cpa(const Particl
     const bool next_staged = next + tile <= a.np;
     if (next_staged) stage_in(next, st ^ 1);
     const int64_t i = base + (int64_t)threadIdx.x * 2;
+    bool redo = true;
     if (cur_staged) {
       if (next_staged)
         cpa::wait<1>();
@@ -867,10 +910,9 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push_cpa(const Particl
         vb = rs[5 * B];
         wb = rs[6 * B];
       }
-      push_pair_body<DIST, IRK2, DEP, true, CFG, true>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
-    } else {
-      push_pair<DIST, IRK2, DEP, true, CFG, false>(a, sE, dep, i, noob);
+      redo = push_pair_fast<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
     }
+    push_pair_redo<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, redo);
     cur_staged = next_staged;
   }
   dep_flush<DEP>(dep_base, a.nx, my_partial);
@@ -982,31 +1024,11 @@ __global__ void __launch_bounds__(1024, 1) k_push_tma(const ParticleArgs a) {
     }
     __syncwarp();
     if ((threadIdx.x & 31) == 0) tma::mbar_arrive(empty0 + 8 * st);
-    const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * TILE + (int64_t)threadIdx.x * 2;
-    const bool ok0 = i < a.np, ok1 = i + 1 < a.np;
-    // invalid lanes of the last tile compute on harmless dummies (v = 1 keeps two-stream1's 2/v finite)
-    const double ax[2] = {ok0 ? in.x.x : 0.0, ok1 ? in.x.y : 0.0}, av[2] = {ok0 ? in.v.x : 1.0, ok1 ? in.v.y : 1.0};
-    const double aw[2] = {ok0 ? in.w.x : 0.0, ok1 ? in.w.y : 0.0}, ap[2] = {ok0 ? in.p.x : 0.0, ok1 ? in.p.y : 0.0};
-    const double axb[2] = {ok0 ? in.xb.x : 0.0, ok1 ? in.xb.y : 0.0}, avb[2] = {ok0 ? in.vb.x : 1.0, ok1 ? in.vb.y : 1.0};
-    const double awb[2] = {ok0 ? in.wb.x : 0.0, ok1 ? in.wb.y : 0.0};
-    double axo[2], avo[2], awo[2];
-    push_n<DIST, CFG, 2>(a, sE, ax, av, aw, ap, axb, avb, awb, axo, avo, awo);
-    wrap_n<2>(axo, a.lx);
-    Shape sd[2];
-    bool od[2];
-    shape_n<2>(axo, a.lx, a.rlx, a.rnx, a.nx, right_frac, sd, od);
-    if (ok1) {
-      st2(a.x_out + i, make_double2(axo[0], axo[1]));
-      st2(a.v_out + i, make_double2(avo[0], avo[1]));
-      st2(a.w_out + i, make_double2(awo[0], awo[1]));
-    } else if (ok0) {
-      st1(a.x_out + i, axo[0]);
-      st1(a.v_out + i, avo[0]);
-      st1(a.w_out + i, awo[0]);
-    }
-    dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, awo[0]), dmul(sd[0].sr, awo[0]), ok0);
-    dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, awo[1]), dmul(sd[1].sr, awo[1]), ok1);
-    noob += (ok0 && od[0]) + (ok1 && od[1]);
+    const int64_t m0 = ((int64_t)blockIdx.x + k * gridDim.x) * TILE, i = m0 + (int64_t)threadIdx.x * 2;
+    bool redo = true;  // partial tile: scalar path with per-marker validity (reads global memory itself)
+    if (m0 + TILE <= a.np)
+      redo = push_pair_fast<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, in.x, in.v, in.w, in.p, in.xb, in.vb, in.wb);
+    push_pair_redo<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, redo);
   }
   dep_flush<DEP>(dep_base, a.nx, my_partial);
   if (noob) atomicAdd(a.noob, noob);

@@ -104,6 +104,10 @@ struct pic1dp_gpu {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t pev[7] = {};
+  // launch timing of the fused particle kernels inside step() / push() (pic1dp_gpu_launch_timing_*)
+  bool lt_on = false;
+  std::vector<cudaEvent_t> lt_ev;   // pairs (before, after)
+  std::vector<int> lt_irk;          // irk of each recorded pair
   Species sp[PIC1DP_MAX_SPECIES];
   double *d_E = nullptr, *d_rho = nullptr, *d_mre = nullptr, *d_mim = nullptr;
   double *d_Fre = nullptr, *d_Fim = nullptr, *d_ginv = nullptr;
@@ -406,6 +410,7 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t e : h->pev)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->lt_ev) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return PIC1DP_OK;
@@ -1013,6 +1018,17 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
     a.v_out = S.v[out];
     a.w_out = S.w[out];
     const int cfg = (h->cfg == 1) ? (S.c.unit ? 25 : S.c.pow2 ? 9 : 1) : -1;
+    const bool timed = h->lt_on && h->lt_irk.size() < 8192;
+    if (timed) {
+      if (h->lt_ev.size() < 2 * (h->lt_irk.size() + 1)) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        h->lt_ev.push_back(e0);
+        h->lt_ev.push_back(e1);
+      }
+      CK(cudaEventRecord(h->lt_ev[2 * h->lt_irk.size()], h->stream));
+    }
     if (fused && h->use_cpa[irk - 1] && cfg > 0) {
       PushKernel k = pick_cpa(p.iptcldist, h->dep, irk == 2, cfg);
       k<<<h->grid, h->threads, h->cpa_smem[irk - 1], h->stream>>>(a);
@@ -1024,9 +1040,37 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
       k<<<h->grid, h->threads, h->smem_push, h->stream>>>(a);
     }
     CKL(h);
+    if (timed) {
+      CK(cudaEventRecord(h->lt_ev[2 * h->lt_irk.size() + 1], h->stream));
+      h->lt_irk.push_back(irk);
+    }
     S.cur = out;
   }
   h->partial_valid = fused;
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_launch_timing_start(pic1dp_gpu_t *h) {
+  if (!h) return PIC1DP_EINVAL;
+  h->lt_irk.clear();
+  h->lt_on = true;
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_launch_timing_stop(pic1dp_gpu_t *h, double ms_sum[2], int64_t launches[2]) {
+  if (!h || !ms_sum || !launches) return PIC1DP_EINVAL;
+  CK(cudaSetDevice(h->p.device));
+  h->lt_on = false;
+  CK(cudaStreamSynchronize(h->stream));
+  ms_sum[0] = ms_sum[1] = 0.0;
+  launches[0] = launches[1] = 0;
+  for (size_t k = 0; k < h->lt_irk.size(); k++) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->lt_ev[2 * k], h->lt_ev[2 * k + 1]));
+    ms_sum[h->lt_irk[k] - 1] += (double)ms;
+    launches[h->lt_irk[k] - 1]++;
+  }
+  h->lt_irk.clear();
   return PIC1DP_OK;
 }
 

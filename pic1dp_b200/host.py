@@ -267,6 +267,16 @@ class Pic1dGpu:
         self._ck(self.L.pic1dp_gpu_get_counters(self._h, C.byref(c)), "get_counters")
         return c
 
+    def launch_timing_start(self):
+        self._ck(self.L.pic1dp_gpu_launch_timing_start(self._h), "launch_timing_start")
+
+    def launch_timing_stop(self):
+        """[(ms_sum, launches) for irk = 1, 2] of the fused particle kernels since launch_timing_start."""
+        ms = (C.c_double * 2)()
+        n = (C.c_int64 * 2)()
+        self._ck(self.L.pic1dp_gpu_launch_timing_stop(self._h, ms, n), "launch_timing_stop")
+        return [(ms[0], n[0]), (ms[1], n[1])]
+
     def profile_step(self):
         ms = (C.c_float * 6)()
         self._ck(self.L.pic1dp_gpu_profile_step(self._h, ms), "profile_step")
