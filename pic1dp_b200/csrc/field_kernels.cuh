@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128) k_finalize_rho(const GridArgs g) {
 
 // Single CTA, 1024 threads.  smem: rho[nx] + 2*nmode mode values.
 // SEQ=true : thread m walks j = 0..nx-1 in order (bit-identical to sequential-AIJ MatMultTranspose).
-// SEQ=false: warp per mode, lanes stride j, fixed shuffle tree (deterministic).
+// SEQ=false: one or more warps per mode, lanes stride j, fixed shuffle tree + warp-ordered sum (deterministic).
 // FINALIZE: also does k_finalize_rho's work first (one launch less per substep inside step()).
 template <bool SEQ, bool FINALIZE>
 __global__ void __launch_bounds__(1024) k_field_solve(const GridArgs g) {
@@ -207,12 +207,22 @@ __global__ void __launch_bounds__(1024) k_field_solve(const GridArgs g) {
       s_re[m] = dmul(dmul(sre, g.a_re), g.ginv[m]);  // :239, :243
     }
   } else {
+    // G warps share one mode (G = largest power of two <= warps / modes, 1 when there are more modes than warps): with
+    // the reference's single kept mode the whole CTA projects it instead of one warp walking all nx cells.  Lanes
+    // stride j, fixed shuffle tree per warp, then the G warp sums are added in warp order: a fixed summation tree.
+    __shared__ double s_part[32][2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int m = wid; m < M; m += nw) {
+    int G = 1;
+    while (2 * G * M <= nw) G *= 2;
+    const int per_pass = nw / G, grp = wid / G, sub = wid % G;
+    for (int mb = 0; mb < M; mb += per_pass) {
+      const int m = mb + grp;
       double sim = 0.0, sre = 0.0;
-      for (int j = lane; j < nx; j += 32) {
-        sim = dadd(sim, dmul(g.F_re[(size_t)j * M + m], s_rho[j]));
-        sre = dadd(sre, dmul(g.F_im[(size_t)j * M + m], s_rho[j]));
+      if (m < M && grp < per_pass) {
+        for (int j = sub * 32 + lane; j < nx; j += 32 * G) {
+          sim = dadd(sim, dmul(g.F_re[(size_t)j * M + m], s_rho[j]));
+          sre = dadd(sre, dmul(g.F_im[(size_t)j * M + m], s_rho[j]));
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -220,9 +230,19 @@ __global__ void __launch_bounds__(1024) k_field_solve(const GridArgs g) {
         sre = dadd(sre, __shfl_xor_sync(0xffffffffu, sre, o));
       }
       if (lane == 0) {
+        s_part[wid][0] = sim;
+        s_part[wid][1] = sre;
+      }
+      __syncthreads();
+      if (lane == 0 && sub == 0 && m < M && grp < per_pass) {
+        for (int q = 1; q < G; q++) {
+          sim = dadd(sim, s_part[wid + q][0]);
+          sre = dadd(sre, s_part[wid + q][1]);
+        }
         s_im[m] = dmul(dmul(sim, g.a_im), g.ginv[m]);
         s_re[m] = dmul(dmul(sre, g.a_re), g.ginv[m]);
       }
+      __syncthreads();
     }
   }
   __syncthreads();
