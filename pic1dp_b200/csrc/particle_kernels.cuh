@@ -19,7 +19,7 @@
 #endif
 // which fused-kernel variants issue L2 prefetches: bit 0/1 = atomic deposits irk 1/2, bit 2/3 = warp-private irk 1/2
 #ifndef PIC1DP_PF_MASK
-#define PIC1DP_PF_MASK 12
+#define PIC1DP_PF_MASK 13
 #endif
 // which fused-kernel variants stage the next tile step's v in registers (same bit layout as PIC1DP_PF_MASK).
 // Measured on B200 at 1e8 markers, nx = 1024: warp-private irk=1 1.264 -> 1.158 ms; atomic deposits +0.5 % slower.
@@ -810,8 +810,9 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
     // L2 prefetch of this thread's markers of the next tile step: the loads then hit L2 instead of HBM.
-    // Measured on B200 at 1e8 markers (profiles/r01_ab_experiments.md): helps where fewer warps are resident
-    // (warp-private deposit, irk=2: 1.60 -> 1.35 ms) and hurts with 32 resident warps, so it is enabled per variant.
+    // Measured on B200 at 1e8 markers (profiles/r01_ab_experiments.md), enabled per variant: it helps the warp-private
+    // deposit in both substeps and the atomic deposit at irk=1 (1.060 -> 1.040 ms: with the rare-path-free body the
+    // first use of the streamed v is the top stall) and hurts the HBM-bound atomic irk=2 kernel (1.24 -> 1.54 ms).
     if (PIC1DP_PF_MASK & ((DEP == DEP_WARP_PRIVATE ? 4 : 1) << (IRK2 ? 1 : 0))) {
       const int64_t inext = i + (int64_t)gridDim.x * tile;
       if (inext + 1 < a.np) {
