@@ -83,7 +83,10 @@ class ClockSampler:
     `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; a piped nvidia-smi block-buffers its output,
     which loses samples of a ~100 ms region)."""
 
-    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+    # nvmlClocksEventReason* bits (gpu_idle 0x1 is not a slowdown of a busy GPU and is left out of `reasons`)
+    REASONS = {"applications_clocks_setting": 0x2, "sw_power_cap": 0x4, "hw_slowdown": 0x8, "sync_boost": 0x10,
+               "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80,
+               "display_clock_setting": 0x100}
 
     def __init__(self, index: int):
         self.index = index
@@ -133,8 +136,12 @@ class ClockSampler:
             inside = sorted(self.rows, key=lambda r: abs(r[0] - mid))[:3]
             note = "no sample inside the %.0f ms timed region; nearest samples used" % (1e3 * (t1 - t0))
         reasons = sorted(k for k, bit in self.REASONS.items() if any(r[3] & bit for r in inside))
+        mask = 0
+        for r in inside:
+            mask |= int(r[3])
         out = {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": float(inside[0][2]),
-               "reasons": reasons, "samples": len(inside)}
+               "reasons": reasons, "samples": len(inside), "reason_mask": hex(mask),
+               "sm_mhz_min": float(min(r[1] for r in inside))}
         if note:
             out["note"] = note
         return out
