@@ -48,21 +48,6 @@ __constant__ double c_exp_red[3] = {0x1.71547652b82fep+0 /* log2 e */, 0x1.62e42
                                     0x1.abc9e3b39803fp-56 /* ln2 lo */};
 
 __device__ double exp_slow(double a);
-__device__ __forceinline__ double exp_fast(double a) {
-  const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
-  const double t = fma(a, c_exp_red[0], magic);
-  const int n = __double2loint(t);
-  const double nf = t - magic;
-  double r = fma(nf, -c_exp_red[1], a);
-  r = fma(nf, -c_exp_red[2], r);
-  double q = c_exp_poly[0];
-#pragma unroll
-  for (int k = 1; k < 10; k++) q = fma(q, r, c_exp_poly[k]);
-  const double r2 = r * r;
-  const double pr = fma(r2, q, r) + 1.0;  // in [0.70, 1.42]
-  if (__builtin_expect(!(fabs(a) <= 700.0), 0)) return exp_slow(a);  // never reached by physical velocities
-  return __hiloint2double(__double2hiint(pr) + (n << 20), __double2loint(pr));  // * 2^n, |n| <= 1010
-}
 
 // ---- correctly rounded division with a straight-line fast path ---------------------------------------------
 // q0 = a*y, r = a - q0*b (exact, FMA), q1 = q0 + r*y is RN(a/b + d) with |d| <= 2^-104 |a/b| when y is 1/b to
@@ -70,14 +55,9 @@ __device__ __forceinline__ double exp_fast(double a) {
 // residual r1 = a - q1*b detects that: RN(a/b) != q1 implies |r1| > b * ulp(q1) / 2; such operands (and anything
 // outside 2^+-500) are re-divided with the IEEE routine on a rare noinline path.  (Not covered: q1 an exact power
 // of two AND a/b within 2^-104 of the midpoint just below it, where the lower half-ulp is smaller.)
-// rare paths: IEEE division, libdevice exp, fmod
-// (measured: __noinline__ rare paths cost 7% on the irk=2 kernel -- ABI call sites constrain register allocation --
-// so they are inlined; __builtin_expect keeps them off the fall-through path)
-#ifdef PIC1DP_EXP_NOINLINE_RARE
-#define PIC1DP_RARE __noinline__
-#else
+// rare paths: IEEE division, libdevice exp, fmod.  They are reached only from the scalar functions (push_one, wrap_x,
+// shape_of), i.e. from push_pair_slow; the 2-wide hot loop only raises a flag.
 #define PIC1DP_RARE __forceinline__
-#endif
 __device__ PIC1DP_RARE double div_slow(double a, double b) { return __ddiv_rn(a, b); }
 __device__ PIC1DP_RARE double exp_slow(double a) { return exp(a); }
 __device__ PIC1DP_RARE double wrap_slow(double x, double lx) {
@@ -521,11 +501,6 @@ struct Depositor<DEP_SMEM_ATOMIC> {
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     (void)ixr;
     if (!valid) return;
-#ifdef PIC1DP_EXP_CAS64  // experiment: two 64-bit CAS loops on the same pair slot
-    atomicAdd(g + 2 * ix, a);
-    atomicAdd(g + 2 * ix + 1, b);
-    return;
-#endif
     double2 *slot = reinterpret_cast<double2 *>(g) + ix;
     const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
     double2 old = *slot;
@@ -590,25 +565,10 @@ struct Depositor<DEP_WARP_PRIVATE> {
 
 // Marker arrays are touched once per substep.  Measured on B200 (profiles/r01_ab_experiments.md): the default cache
 // policy beats the streaming hints (.cs evict-first loads/stores cost ~3% of the step; .cg is on par with default).
-#ifndef PIC1DP_EXP_MEMPOLICY
-#define PIC1DP_EXP_MEMPOLICY 0
-#endif
-#if PIC1DP_EXP_MEMPOLICY == 1  // experiment: streaming (evict-first) loads and stores
-__device__ __forceinline__ double2 ld2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
-__device__ __forceinline__ double ld1(const double *p) { return __ldcs(p); }
-__device__ __forceinline__ void st2(double *p, double2 v) { __stcs(reinterpret_cast<double2 *>(p), v); }
-__device__ __forceinline__ void st1(double *p, double v) { __stcs(p, v); }
-#elif PIC1DP_EXP_MEMPOLICY == 3  // experiment: L2-only (cg) loads and stores
-__device__ __forceinline__ double2 ld2(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
-__device__ __forceinline__ double ld1(const double *p) { return __ldcg(p); }
-__device__ __forceinline__ void st2(double *p, double2 v) { __stcg(reinterpret_cast<double2 *>(p), v); }
-__device__ __forceinline__ void st1(double *p, double v) { __stcg(p, v); }
-#else
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ double ld1(const double *p) { return *p; }
 __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
 __device__ __forceinline__ void st1(double *p, double v) { *p = v; }
-#endif
 // pull the line a later tile step will read into L2 (no destination register, no scoreboard wait)
 __device__ __forceinline__ void prefetch_l2(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
