@@ -120,6 +120,11 @@ interface
     type(c_ptr), value :: handle
     real(c_double), intent(out) :: electric(*), chargeden(*), mode_re(*), mode_im(*)
   end function
+  integer(c_int) function pic1dp_gpu_set_field(handle, electric, chargeden) bind(c, name = 'pic1dp_gpu_set_field')
+    import :: c_ptr, c_int
+    type(c_ptr), value :: handle
+    type(c_ptr), value :: electric, chargeden   ! const double*, either may be c_null_ptr
+  end function
   integer(c_int) function pic1dp_gpu_p2p_export(handle, ipc) bind(c, name = 'pic1dp_gpu_p2p_export')
     import :: c_ptr, c_int8_t, c_int
     type(c_ptr), value :: handle
@@ -190,7 +195,7 @@ public :: pic1dp_gpu_params_default, pic1dp_gpu_create, pic1dp_gpu_destroy
 public :: pic1dp_gpu_comm_unique_id, pic1dp_gpu_comm_init
 public :: pic1dp_gpu_set_markers, pic1dp_gpu_load_markers, pic1dp_gpu_get_markers, pic1dp_gpu_compute_shape_x
 public :: pic1dp_gpu_collect_charge, pic1dp_gpu_solve_field, pic1dp_gpu_push
-public :: pic1dp_gpu_get_field, pic1dp_gpu_sync
+public :: pic1dp_gpu_get_field, pic1dp_gpu_set_field, pic1dp_gpu_sync
 public :: pic1dp_gpu_p2p_export, pic1dp_gpu_p2p_import, pic1dp_gpu_output_field, pic1dp_gpu_output_ptcldist
 public :: pic1dp_gpu_compute_dist_pertb_abs_v, pic1dp_gpu_particle_merge, pic1dp_gpu_particle_remove
 public :: pic1dp_gpu_particle_split
@@ -412,6 +417,20 @@ if (im_high > im_low) then
   CHKERRQ(global_ierr)
 end if
 end subroutine gpu_field_refresh_host
+
+! field_test (src/pic1dp_field.F90:276-309): the reference fills field_chargeden on the host with VecSetValues; the
+! replicated device copy of rho takes the same values, then field_solve_electric runs on the device as usual
+subroutine gpu_field_test_set_chargeden
+implicit none
+#include "finclude/petsc.h90"
+real(c_double), target :: values(0 : input_nx - 1)
+PetscInt :: ix
+do ix = 0, input_nx - 1
+  values(ix) = cos(2.0_kpr * PETSC_PI * ix / real(input_nx, kpr))
+end do
+global_ierr = pic1dp_gpu_set_field(gpu_handle, c_null_ptr, c_loc(values))
+CHKERRQ(global_ierr)
+end subroutine gpu_field_test_set_chargeden
 
 ! scalar part of output_field (src/pic1dp_output.F90:117-172) from device-side reductions: realbuf(2:) of the
 ! reference = scalars(1:1+3*nspecies); no marker array crosses PCIe

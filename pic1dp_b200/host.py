@@ -407,6 +407,16 @@ class Pic1dpModules:
     def field_solve_electric(self):
         self._call(self.gpu.solve_field)
 
+    def field_test(self):
+        """field_test (src/pic1dp_field.F90:276-309): chargeden = cos(2 pi ix / nx), solve, return field_electric
+        (the reference prints it with VecView)."""
+        nx = self.input.nx
+        ix = np.arange(nx, dtype=np.float64)
+        values = np.cos(2.0 * 3.14159265358979323846264338327950288419716939937510582 * ix / float(nx))  # :290
+        self._call(self.gpu.set_field, None, values)
+        self.field_solve_electric()
+        return self.field_electric
+
     def field_final(self):
         self.particle_final()
 

@@ -76,6 +76,11 @@ def test_field_test_analytic():
         g.solve_field()
         E = g.get_field()["electric"]
     assert np.max(np.abs(E - np.sin(2.0 * np.pi * j / gp.nx) / 0.36)) < 1e-13
+    m = P.Pic1dpModules(gp)   # the same through the module mirror's field_test
+    m.field_init()
+    E2 = m.field_test()
+    m.field_final()
+    assert np.array_equal(E, E2)
 
 
 @pytest.mark.parametrize("shape", [4, 1])
