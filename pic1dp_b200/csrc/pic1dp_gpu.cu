@@ -15,6 +15,7 @@
 #include <math.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -125,6 +126,7 @@ struct pic1dp_gpu {
   int opt_nv = 0;
   double opt_vmax = 0.0;
   double *stage[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool stage_pinned[4] = {false, false, false, false};  // pageable fallback when the pinned allocation is refused
   size_t max_smem = 0;
   int grid = 0, threads = 512, smem_push = 0, smem_dep = 0, dep = 0, nsm = 0, cfg = -1;
   bool use_tma[2] = {false, false};  // per substep (irk = 1, 2)
@@ -398,8 +400,11 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
                     h->d_diag_part, h->d_diag_sums, h->d_hist, h->d_hist_out, h->d_dist_part};
   for (double *b : bufs)
     if (b) cudaFree(b);
-  for (double *b : h->stage)
-    if (b) cudaFreeHost(b);
+  for (int q = 0; q < 4; q++)
+    if (h->stage[q]) {
+      if (h->stage_pinned[q]) cudaFreeHost(h->stage[q]);
+      else free(h->stage[q]);
+    }
   if (h->d_noob) cudaFree(h->d_noob);
   for (int r = 0; r < 8; r++)
     if (h->peer_base[r] && h->peer_base[r] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
@@ -1411,8 +1416,18 @@ int pic1dp_gpu_compute_dist_pertb_abs_v(pic1dp_gpu_t *h, int32_t nv, double v_ma
 static int stage_species(pic1dp_gpu_t *h, int isp, const char *who) {
   if (h->opt_nv == 0) { h->err = std::string(who) + ": compute_dist_pertb_abs_v must be called first"; return PIC1DP_ESTATE; }
   CK(cudaSetDevice(h->p.device));
-  for (double *&b : h->stage)
-    if (!b) CK(cudaMallocHost(&b, (size_t)(h->p.capacity > 0 ? h->p.capacity : 1) * 8));
+  const size_t bytes = (size_t)(h->p.capacity > 0 ? h->p.capacity : 1) * 8;
+  for (int q = 0; q < 4; q++) {
+    if (h->stage[q]) continue;
+    if (cudaMallocHost(&h->stage[q], bytes) == cudaSuccess) {
+      h->stage_pinned[q] = true;
+    } else {  // 4 x capacity x 8 B of pinned memory can be refused on a large handle: pageable staging still works
+      cudaGetLastError();
+      h->stage[q] = static_cast<double *>(malloc(bytes));
+      h->stage_pinned[q] = false;
+      if (!h->stage[q]) { h->err = std::string(who) + ": host staging allocation failed"; return PIC1DP_ENOMEM; }
+    }
+  }
   return pic1dp_gpu_get_markers(h, isp, h->stage[0], h->stage[1], h->stage[2], h->stage[3], nullptr);
 }
 
