@@ -297,7 +297,7 @@ class Pic1dpModules:
     Usage replays src/pic1dp.F90:57-90::
 
         m = Pic1dpModules(params); m.particle_init(); m.field_init()
-        m.particle_set(0, x, v, p, w)             # stands in for particle_load (host-generated markers)
+        m.particle_set(0, x, v, p, w)             # host-generated markers; or m.particle_load(0, rand_v, rand_x, n)
         if m.input.iptclshape < 4: m.particle_compute_shape_x()
         m.interaction_collect_charge(); m.field_solve_electric()
         for m.global_irk in (1, 2):
@@ -332,6 +332,14 @@ class Pic1dpModules:
     def particle_set(self, isp: int, x, v, p, w):
         self.particle_np[isp] = x.size
         self._call(self.gpu.set_markers, isp, x, v, p, w)
+
+    def particle_load(self, isp: int, rand_v, rand_x, nparticle_init: int, v_max: float = 8.0, init_mode=(1,),
+                      init_cos=(0.0,), init_sin=(1e-5,)):
+        """particle_load (src/pic1dp_particle.F90:145-269) for uniform-v markers: the host draws the two uniform streams
+        in the reference's order (multirand_real_array(pv) :180, then (px) :222); the loader arithmetic runs on the
+        device.  particle_np = number of streamed values (the unloaded tail, :240-248, is simply not passed)."""
+        self.particle_np[isp] = rand_v.size
+        self._call(self.gpu.load_markers, isp, rand_v, rand_x, nparticle_init, v_max, init_mode, init_cos, init_sin)
 
     def particle_get(self, isp: int):
         return self._call(self.gpu.get_markers, isp)

@@ -493,6 +493,13 @@ def test_device_side_particle_load_matches_oracle_loader(dist, linear):
     assert np.array_equal(out["x"], x) and np.array_equal(out["v"], v)
     assert rel_err(out["p"], p) < 1e-14
     assert rel_err(out["w"], w) < 1e-13
+    if dist == 3 and linear == 0:  # the same through the module mirror's particle_load
+        m = P.Pic1dpModules(gp)
+        m.particle_init()
+        m.particle_load(0, rand_v, rand_x, ntot, 8.0, (1, 3), (2e-6, 0.0), (1e-5, 3e-6))
+        out2 = m.particle_get(0)
+        m.particle_final()
+        assert m.particle_np[0] == n and all(np.array_equal(out[k], out2[k]) for k in ("x", "v", "p", "w"))
 
 
 def test_randomized_configurations_two_steps():
