@@ -64,6 +64,64 @@ def test_two_rank_sharding_and_allreduce_gloo():
     assert err < 1e-12
 
 
+def _opt_worker(rank, world, port, q):
+    """Marker optimisation across ranks (src/pic1dp_particle.F90:356-522): per-rank |w| histogram, all-reduce, then the
+    product's host half of particle_merge on this rank's block against the oracle's."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes as C
+        import pic1dp_b200 as P
+        from helpers import make_params, synth_markers
+        from oracle import oracle as O
+        from pic1dp_b200 import _capi
+        op, _ = make_params(nx=64)
+        n = 60001
+        st = synth_markers(op, n, seed=5, spread=0.2)
+        st["w"] = st["w"] * (1.0 + 50.0 * np.exp(-(st["v"] - 3.2) ** 2)) * np.sign(np.sin(7.0 * st["x"]) + 0.3)
+        lo, hi = P.petsc_decide(n, world, rank)
+        mine = {k: a[lo:hi].copy() for k, a in st.items()}
+        orc = O.Oracle(op)
+        local = torch.from_numpy(orc.dist_pertb_abs_v([mine["v"]], [mine["w"]], 128, 8.0))
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)                 # MPI_Allreduce :392-395
+        dist_v = local.numpy().copy()
+        ref = {k: a.copy() for k, a in mine.items()}
+        n_ref = orc.particle_merge(ref, hi - lo, dist_v, 0.3, 8.0)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        n_got = _capi.load().pic1dp_host_particle_merge(hi - lo, dp(mine["x"]), dp(mine["v"]), dp(mine["p"]), dp(mine["w"]),
+                                                        dp(dist_v), 128, 8.0, 0.3, op.nx, op.lx)
+        same = n_got == n_ref and all(np.array_equal(mine[k][:n_ref], ref[k][:n_ref]) for k in ("x", "v", "p", "w"))
+        res = [None] * world
+        dist.all_gather_object(res, (bool(same), int(n_ref), hi - lo, dist_v))
+        if rank == 0:
+            blocks = [P.petsc_decide(n, world, r) for r in range(world)]
+            whole = orc.dist_pertb_abs_v([st["v"][a:b].copy() for a, b in blocks], [st["w"][a:b].copy() for a, b in blocks],
+                                         128, 8.0)
+            err = float(np.max(np.abs(res[0][3] - whole)) / np.max(whole))
+            q.put(("ok", err, [r[:3] for r in res], bool(np.array_equal(res[0][3], res[1][3]))))
+    except Exception as e:  # pragma: no cover
+        q.put(("fail", repr(e), [], False))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_marker_optimisation_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_opt_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    status, err, per_rank, identical = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+    assert status == "ok", err
+    assert err < 1e-13 and identical            # the all-reduced histogram is the emulated-rank one, same on both ranks
+    assert all(ok and n_after < n_before for ok, n_after, n_before in per_rank)
+
+
 def test_bench_reference_arm_runs_on_cpu():
     """`bench.py --impl reference` is the CPU arm: must work without a GPU and print one JSON line."""
     import json
