@@ -131,3 +131,52 @@ def test_split_shares_the_parent_weight():
     assert abs(a["p"][:n2].sum() - before["p"].sum()) < 1e-12 * abs(before["p"]).sum()
     assert abs(a["w"][:n2].sum() - before["w"].sum()) < 1e-12 * abs(before["w"]).sum()
     assert abs((a["v"][:n2] * a["p"][:n2]).sum() - (before["v"] * before["p"]).sum()) < 1e-9  # +dv and -dv cancel
+
+
+def test_randomized_merge_remove_split_sequences_match_oracle():
+    """40 pseudo-random (size, grid, threshold, mode) draws, each applying merge -> remove -> split in sequence to the
+    same arrays on both sides with one shared RNG stream position: marker counts and arrays stay bit-identical."""
+    rs = np.random.default_rng(12345)
+    L = _capi.load()
+    for trial in range(40):
+        n = int(rs.choice([0, 1, 2, 7, 300, 5000, 20000]))
+        nx = int(rs.choice([2, 5, 64, 192]))
+        nv = int(rs.choice([2, 16, 128]))
+        cap = n + int(rs.choice([0, 3, 9, 4 * n + 50]))
+        thm, ths = float(rs.choice([0.0, 0.05, 0.5, 2.0])), float(rs.choice([0.0, 0.2, 0.9, 1.5]))
+        typeremove, frac = int(rs.choice([1, 2])), float(rs.choice([0.1, 0.5, 0.9]))
+        ngroup = int(rs.choice([1, 2, 5]))
+        op, a = _markers(n, 100 + trial, nx=nx, cap=max(cap, 1))
+        b = {k: v.copy() for k, v in a.items()}
+        orc = O.Oracle(op)
+        r1, r2 = O.MultiRand(), O.MultiRand()
+        r1.init_const(1 + trial % 3, trial, 2)
+        r2.init_const(1 + trial % 3, trial, 2)
+        na = nb = n
+        cb_r = _capi.REAL64_FN(lambda _ctx: r2.real64())
+
+        def fill(_ctx, arr, k):
+            g = r2.gaussian_array(k)
+            for i in range(k):
+                arr[i] = g[i]
+        cb_g = _capi.GAUSSIAN_ARRAY_FN(fill)
+        for stage in ("merge", "remove", "split"):
+            dist = orc.dist_pertb_abs_v([a["v"][:na].copy()], [a["w"][:na].copy()], nv, VMAX) if na else np.ones(nv)
+            if not dist.max() > 0:
+                dist = np.ones(nv)
+            if stage == "merge":
+                na = orc.particle_merge(a, na, dist, thm, VMAX)
+                nb = L.pic1dp_host_particle_merge(nb, _dp(b["x"]), _dp(b["v"]), _dp(b["p"]), _dp(b["w"]), _dp(dist), nv, VMAX,
+                                                  thm, nx, op.lx)
+            elif stage == "remove":
+                na = orc.particle_remove(a, na, dist, thm, typeremove, frac, r1, VMAX)
+                nb = L.pic1dp_host_particle_remove(nb, _dp(b["x"]), _dp(b["v"]), _dp(b["p"]), _dp(b["w"]), _dp(dist), nv, VMAX,
+                                                   thm, typeremove, frac, cb_r, None)
+            else:
+                na = orc.particle_split(a, na, dist, ths, ngroup, 0.1, r1, VMAX)
+                nb = L.pic1dp_host_particle_split(nb, a["x"].size, _dp(b["x"]), _dp(b["v"]), _dp(b["p"]), _dp(b["w"]),
+                                                  _dp(dist), nv, VMAX, ths, ngroup, 0.1, 1, cb_g, None)
+            assert na == nb, (trial, stage)
+            for k in ("x", "v", "p", "w"):
+                assert np.array_equal(a[k][:na], b[k][:na], equal_nan=True), (trial, stage, k)
+        assert r1.int64() == r2.int64(), trial
