@@ -180,6 +180,17 @@ int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t np
                             const double *init_mode_cos, const double *init_mode_sin);
 
 /*
+ * load_markers_maxwellian: the same for input_imarker = 1 (src/pic1dp_particle.F90:172-178, iptcldist = 0 only, as
+ * input_init enforces, src/pic1dp_input.F90:291-299): gauss_v is the multirand_gaussian_array(pv) stream (:174), the
+ * device forms v = gauss_v * sqrt(T/m) + v0 (:175-176) and p = n * lx / nparticle_init (:177-178); x, w and the
+ * nonlinear p = p + w as in load_markers.
+ */
+int pic1dp_gpu_load_markers_maxwellian(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init,
+                                       const double *gauss_v, const double *rand_x, int32_t init_nmode,
+                                       const int32_t *init_mode, const double *init_mode_cos,
+                                       const double *init_mode_sin);
+
+/*
  * get_markers: D2H refresh of the host Vecs before pic1dp_output reads them (src/pic1dp_output.F90:128-150,
  * :228-237) or before particle_optimize.  Any of x,v,p,w may be NULL.  *np receives particle_np.
  */

@@ -76,7 +76,7 @@ EXPORTS = [
     "pic1dp_gpu_params_default", "pic1dp_gpu_abi_version", "pic1dp_gpu_strerror", "pic1dp_gpu_last_error",
     "pic1dp_gpu_create", "pic1dp_gpu_destroy", "pic1dp_gpu_comm_unique_id", "pic1dp_gpu_comm_init",
     "pic1dp_gpu_p2p_export", "pic1dp_gpu_p2p_import",
-    "pic1dp_gpu_set_markers", "pic1dp_gpu_load_markers", "pic1dp_gpu_get_markers", "pic1dp_gpu_compute_shape_x", "pic1dp_gpu_get_shape_x",
+    "pic1dp_gpu_set_markers", "pic1dp_gpu_load_markers", "pic1dp_gpu_load_markers_maxwellian", "pic1dp_gpu_get_markers", "pic1dp_gpu_compute_shape_x", "pic1dp_gpu_get_shape_x",
     "pic1dp_gpu_collect_charge", "pic1dp_gpu_solve_field", "pic1dp_gpu_push", "pic1dp_gpu_step",
     "pic1dp_gpu_get_field", "pic1dp_gpu_set_field", "pic1dp_gpu_get_operators", "pic1dp_gpu_field_energy",
     "pic1dp_gpu_output_field", "pic1dp_gpu_output_ptcldist",
@@ -126,6 +126,7 @@ def load() -> C.CDLL:
     L.pic1dp_gpu_p2p_import.argtypes = [vp, u8p]
     L.pic1dp_gpu_set_markers.argtypes = [vp, i32, i64, dp, dp, dp, dp]
     L.pic1dp_gpu_load_markers.argtypes = [vp, i32, i64, i64, dp, dp, C.c_double, i32, C.POINTER(i32), dp, dp]
+    L.pic1dp_gpu_load_markers_maxwellian.argtypes = [vp, i32, i64, i64, dp, dp, i32, C.POINTER(i32), dp, dp]
     L.pic1dp_gpu_get_markers.argtypes = [vp, i32, dp, dp, dp, dp, C.POINTER(i64)]
     L.pic1dp_gpu_compute_shape_x.argtypes = [vp]
     L.pic1dp_gpu_get_shape_x.argtypes = [vp, i32, C.POINTER(i32), dp, dp]

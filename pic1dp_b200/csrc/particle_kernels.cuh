@@ -1048,6 +1048,7 @@ struct LoadArgs {
   SpeciesConst c;
   double T2;              // temperature2 (SpeciesConst keeps only T2/m)
   int dist, linear, init_nmode;
+  int imarker;            // 2: uniform v in [-v_max, v_max] (v holds uniforms); 1: physical Maxwellian (v holds Gaussians)
   int init_mode[8];
   double init_cos[8], init_sin[8];
 };
@@ -1055,11 +1056,16 @@ struct LoadArgs {
 __global__ void __launch_bounds__(256) k_load_markers(const LoadArgs a) {
   const double PI = 3.14159265358979323846264338327950288419716939937510582;  // PETSC_PI
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.np; i += (int64_t)gridDim.x * blockDim.x) {
-    const double pv = dmul(dmul(dsub(a.v[i], 0.5), 2.0), a.v_max);  // :181
-    // lx * 2 * v_max / nparticle_init, left to right as written (:183-185, :198-200)
     const double n = a.c.n, v0 = a.c.v0, T = a.c.T, m = a.c.m, T2 = a.T2;
+    // input_imarker == 1 (:172-178): markers loaded like the physical (shifted) Maxwellian from the Gaussian stream,
+    // all with the same p; input_imarker == 2 (:179-219): uniform in velocity space
+    const double pv = (a.imarker == 1) ? dadd(dmul(a.v[i], __dsqrt_rn(ddiv(T, m))), v0)
+                                       : dmul(dmul(dsub(a.v[i], 0.5), 2.0), a.v_max);  // :181
+    // lx * 2 * v_max / nparticle_init, left to right as written (:183-185, :198-200)
     double pp;
-    if (a.dist == 1) {  // two-stream1 :183-186
+    if (a.imarker == 1) {  // :176-177
+      pp = ddiv(dmul(n, a.lx), a.ninit);
+    } else if (a.dist == 1) {  // two-stream1 :183-186
       const double pre = ddiv(dmul(dmul(dmul(n, a.lx), 2.0), a.v_max), a.ninit);
       pp = ddiv(dmul(dmul(pre, dmul(pv, pv)), exp(ddiv(-dmul(pv, pv), 2.0))), __dsqrt_rn(dmul(2.0, PI)));
     } else if (a.dist == 2) {  // two-stream2 :188-196

@@ -742,9 +742,9 @@ int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const doubl
   return upload_species(h, isp, np, x, v, p, w);
 }
 
-int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
-                            const double *rand_x, double v_max, int32_t init_nmode, const int32_t *init_mode,
-                            const double *init_mode_cos, const double *init_mode_sin) {
+static int load_markers_impl(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
+                             const double *rand_x, double v_max, int32_t init_nmode, const int32_t *init_mode,
+                             const double *init_mode_cos, const double *init_mode_sin, int imarker) {
   if (!h || isp < 0 || isp >= h->p.nspecies || np < 0 || nparticle_init < 1 || !rand_v || !rand_x || !(v_max > 0.0) ||
       init_nmode < 0 || init_nmode > 8 || (init_nmode > 0 && (!init_mode || !init_mode_cos || !init_mode_sin))) {
     if (h) h->err = "load_markers: bad argument (at most 8 initial modes)";
@@ -774,6 +774,7 @@ int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t np
   a.T2 = h->p.temperature2[isp];
   a.dist = h->p.iptcldist;
   a.linear = h->p.linear;
+  a.imarker = imarker;
   a.init_nmode = init_nmode;
   for (int i = 0; i < init_nmode; i++) {
     a.init_mode[i] = init_mode[i];
@@ -786,6 +787,25 @@ int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t np
   S.loaded = true;
   h->partial_valid = false;
   return PIC1DP_OK;
+}
+
+int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
+                            const double *rand_x, double v_max, int32_t init_nmode, const int32_t *init_mode,
+                            const double *init_mode_cos, const double *init_mode_sin) {
+  return load_markers_impl(h, isp, np, nparticle_init, rand_v, rand_x, v_max, init_nmode, init_mode, init_mode_cos,
+                           init_mode_sin, 2);
+}
+
+int pic1dp_gpu_load_markers_maxwellian(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init,
+                                       const double *gauss_v, const double *rand_x, int32_t init_nmode,
+                                       const int32_t *init_mode, const double *init_mode_cos,
+                                       const double *init_mode_sin) {
+  if (h && h->p.iptcldist != 0) {  // input_init: "case of input_iptcldist >= 1 and input_imarker = 1 not implemented yet"
+    h->err = "load_markers_maxwellian: input_imarker = 1 supports only iptcldist = 0 (src/pic1dp_input.F90:291-299)";
+    return PIC1DP_EINVAL;
+  }
+  return load_markers_impl(h, isp, np, nparticle_init, gauss_v, rand_x, 1.0, init_nmode, init_mode, init_mode_cos,
+                           init_mode_sin, 1);
 }
 
 int pic1dp_gpu_get_markers(pic1dp_gpu_t *h, int32_t isp, double *x, double *v, double *p, double *w, int64_t *np) {

@@ -132,6 +132,16 @@ class Pic1dGpu:
         self._ck(self.L.pic1dp_gpu_load_markers(self._h, isp, n, int(nparticle_init), pv, px, float(v_max), nm, im, ic, isn),
                  "load_markers")
 
+    def load_markers_maxwellian(self, isp: int, gauss_v, rand_x, nparticle_init: int, init_mode=(1,), init_cos=(0.0,),
+                                init_sin=(1e-5,)):
+        """Device-side particle_load for input_imarker = 1 (Gaussian v stream, iptcldist = 0)."""
+        nm = len(init_mode)
+        im = (C.c_int32 * nm)(*init_mode)
+        ic = (C.c_double * nm)(*init_cos)
+        isn = (C.c_double * nm)(*init_sin)
+        self._ck(self.L.pic1dp_gpu_load_markers_maxwellian(self._h, isp, gauss_v.size, int(nparticle_init), _dp(gauss_v),
+                                                           _dp(rand_x), nm, im, ic, isn), "load_markers_maxwellian")
+
     def get_markers(self, isp: int, want=("x", "v", "p", "w")):
         n = C.c_int64()
         self._ck(self.L.pic1dp_gpu_get_markers(self._h, isp, None, None, None, None, C.byref(n)), "get_markers")

@@ -502,6 +502,33 @@ def test_device_side_particle_load_matches_oracle_loader(dist, linear):
         assert m.particle_np[0] == n and all(np.array_equal(out[k], out2[k]) for k in ("x", "v", "p", "w"))
 
 
+@pytest.mark.parametrize("linear", [0, 1])
+def test_device_side_particle_load_maxwellian_markers(linear):
+    """input_imarker = 1 (src/pic1dp_particle.F90:172-178): v from the Gaussian stream, constant p -- against the oracle's
+    loader; x, v bit-exact, p and w within a few ulp (device sin / cos vs glibc)."""
+    from oracle import oracle as O
+    n, ntot = 100003, 400012
+    op, gp = make_params(nx=192, iptcldist=0, linear=linear, capacity=n, temperature=[1.3], mass=[1.1], density=[0.85],
+                         v0=[2.5], imarker=1, init_nmode=2, init_mode=[1, 3], init_mode_cos=[2e-6, 0.0],
+                         init_mode_sin=[1e-5, 3e-6])
+    x, v, p, w = O.Oracle(op).particle_load(0, 3, 1, 5, n, ntot)
+    rng = O.MultiRand()
+    rng.init_const(3, 1, 5)
+    gauss_v = rng.gaussian_array(n)   # multirand_gaussian_array(pv) :174, then the uniform x stream :222
+    rand_x = rng.real_array(n)
+    with _gpu(gp) as g:
+        g.load_markers_maxwellian(0, gauss_v, rand_x, ntot, init_mode=(1, 3), init_cos=(2e-6, 0.0), init_sin=(1e-5, 3e-6))
+        out = g.get_markers(0)
+    assert np.array_equal(out["x"], x) and np.array_equal(out["v"], v)
+    assert rel_err(out["p"], p) < 1e-14 and rel_err(out["w"], w) < 1e-13
+    assert abs(np.mean(v) - 2.5) < 0.02 and abs(np.std(v) / np.sqrt(1.3 / 1.1) - 1.0) < 0.01
+    _, gp3 = make_params(nx=192, iptcldist=3, capacity=n)   # input_init rejects imarker = 1 with iptcldist >= 1
+    with _gpu(gp3) as g:
+        with pytest.raises(P.Pic1dpError) as e:
+            g.load_markers_maxwellian(0, gauss_v, rand_x, ntot)
+        assert e.value.code == 1
+
+
 def test_randomized_configurations_two_steps():
     """24 pseudo-random parameter sets (fixed seed): equilibrium, delta-f / full-f, linear, weight rounding, deposit
     mode, fuse, species constants, grid size, mode set, ragged marker counts -- two full steps against the oracle."""
