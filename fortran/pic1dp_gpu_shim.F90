@@ -90,6 +90,15 @@ interface
     real(c_double), value :: v_max
     integer(c_int32_t), intent(in) :: init_mode(*)
   end function
+  integer(c_int) function pic1dp_gpu_load_markers_maxwellian(handle, isp, np, nparticle_init, gauss_v, rand_x, &
+      init_nmode, init_mode, init_mode_cos, init_mode_sin) bind(c, name = 'pic1dp_gpu_load_markers_maxwellian')
+    import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: isp, init_nmode
+    integer(c_int64_t), value :: np, nparticle_init
+    real(c_double), intent(in) :: gauss_v(*), rand_x(*), init_mode_cos(*), init_mode_sin(*)
+    integer(c_int32_t), intent(in) :: init_mode(*)
+  end function
   integer(c_int) function pic1dp_gpu_get_markers(handle, isp, x, v, p, w, np) bind(c, name = 'pic1dp_gpu_get_markers')
     import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
     type(c_ptr), value :: handle
@@ -193,7 +202,8 @@ type(c_ptr), save, public :: gpu_handle = c_null_ptr
 
 public :: pic1dp_gpu_params_default, pic1dp_gpu_create, pic1dp_gpu_destroy
 public :: pic1dp_gpu_comm_unique_id, pic1dp_gpu_comm_init
-public :: pic1dp_gpu_set_markers, pic1dp_gpu_load_markers, pic1dp_gpu_get_markers, pic1dp_gpu_compute_shape_x
+public :: pic1dp_gpu_set_markers, pic1dp_gpu_load_markers, pic1dp_gpu_load_markers_maxwellian
+public :: pic1dp_gpu_get_markers, pic1dp_gpu_compute_shape_x
 public :: pic1dp_gpu_collect_charge, pic1dp_gpu_solve_field, pic1dp_gpu_push
 public :: pic1dp_gpu_get_field, pic1dp_gpu_set_field, pic1dp_gpu_sync
 public :: pic1dp_gpu_p2p_export, pic1dp_gpu_p2p_import, pic1dp_gpu_output_field, pic1dp_gpu_output_ptcldist
