@@ -148,6 +148,7 @@ static bool parse(Input &in, int argc, char **argv) {
     else if (k == "split_ngroup") in.input_split_ngroup = (int)d;
     else if (k == "split_dv_sig_frac") in.input_split_dv_sig_frac = d;
     else if (k == "markers_out") in.markers_out = v;
+    else if (k == "imarker") in.input_imarker = (int)d;
     else return false;
   }
   return true;
@@ -419,16 +420,24 @@ static void particle_load(Rank &r) {
   const int64_t n = r.particle_ip_high - r.particle_ip_low;
   r.v.resize(n);
   r.x.resize(n);
-  rng.real_array(r.v.data(), n);  // :180  (the whole local array is drawn, used or not)
+  if (in.input_imarker == 1)
+    rng.gaussian_array(r.v.data(), n);  // :174  markers loaded like the physical Maxwellian
+  else
+    rng.real_array(r.v.data(), n);  // :180  (the whole local array is drawn, used or not)
   rng.real_array(r.x.data(), n);  // :222
   // unload not used particles (:240-248): the tail of the local array stays free for particle_split
   const int64_t ninit = in.input_species_nparticle_init > 0 ? in.input_species_nparticle_init : in.input_nparticle_max;
   int64_t nparticle_unload = (in.input_nparticle_max - ninit) / r.g.global_npe;
   if (r.g.global_mype == 0) nparticle_unload += (in.input_nparticle_max - ninit) % r.g.global_npe;
   r.particle_np = n - nparticle_unload;
-  r.g.global_ierr = pic1dp_gpu_load_markers(r.h, 0, r.particle_np, ninit, r.v.data(), r.x.data(), in.input_v_max,
-                                            in.input_init_nmode, in.input_init_mode, in.input_init_mode_cos,
-                                            in.input_init_mode_sin);
+  if (in.input_imarker == 1)
+    r.g.global_ierr = pic1dp_gpu_load_markers_maxwellian(r.h, 0, r.particle_np, ninit, r.v.data(), r.x.data(),
+                                                         in.input_init_nmode, in.input_init_mode,
+                                                         in.input_init_mode_cos, in.input_init_mode_sin);
+  else
+    r.g.global_ierr = pic1dp_gpu_load_markers(r.h, 0, r.particle_np, ninit, r.v.data(), r.x.data(), in.input_v_max,
+                                              in.input_init_nmode, in.input_init_mode, in.input_init_mode_cos,
+                                              in.input_init_mode_sin);
   CHKERRQ(r.g, r.h);
   r.v.clear();
   r.x.clear();

@@ -166,3 +166,32 @@ def test_cpp_host_driver_writes_reference_output_file(tmp_path):
     f = od.get_ptcldist_xv(6, 0, 1)
     assert abs(np.sum(f) * (od.lx / 64) * (16.0 / 63) / od.lx - 1.0) < 0.03   # int f dx dv / lx = n0 = 1
     assert sc[2, 0] > 0 and abs(sc[3, 0] / (od.lx * 3.4) - 1.0) < 0.1          # sum v^2 p ~ lx * <v^2> = lx * (0.9 + 0.1*26)
+
+
+def test_cpp_host_driver_maxwellian_markers_match_oracle(tmp_path):
+    """host/pic1dp_host imarker=1 iptcldist=0: Gaussian marker velocities from the product-side multirand (Marsaglia polar
+    method, src/multirand.F90:838-872) and the device loader's Maxwellian branch, 3 steps, against the oracle."""
+    from pic1dp_b200 import build
+    from oracle import oracle as O
+    from helpers import OracleRun, make_params, rel_err
+    exe = build.build_host()
+    n, nx, nsteps = 200001, 128, 3
+    out, mk = tmp_path / "energy.txt", tmp_path / "markers.bin"
+    r = subprocess.run([exe, f"nparticle_max={n}", f"nx={nx}", f"ntime_max={nsteps}", "seed_type=1", "iptcldist=0", "imarker=1",
+                        "density=1.0", "v0=0.5", "temperature=1.2", f"out={out}", f"markers_out={mk}"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(mk, dtype=np.float64)
+    n_gpu = int(np.frombuffer(raw[:1].tobytes(), dtype=np.int64)[0])
+    got = dict(zip(("x", "v", "p", "w"), raw[1:].reshape(4, n_gpu)))
+    op, _ = make_params(nx=nx, iptcldist=0, imarker=1, density=[1.0], v0=[0.5], temperature=[1.2])
+    x, v, p, w = O.Oracle(op).particle_load(0, 3, 0, 5, n, n)
+    ref = OracleRun(op, [[dict(x=x, v=v, p=p, w=w)]])
+    ref.init_field()
+    for _ in range(nsteps):
+        ref.step()
+    assert n_gpu == n
+    for k in ("x", "v", "p", "w"):
+        assert rel_err(got[k], ref.st[0][0][k]) < 1e-11, k
+    rows = np.loadtxt(out)
+    assert np.allclose(rows[-1, 1], ref.o.field_energy(ref.E), rtol=1e-9)
