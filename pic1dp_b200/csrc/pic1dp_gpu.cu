@@ -712,6 +712,15 @@ int pic1dp_gpu_p2p_import(pic1dp_gpu_t *h, const uint8_t *all_handles) {
   return PIC1DP_OK;
 }
 
+// The markers changed behind a fused push: its deposit must not be collected.  The shared-memory deposits overwrite
+// their CTA grid at the next flush; the RED deposit accumulates into the L2 grids, which therefore have to be cleared.
+static int invalidate_partials(pic1dp_gpu_t *h) {
+  if (h->partial_valid && h->dep == DEP_GLOBAL_RED)
+    CK(cudaMemsetAsync(h->d_partial, 0, (size_t)h->p.nspecies * h->grid * h->p.nx * 8, h->stream));
+  h->partial_valid = false;
+  return PIC1DP_OK;
+}
+
 // H2D of one species into buffer set 0; the marker count becomes np
 static int upload_species(pic1dp_gpu_t *h, int isp, int64_t np, const double *x, const double *v, const double *p,
                           const double *w) {
@@ -728,8 +737,7 @@ static int upload_species(pic1dp_gpu_t *h, int isp, int64_t np, const double *x,
   CK(cudaStreamSynchronize(h->stream));  // host buffers are only borrowed for the call
   h->h2d += 4 * (int64_t)b;
   S.loaded = true;
-  h->partial_valid = false;
-  return PIC1DP_OK;
+  return invalidate_partials(h);
 }
 
 int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const double *x, const double *v,
@@ -785,8 +793,7 @@ static int load_markers_impl(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t n
   CKL(h);
   CK(cudaStreamSynchronize(h->stream));  // host buffers are only borrowed for the call
   S.loaded = true;
-  h->partial_valid = false;
-  return PIC1DP_OK;
+  return invalidate_partials(h);
 }
 
 int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,

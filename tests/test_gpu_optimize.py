@@ -101,7 +101,7 @@ def test_merge_remove_split_on_device_markers_match_oracle_bit_for_bit(fuse):
         assert g.get_markers(0)["x"].size == n3 and np.isfinite(g.field_energy())
 
 
-@pytest.mark.parametrize("fuse,dep", [(1, P.DEPOSIT_AUTO), (0, P.DEPOSIT_WARP_PRIVATE)])
+@pytest.mark.parametrize("fuse,dep", [(1, P.DEPOSIT_AUTO), (0, P.DEPOSIT_WARP_PRIVATE), (1, P.DEPOSIT_GLOBAL_RED)])
 def test_time_loop_with_optimisation_events_matches_oracle(fuse, dep):
     """src/pic1dp.F90:78-93 with particle_optimize between push and collect_charge at irk == 2: a merge at t = 0.1,
     a removal at t = 0.2 and a split at t = 0.3 (dt = 0.05), GPU modules vs the oracle's replay."""
