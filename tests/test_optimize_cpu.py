@@ -180,3 +180,57 @@ def test_randomized_merge_remove_split_sequences_match_oracle():
             for k in ("x", "v", "p", "w"):
                 assert np.array_equal(a[k][:na], b[k][:na], equal_nan=True), (trial, stage, k)
         assert r1.int64() == r2.int64(), trial
+
+
+def _golden():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "optimize_tiny.json")))
+
+
+def _unhex(a):
+    return np.array([float.fromhex(t) for t in a])
+
+
+@pytest.mark.parametrize("side", ["oracle", "product"])
+def test_committed_optimisation_fixture_is_reproduced(side):
+    """tests/golden/optimize_tiny.json (oracle-generated, tests/golden/make_golden.py): merge -> remove -> split on 400
+    loader markers; the oracle (regression) and the product's host halves (given the fixture's dist, no oracle
+    arithmetic) reproduce every stage bit for bit and leave the RNG stream at the same position."""
+    g = _golden()
+    nx, nv, vmax, cap, m = g["nx"], g["nv"], g["v_max"], g["capacity"], g["n0"]
+    op, _ = make_params(nx=nx)
+    st = {k: np.concatenate([_unhex(g["init"][k]), np.zeros(cap - m)]) for k in ("x", "v", "p", "w")}
+    rng = O.MultiRand()
+    rng.init_const(g["rng"]["al_int"], g["rng"]["mype"], g["rng"]["warmup"])
+    L = _capi.load()
+    cb_r = _capi.REAL64_FN(lambda _ctx: rng.real64())
+
+    def fill(_ctx, arr, k):
+        gz = rng.gaussian_array(k)
+        for i in range(k):
+            arr[i] = gz[i]
+    cb_g = _capi.GAUSSIAN_ARRAY_FN(fill)
+    orc = O.Oracle(op)
+    for rec in g["stages"]:
+        dist = _unhex(rec["dist"])
+        if side == "oracle":
+            assert np.array_equal(orc.dist_pertb_abs_v([st["v"][:m].copy()], [st["w"][:m].copy()], nv, vmax), dist)
+            if rec["stage"] == "merge":
+                m = orc.particle_merge(st, m, dist, 0.5, vmax)
+            elif rec["stage"] == "remove":
+                m = orc.particle_remove(st, m, dist, 0.0, 2, 0.9, rng, vmax)
+            else:
+                m = orc.particle_split(st, m, dist, 0.5, 2, 0.1, rng, vmax)
+        else:
+            a = [_dp(st[k]) for k in ("x", "v", "p", "w")]
+            if rec["stage"] == "merge":
+                m = L.pic1dp_host_particle_merge(m, *a, _dp(dist), nv, vmax, 0.5, nx, op.lx)
+            elif rec["stage"] == "remove":
+                m = L.pic1dp_host_particle_remove(m, *a, _dp(dist), nv, vmax, 0.0, 2, 0.9, cb_r, None)
+            else:
+                m = L.pic1dp_host_particle_split(m, cap, *a, _dp(dist), nv, vmax, 0.5, 2, 0.1, 1, cb_g, None)
+        assert m == rec["np"], rec["stage"]
+        for k in ("x", "v", "p", "w"):
+            assert np.array_equal(st[k][:m], _unhex(rec[k])), (rec["stage"], k)
+    assert rng.int64() == g["next_int64"]
