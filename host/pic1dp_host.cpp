@@ -671,7 +671,33 @@ static void run_rank(const pic1dp_input::Input *in, int mype, int npe, const uin
   if (fb) fclose(fb);
 }
 
+// `pic1dp_host multirand_selftest`: prints the head of every engine after the default seeds (the reference's known-answer
+// values, src/multirand.F90:396-425) and, after the rank-dependent constant-seed initialisation, uniform and Gaussian
+// draws -- no GPU needed, so the product-side RNG can be checked on any machine (tests/test_capi_cpu.py).
+static int multirand_selftest_dump() {
+  for (int al = 1; al <= 3; al++) {
+    multirand::Generator g;  // fresh module state per engine (like the reference, init does not clear the Gaussian buffer)
+    g.default_seeds(al);
+    printf("default %d", al);
+    for (int i = 0; i < 10; i++) printf(" %lld", (long long)g.int64());
+    printf("\n");
+    g.init(al, 1, 2, 5);
+    printf("real64 %d", al);
+    for (int i = 0; i < 5; i++) printf(" %a", g.real64());
+    printf("\n");
+    double a[7], b[4];
+    g.gaussian_array(a, 7);  // odd count: the second value of the last pair stays buffered ...
+    g.gaussian_array(b, 4);  // ... and is consumed first by the next call
+    printf("gauss %d", al);
+    for (double t : a) printf(" %a", t);
+    for (double t : b) printf(" %a", t);
+    printf("\n");
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc == 2 && std::string(argv[1]) == "multirand_selftest") return multirand_selftest_dump();
   pic1dp_input::Input in;
   if (!pic1dp_input::parse(in, argc, argv)) {
     fprintf(stderr, "usage: %s [key=value ...]  (keys: nparticle_max nx time_max dt ngpus seed_type out ...)\n", argv[0]);

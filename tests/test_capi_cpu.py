@@ -131,3 +131,26 @@ def test_cpp_host_driver_builds_and_fails_loudly_without_gpu():
     assert "no CUDA device" in out.stderr
     bad = subprocess.run([exe, "linear=1", "deltaf=0"], capture_output=True, text=True)  # input_init check
     assert bad.returncode == 1 and "not implemented" in bad.stderr
+
+
+def test_cpp_host_multirand_against_known_answers_and_oracle():
+    """The product-side RNG of host/pic1dp_host.cpp (no GPU needed): engine heads after the default seeds equal the
+    reference's known-answer values (tests/golden/multirand_kat.json, from src/multirand.F90:396-425); uniform and
+    Gaussian draws after the constant-seed initialisation (rank 2, warm-up 5) equal the KAT-pinned oracle bit for bit,
+    including the one-value buffer of the polar method across calls."""
+    import json
+    from pic1dp_b200 import build
+    from oracle import oracle as O
+    exe = build.build_host()
+    out = subprocess.run([exe, "multirand_selftest"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "multirand_kat.json")))
+    heads = {1: kat["kiss64"], 2: kat["mt19937_64_head"], 3: kat["superkiss64_head"]}
+    lines = {(l.split()[0], int(l.split()[1])): l.split()[2:] for l in out.stdout.splitlines() if l.strip()}
+    for al in (1, 2, 3):
+        assert [int(t) for t in lines[("default", al)]] == heads[al], al
+        r = O.MultiRand()
+        r.init_const(al, 2, 5)
+        assert [float.fromhex(t) for t in lines[("real64", al)]] == [r.real64() for _ in range(5)], al
+        g = list(r.gaussian_array(7)) + list(r.gaussian_array(4))
+        assert [float.fromhex(t) for t in lines[("gauss", al)]] == g, al
