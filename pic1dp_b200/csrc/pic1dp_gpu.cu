@@ -23,9 +23,11 @@
 
 #include "diag_kernels.cuh"
 #include "field_kernels.cuh"
+#include "loader_kernels.cuh"
 #include "optimize_host.hpp"
 #include "optimize_kernels.cuh"
 #include "particle_kernels.cuh"
+#include "push_tables.hpp"
 
 using namespace pic1dp;
 
@@ -213,87 +215,8 @@ static void species_const(const pic1dp_params &p, int s, SpeciesConst &c) {
   c.i_sqT2m = 1.0 / c.sqT2m;
 }
 
-// ---- kernel dispatch tables -----------------------------------------------------------------------------
-typedef void (*PushKernel)(const ParticleArgs);
-
-// cfg: -1 generic (switches read at run time), 1 = delta-f nonlinear shape 3/4, 9 = same with power-of-two
-// divisors, 25 = same with T = T2 = m = 1 (the reference default input)
-template <int DIST, bool IRK2, int CFG>
-static PushKernel pick_dep(int dep) {
-  switch (dep) {
-    case DEP_SMEM_ATOMIC: return k_push<DIST, IRK2, DEP_SMEM_ATOMIC, true, CFG>;
-    case DEP_GLOBAL_RED: return k_push<DIST, IRK2, DEP_GLOBAL_RED, true, CFG>;
-    default: return k_push<DIST, IRK2, DEP_WARP_PRIVATE, true, CFG>;
-  }
-}
-template <int DIST, bool IRK2>
-static PushKernel pick_cfg(int dep, bool fused, int cfg) {
-  if (!fused) return k_push<DIST, IRK2, DEP_SMEM_ATOMIC, false, -1>;
-  if (cfg == 1) return pick_dep<DIST, IRK2, 1>(dep);
-  if (cfg == 9) return pick_dep<DIST, IRK2, 9>(dep);
-  if (cfg == 25) return pick_dep<DIST, IRK2, 25>(dep);
-  return pick_dep<DIST, IRK2, -1>(dep);
-}
-template <int DIST>
-static PushKernel pick_irk(int dep, bool irk2, bool fused, int cfg) {
-  return irk2 ? pick_cfg<DIST, true>(dep, fused, cfg) : pick_cfg<DIST, false>(dep, fused, cfg);
-}
-static PushKernel pick_push(int dist, int dep, bool irk2, bool fused, int cfg) {
-  switch (dist) {
-    case 1: return pick_irk<1>(dep, irk2, fused, cfg);
-    case 2: return pick_irk<2>(dep, irk2, fused, cfg);
-    case 3: return pick_irk<3>(dep, irk2, fused, cfg);
-    default: return pick_irk<0>(dep, irk2, fused, cfg);
-  }
-}
-// TMA-pipelined flagship kernels (delta-f nonlinear, fused): cfg in {1, 9, 25}
-template <int DIST, bool IRK2, int CFG>
-static PushKernel pick_tma_dep(int dep) {
-  switch (dep) {
-    case DEP_SMEM_ATOMIC: return k_push_tma<DIST, IRK2, DEP_SMEM_ATOMIC, CFG>;
-    case DEP_GLOBAL_RED: return k_push_tma<DIST, IRK2, DEP_GLOBAL_RED, CFG>;
-    default: return k_push_tma<DIST, IRK2, DEP_WARP_PRIVATE, CFG>;
-  }
-}
-template <int DIST>
-static PushKernel pick_tma_dist(int dep, bool irk2, int cfg) {
-  if (cfg == 25) return irk2 ? pick_tma_dep<DIST, true, 25>(dep) : pick_tma_dep<DIST, false, 25>(dep);
-  if (cfg == 9) return irk2 ? pick_tma_dep<DIST, true, 9>(dep) : pick_tma_dep<DIST, false, 9>(dep);
-  return irk2 ? pick_tma_dep<DIST, true, 1>(dep) : pick_tma_dep<DIST, false, 1>(dep);
-}
-static PushKernel pick_tma(int dist, int dep, bool irk2, int cfg) {
-  switch (dist) {
-    case 1: return pick_tma_dist<1>(dep, irk2, cfg);
-    case 2: return pick_tma_dist<2>(dep, irk2, cfg);
-    case 3: return pick_tma_dist<3>(dep, irk2, cfg);
-    default: return pick_tma_dist<0>(dep, irk2, cfg);
-  }
-}
-
-// cp.async-staged flagship kernels (delta-f nonlinear, fused): cfg in {1, 9, 25}
-template <int DIST, bool IRK2, int CFG>
-static PushKernel pick_cpa_dep(int dep) {
-  switch (dep) {
-    case DEP_SMEM_ATOMIC: return k_push_cpa<DIST, IRK2, DEP_SMEM_ATOMIC, CFG>;
-    case DEP_GLOBAL_RED: return k_push_cpa<DIST, IRK2, DEP_GLOBAL_RED, CFG>;
-    default: return k_push_cpa<DIST, IRK2, DEP_WARP_PRIVATE, CFG>;
-  }
-}
-template <int DIST>
-static PushKernel pick_cpa_dist(int dep, bool irk2, int cfg) {
-  if (cfg == 25) return irk2 ? pick_cpa_dep<DIST, true, 25>(dep) : pick_cpa_dep<DIST, false, 25>(dep);
-  if (cfg == 9) return irk2 ? pick_cpa_dep<DIST, true, 9>(dep) : pick_cpa_dep<DIST, false, 9>(dep);
-  return irk2 ? pick_cpa_dep<DIST, true, 1>(dep) : pick_cpa_dep<DIST, false, 1>(dep);
-}
-static PushKernel pick_cpa(int dist, int dep, bool irk2, int cfg) {
-  switch (dist) {
-    case 1: return pick_cpa_dist<1>(dep, irk2, cfg);
-    case 2: return pick_cpa_dist<2>(dep, irk2, cfg);
-    case 3: return pick_cpa_dist<3>(dep, irk2, cfg);
-    default: return pick_cpa_dist<0>(dep, irk2, cfg);
-  }
-}
-
+// ---- kernel dispatch tables: the fused-kernel instantiations live in push_dist.cu, compiled once per iptcldist
+// (4 translation units built in parallel); see push_tables.hpp ----
 static PushKernel pick_deposit(int dep, bool deposit) {
   if (!deposit) return k_deposit<DEP_SMEM_ATOMIC, false>;
   switch (dep) {
