@@ -47,7 +47,9 @@ type, bind(c), public :: pic1dp_params
   integer(c_int32_t) :: field_mode
   integer(c_int32_t) :: fuse
   integer(c_int32_t) :: load_path
-  integer(c_int32_t) :: reserved(7)
+  integer(c_int32_t) :: arith_mode
+  integer(c_int32_t) :: no_step_graph
+  integer(c_int32_t) :: reserved(5)
 end type pic1dp_params
 
 interface

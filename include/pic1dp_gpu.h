@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PIC1DP_ABI_VERSION 1
+#define PIC1DP_ABI_VERSION 2
 #define PIC1DP_MAX_SPECIES 4
 #define PIC1DP_MAX_MODES 64
 #define PIC1DP_UNIQUE_ID_BYTES 128
@@ -66,6 +66,19 @@ enum {
   PIC1DP_LOAD_TMA = 2,    /* cp.async.bulk tiles into a shared-memory ring (mbarrier pipeline) */
   PIC1DP_LOAD_CPASYNC = 3 /* per-thread cp.async (LDGSTS.128) into thread-private slots of a 2-stage shared-memory ring:
                              next tile in flight during the current one, no barrier; used where the ring fits */
+};
+
+/*
+ * arithmetic of the weight push (src/pic1dp_interaction.F90:266-331).  Cell index, weights, gather, x and v are
+ * evaluated in the reference's operation order in BOTH modes and are bit-identical to it given the same inputs.
+ */
+enum {
+  PIC1DP_ARITH_STRICT = 0,   /* tmp2 = -d ln f0/dv exactly as written at :275-326: two exponentials, every division and
+                                rounding of the reference (w then differs from glibc only through exp, <= 1 ulp) */
+  PIC1DP_ARITH_TOLERANCE = 1 /* two-stream2 / bump-on-tail: numerator and denominator divided through by the first
+                                exponential, so ONE exponential of the difference of the two arguments and fused
+                                multiply-adds; algebraically identical, w agrees with STRICT to a few ulp
+                                (tested <= 1e-14 of max|w| per substep; north_star bar 1e-12) */
 };
 
 /* field-solve summation order for the partial-DFT projections */
@@ -113,7 +126,10 @@ typedef struct pic1dp_params {
   int32_t fuse;                             /* 1: push also wraps x and deposits (collect_charge then only reduces);
                                                0: each call has exactly the reference's side effects */
   int32_t load_path;                        /* PIC1DP_LOAD_*: how marker tiles reach the SM (delta-f nonlinear kernels) */
-  int32_t reserved[7];
+  int32_t arith_mode;                       /* PIC1DP_ARITH_*: evaluation of -d ln f0/dv on the w path */
+  int32_t no_step_graph;                    /* 1: pic1dp_gpu_step launches its kernels one by one instead of replaying a
+                                               captured CUDA graph of the timestep */
+  int32_t reserved[5];
 } pic1dp_params;
 
 typedef struct pic1dp_gpu pic1dp_gpu_t; /* opaque handle: the module-global state of the three Fortran modules */
@@ -160,6 +176,16 @@ int pic1dp_gpu_p2p_export(pic1dp_gpu_t *h, uint8_t handle[PIC1DP_IPC_HANDLE_BYTE
 int pic1dp_gpu_p2p_import(pic1dp_gpu_t *h, const uint8_t *all_handles /* nranks * PIC1DP_IPC_HANDLE_BYTES */);
 
 /*
+ * Rendezvous trace of the peer-memory all-reduce (measurement aid): with capacity > 0 the kernels stamp %globaltimer
+ * (ns) when this rank publishes its partial density, when its gather kernel starts waiting and when the wait ends --
+ * 3 stamps per all-reduce in a ring of `capacity` entries indexed by epoch % capacity; capacity = 0 turns it off.
+ * trace_read copies the ring (capacity * 3 values) and the epoch of the last all-reduce.  (wait_end - publish) of the
+ * rank that arrived last is the exchange latency; for the others the excess is arrival skew.
+ */
+int pic1dp_gpu_p2p_trace(pic1dp_gpu_t *h, int32_t capacity);
+int pic1dp_gpu_p2p_trace_read(pic1dp_gpu_t *h, uint64_t *stamps, int64_t *last_epoch);
+
+/*
  * set_markers: H2D of one species after particle_load (src/pic1dp_particle.F90:145-269 fills x,v,p,w through
  * VecGetArrayF90).  np = particle_np(ispecies) (:248).  isp is 0-based.
  */
@@ -189,6 +215,46 @@ int pic1dp_gpu_load_markers_maxwellian(pic1dp_gpu_t *h, int32_t isp, int64_t np,
                                        const double *gauss_v, const double *rand_x, int32_t init_nmode,
                                        const int32_t *init_mode, const double *init_mode_cos,
                                        const double *init_mode_sin);
+
+/*
+ * ---- device-side random streams: particle_load without a marker-sized host-to-device copy ----
+ *
+ * load_markers_kiss64: load_markers with the two uniform streams generated ON THE DEVICE by Marsaglia's 64-bit KISS,
+ * the generator multirand_al_int = 1 selects (src/multirand.F90:921-945), bit for bit.  seeds = multirand_seeds(0:3)
+ * as multirand_init leaves them (any seed_type; :256-381 stay on the host: a few dozen generator calls), offset_v /
+ * offset_x = how many 64-bit outputs the host generator would have produced before the first element of this rank's
+ * pv / px arrays (particle_load draws the whole local Vec: offset_v = 2 * isp * nlocal, offset_x = offset_v + nlocal,
+ * nlocal = particle_ip_high - particle_ip_low, :180, :222).  Each device thread jumps the three recurrences of KISS64
+ * (LCG, xorshift, multiply-with-carry) to its chunk in O(log offset) and then runs the sequential generator; the
+ * uniforms are INT2REAL64 of its outputs (:49).  Afterwards the host advances its own state with
+ * pic1dp_host_kiss64_jump(seeds, 2 * nlocal * nspecies) so that later draws (particle_remove, particle_split)
+ * continue the same stream.  SuperKISS64 (al_int = 3: lag-20632 carry chain, no practical jump) and MT19937-64
+ * streams keep coming from the host through load_markers.
+ */
+int pic1dp_gpu_load_markers_kiss64(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init,
+                                   const uint64_t seeds[4], int64_t offset_v, int64_t offset_x, double v_max,
+                                   int32_t init_nmode, const int32_t *init_mode, const double *init_mode_cos,
+                                   const double *init_mode_sin);
+
+/*
+ * load_markers_counter: the same with a counter-based generator (Philox-4x32-10) for synthetic markers that need no
+ * reference stream: the uniforms of marker i depend only on (seed, isp, first_index + i), so any decomposition over
+ * ranks loads the same global marker set (first_index = global index of this rank's first marker).
+ */
+int pic1dp_gpu_load_markers_counter(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, uint64_t seed,
+                                    int64_t first_index, double v_max, int32_t init_nmode, const int32_t *init_mode,
+                                    const double *init_mode_cos, const double *init_mode_sin);
+
+/* debug / parity: n uniforms of the device KISS64 stream starting at `offset`, copied to the host */
+int pic1dp_gpu_kiss64_uniforms(pic1dp_gpu_t *h, const uint64_t seeds[4], int64_t offset, int64_t n, double *out);
+
+/* the same generator code on the host (no handle, no GPU): jump advances multirand_seeds(0:3) by n outputs in
+ * O(log n); fill writes n uniforms (multirand_real_array) and advances the state; counter_uniforms = the two streams
+ * of load_markers_counter */
+int pic1dp_host_kiss64_jump(uint64_t seeds[4], int64_t n);
+int pic1dp_host_kiss64_fill(uint64_t seeds[4], int64_t n, double *out);
+void pic1dp_host_counter_uniforms(uint64_t seed, int32_t stream, int64_t first_index, int64_t n, double *u_v,
+                                  double *u_x);
 
 /*
  * get_markers: D2H refresh of the host Vecs before pic1dp_output reads them (src/pic1dp_output.F90:128-150,
@@ -342,6 +408,7 @@ typedef struct pic1dp_counters {
   int32_t grid_ctas;         /* CTAs of the particle kernels */
   int32_t cta_threads;
   int32_t smem_bytes;        /* dynamic shared memory of the fused kernel */
+  int64_t graph_replays;     /* timesteps executed by replaying the captured CUDA graph of the step */
 } pic1dp_counters;
 int pic1dp_gpu_get_counters(pic1dp_gpu_t *h, pic1dp_counters *c);
 

@@ -106,6 +106,14 @@ int64_t orc_multirand_int64(orc_multirand *g) {
   return (int64_t)r;
 }
 
+/* test access to the generator state: multirand_seeds(0:3) (KISS64) and discarding n outputs */
+void orc_multirand_get_seeds4(const orc_multirand *g, uint64_t out[4]) {
+  for (int i = 0; i < 4; i++) out[i] = g->seeds[i];
+}
+void orc_multirand_skip(orc_multirand *g, int64_t n) {
+  for (int64_t i = 0; i < n; i++) (void)orc_multirand_int64(g);
+}
+
 /* INT2REAL64: src/multirand.F90:49 -- signed int64 -> real64, / (2^64-1), + 0.5; [0,1] inclusive */
 double orc_multirand_real64(orc_multirand *g) {
   return (double)orc_multirand_int64(g) / 18446744073709551615.0 + 0.5;

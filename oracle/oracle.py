@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.orc_multirand_init_const.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_multirand_int64.argtypes = [C.c_void_p]
         L.orc_multirand_int64.restype = C.c_int64
+        L.orc_multirand_get_seeds4.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.orc_multirand_skip.argtypes = [C.c_void_p, C.c_int64]
         L.orc_multirand_real64.argtypes = [C.c_void_p]
         L.orc_multirand_real64.restype = C.c_double
         L.orc_multirand_real_array.argtypes = [C.c_void_p, dp, C.c_int64]
@@ -297,6 +299,14 @@ class MultiRand:
 
     def int64(self):
         return self.L.orc_multirand_int64(self.g)
+
+    def seeds4(self):
+        out = (C.c_uint64 * 4)()
+        self.L.orc_multirand_get_seeds4(self.g, out)
+        return [int(v) for v in out]
+
+    def skip(self, n):
+        self.L.orc_multirand_skip(self.g, int(n))
 
     def real64(self):
         return self.L.orc_multirand_real64(self.g)

@@ -136,6 +136,8 @@ void orc_multirand_seed_default(orc_multirand *g, int al_int);
 /* constant-seed path (seed_type 1) + warm-up: src/multirand.F90:301-381 */
 void orc_multirand_init_const(orc_multirand *g, int al_int, int mype, int warmup);
 int64_t orc_multirand_int64(orc_multirand *g);
+void orc_multirand_get_seeds4(const orc_multirand *g, uint64_t out[4]); /* multirand_seeds(0:3), KISS64 state */
+void orc_multirand_skip(orc_multirand *g, int64_t n);                   /* discard n outputs */
 double orc_multirand_real64(orc_multirand *g);            /* INT2REAL64, :49 */
 void orc_multirand_real_array(orc_multirand *g, double *a, int64_t n);      /* :664-690 */
 void orc_multirand_gaussian_array(orc_multirand *g, double *a, int64_t n);  /* :838-872 */

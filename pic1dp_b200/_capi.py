@@ -51,7 +51,9 @@ class Params(C.Structure):
         ("field_mode", C.c_int32),
         ("fuse", C.c_int32),
         ("load_path", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("arith_mode", C.c_int32),
+        ("no_step_graph", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -68,6 +70,7 @@ class Counters(C.Structure):
         ("grid_ctas", C.c_int32),
         ("cta_threads", C.c_int32),
         ("smem_bytes", C.c_int32),
+        ("graph_replays", C.c_int64),
     ]
 
 
@@ -86,6 +89,9 @@ EXPORTS = [
     "pic1dp_gpu_particle_split",
     "pic1dp_host_particle_merge", "pic1dp_host_particle_remove", "pic1dp_host_particle_split",
     "pic1dp_gpu_launch_timing_start", "pic1dp_gpu_launch_timing_stop",
+    "pic1dp_gpu_load_markers_kiss64", "pic1dp_gpu_load_markers_counter", "pic1dp_gpu_kiss64_uniforms",
+    "pic1dp_host_kiss64_jump", "pic1dp_host_kiss64_fill", "pic1dp_host_counter_uniforms",
+    "pic1dp_gpu_p2p_trace", "pic1dp_gpu_p2p_trace_read",
 ]
 
 # RNG call-backs of particle_remove / particle_split (pic1dp_real64_fn, pic1dp_gaussian_array_fn)
@@ -159,6 +165,16 @@ def load() -> C.CDLL:
     L.pic1dp_host_particle_split.argtypes = [i64, i64, dp, dp, dp, dp, dp, i32, dbl, dbl, i32, dbl, i32,
                                              GAUSSIAN_ARRAY_FN, vp]
     L.pic1dp_host_particle_split.restype = i64
+    u64p = C.POINTER(C.c_uint64)
+    L.pic1dp_gpu_load_markers_kiss64.argtypes = [vp, i32, i64, i64, u64p, i64, i64, dbl, i32, C.POINTER(i32), dp, dp]
+    L.pic1dp_gpu_load_markers_counter.argtypes = [vp, i32, i64, i64, C.c_uint64, i64, dbl, i32, C.POINTER(i32), dp, dp]
+    L.pic1dp_gpu_kiss64_uniforms.argtypes = [vp, u64p, i64, i64, dp]
+    L.pic1dp_host_kiss64_jump.argtypes = [u64p, i64]
+    L.pic1dp_host_kiss64_fill.argtypes = [u64p, i64, dp]
+    L.pic1dp_host_counter_uniforms.argtypes = [C.c_uint64, i32, i64, i64, dp, dp]
+    L.pic1dp_host_counter_uniforms.restype = None
+    L.pic1dp_gpu_p2p_trace.argtypes = [vp, i32]
+    L.pic1dp_gpu_p2p_trace_read.argtypes = [vp, u64p, i64p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("pic1dp_gpu_abi_version",):

@@ -30,26 +30,33 @@ struct GridArgs {
   double *energy;
   // peer-memory all-reduce of `red` fused into the reduce kernel (scatter) and the finalize / solve kernels (gather);
   // p2p_nranks == 0: off (single rank, or ncclAllReduce between the kernels)
-  int p2p_nranks, p2p_rank, p2p_parity;
-  unsigned long long p2p_epoch;
+  int p2p_nranks, p2p_rank;
   unsigned long long *p2p_peer[8];  // exchange buffer of every rank: flags[2][nranks] (padded to 256 B) | data[2][nranks][count]
   unsigned int *p2p_counter;        // local: CTAs of the reduce kernel that have stored their part
   unsigned long long *p2p_timeouts; // local error counter
+  // The all-reduce epoch lives in device memory (not in a kernel argument) so that a captured CUDA graph of the step
+  // can be replayed: the reduce kernel works on epoch *p2p_epoch_dev + 1 and its last CTA stores that value back
+  // after publishing; the gather side, later in stream order, reads the stored value.  Slot parity = epoch & 1.
+  unsigned long long *p2p_epoch_dev;
+  // optional trace of the rendezvous (pic1dp_gpu_p2p_trace): %globaltimer at publish, wait entry and wait exit,
+  // 3 stamps per epoch in a ring of p2p_stamp_cap entries
+  unsigned long long *p2p_stamps;
+  int p2p_stamp_cap;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ double *p2p_data(unsigned long long *base, int nranks, int count, int parity, int r) {
   const size_t flag_bytes = ((size_t)2 * nranks * 8 + 255) & ~(size_t)255;
   return reinterpret_cast<double *>(reinterpret_cast<char *>(base) + flag_bytes) + ((size_t)parity * nranks + r) * count;
 }
 
-// scatter side: store one reduced value into slot [parity][my rank] of every rank's exchange buffer (NVLink stores)
-__device__ __forceinline__ void p2p_store(const GridArgs &g, int idx, double v) {
-  const int count = (g.matrix_path ? g.nspecies : 1) * g.nx;
-  for (int r = 0; r < g.p2p_nranks; r++) p2p_data(g.p2p_peer[r], g.p2p_nranks, count, g.p2p_parity, g.p2p_rank)[idx] = v;
-}
-
 // scatter side, end of the kernel: the last CTA publishes this rank's epoch flag in every rank's buffer
-__device__ __forceinline__ void p2p_publish(const GridArgs &g) {
+__device__ __forceinline__ void p2p_publish(const GridArgs &g, unsigned long long epoch) {
   __threadfence_system();  // my stores are visible system-wide before the counter / flag
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -57,26 +64,32 @@ __device__ __forceinline__ void p2p_publish(const GridArgs &g) {
     if (prev == gridDim.x - 1) {
       *g.p2p_counter = 0;
       __threadfence_system();
+      const int parity = (int)(epoch & 1);
       for (int r = 0; r < g.p2p_nranks; r++) {
-        unsigned long long *flag = g.p2p_peer[r] + (size_t)g.p2p_parity * g.p2p_nranks + g.p2p_rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(g.p2p_epoch) : "memory");
+        unsigned long long *flag = g.p2p_peer[r] + (size_t)parity * g.p2p_nranks + g.p2p_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
       }
+      *g.p2p_epoch_dev = epoch;  // every CTA of this kernel has read the old value by now (it arrived at the counter)
+      if (g.p2p_stamps) g.p2p_stamps[(size_t)(epoch % g.p2p_stamp_cap) * 3] = globaltimer_ns();
     }
   }
 }
 
 // gather side, start of the kernel: wait (bounded) until every rank's flag shows this epoch; returns false on timeout
-__device__ __forceinline__ bool p2p_wait(const GridArgs &g) {
+__device__ __forceinline__ bool p2p_wait(const GridArgs &g, unsigned long long epoch) {
   __shared__ int s_ok;
-  if (threadIdx.x == 0) s_ok = 1;
+  if (threadIdx.x == 0) {
+    s_ok = 1;
+    if (g.p2p_stamps && blockIdx.x == 0) g.p2p_stamps[(size_t)(epoch % g.p2p_stamp_cap) * 3 + 1] = globaltimer_ns();
+  }
   __syncthreads();
   if ((int)threadIdx.x < g.p2p_nranks) {
-    const unsigned long long *flag = g.p2p_peer[g.p2p_rank] + (size_t)g.p2p_parity * g.p2p_nranks + threadIdx.x;
+    const unsigned long long *flag = g.p2p_peer[g.p2p_rank] + (size_t)(epoch & 1) * g.p2p_nranks + threadIdx.x;
     unsigned long long seen = 0;
     long long spins = 0;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-      if (seen >= g.p2p_epoch) break;
+      if (seen >= epoch) break;
       if (++spins > 200000000LL) {  // seconds: a peer died; report instead of hanging the GPU
         s_ok = 0;
         if (blockIdx.x == 0) atomicAdd(g.p2p_timeouts, 1ULL);
@@ -86,24 +99,31 @@ __device__ __forceinline__ bool p2p_wait(const GridArgs &g) {
     }
   }
   __syncthreads();
+  if (g.p2p_stamps && blockIdx.x == 0 && threadIdx.x == 0)
+    g.p2p_stamps[(size_t)(epoch % g.p2p_stamp_cap) * 3 + 2] = globaltimer_ns();
   return s_ok != 0;
 }
 
 // gather side: the all-reduced value = sum over ranks in rank order (bitwise identical on every rank)
-__device__ __forceinline__ double p2p_sum(const GridArgs &g, int idx) {
+__device__ __forceinline__ double p2p_sum(const GridArgs &g, int idx, int parity) {
   const int count = (g.matrix_path ? g.nspecies : 1) * g.nx;
-  double t = p2p_data(g.p2p_peer[g.p2p_rank], g.p2p_nranks, count, g.p2p_parity, 0)[idx];
+  double t = p2p_data(g.p2p_peer[g.p2p_rank], g.p2p_nranks, count, parity, 0)[idx];
   for (int r = 1; r < g.p2p_nranks; r++)
-    t = dadd(t, p2p_data(g.p2p_peer[g.p2p_rank], g.p2p_nranks, count, g.p2p_parity, r)[idx]);
+    t = dadd(t, p2p_data(g.p2p_peer[g.p2p_rank], g.p2p_nranks, count, parity, r)[idx]);
   return t;
 }
 
 // CTA = 32 cells x 8 warps.  Warp q sums the private grids q, q+8, q+16, ... of its 32 cells in that order (4 loads
 // in flight), then warp 0 adds the 8 partial sums in warp order: a fixed summation tree, hence deterministic.
+// Peer-memory all-reduce, scatter half: the CTA's reduced values (32 cells x nred grids) are staged in shared memory
+// and warp q stores them into slot [parity][my rank] of rank q's exchange buffer -- one coalesced 256-byte NVLink
+// store per peer and grid, all peers in parallel (8 warps = the 8 ranks the exchange supports).
 __global__ void __launch_bounds__(256) k_reduce_charge(const GridArgs g) {
   __shared__ double s_part[8][33];
+  __shared__ double s_out[4][32];  // reduced values of this CTA: [grid (species on the matrix path)][cell]
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
+  const unsigned long long epoch = g.p2p_nranks ? *g.p2p_epoch_dev + 1 : 0;  // a new all-reduce
   double c2 = 0.0;
   for (int s = 0; s < g.nspecies; s++) {
     double c1 = 0.0;
@@ -126,7 +146,7 @@ __global__ void __launch_bounds__(256) k_reduce_charge(const GridArgs g) {
 #pragma unroll
       for (int q = 1; q < 8; q++) t = dadd(t, s_part[q][lane]);
       if (g.matrix_path) {  // field_tmp = S^T w per species (:52-59)
-        if (g.p2p_nranks) p2p_store(g, s * g.nx + j, t);
+        if (g.p2p_nranks) s_out[s][lane] = t;
         else g.red[(size_t)s * g.nx + j] = t;
       } else {
         c2 = dadd(c2, dmul(t, g.Z[s]));   // charge2 += charge1 * Z (:126-127)
@@ -135,30 +155,38 @@ __global__ void __launch_bounds__(256) k_reduce_charge(const GridArgs g) {
     __syncthreads();
   }
   if (wq == 0 && j < g.nx && !g.matrix_path) {
-    if (g.p2p_nranks) p2p_store(g, j, c2);
+    if (g.p2p_nranks) s_out[0][lane] = c2;
     else g.red[j] = c2;
   }
-  if (g.p2p_nranks) p2p_publish(g);  // MPI_Allreduce (:132-133), scatter half
+  if (g.p2p_nranks) {  // MPI_Allreduce (:132-133), scatter half
+    __syncthreads();
+    const int nred = g.matrix_path ? g.nspecies : 1, count = nred * g.nx, parity = (int)(epoch & 1);
+    if (wq < g.p2p_nranks && j < g.nx) {
+      double *dst = p2p_data(g.p2p_peer[wq], g.p2p_nranks, count, parity, g.p2p_rank);
+      for (int q = 0; q < nred; q++) dst[(size_t)q * g.nx + j] = s_out[q][lane];
+    }
+    p2p_publish(g, epoch);
+  }
 }
 
 // rho from the (all-)reduced grid: charge1 * nx / lx and the full-f offset (:140-148); matrix path :64-78
-__device__ __forceinline__ double red_value(const GridArgs &g, int idx) {
+__device__ __forceinline__ double red_value(const GridArgs &g, int idx, int parity) {
   if (!g.p2p_nranks) return g.red[idx];
-  const double t = p2p_sum(g, idx);  // MPI_Allreduce (:132-133), gather half
+  const double t = p2p_sum(g, idx, parity);  // MPI_Allreduce (:132-133), gather half
   g.red[idx] = t;
   return t;
 }
 
-__device__ __forceinline__ double finalize_rho(const GridArgs &g, int j) {
+__device__ __forceinline__ double finalize_rho(const GridArgs &g, int j, int parity) {
   double rho;
   if (!g.matrix_path) {
-    rho = ddiv(dmul(red_value(g, j), g.rnx), g.lx);  // :140-141
+    rho = ddiv(dmul(red_value(g, j, parity), g.rnx), g.lx);  // :140-141
     if (!g.deltaf)
       for (int s = 0; s < g.nspecies; s++) rho = dsub(rho, dmul(g.Z[s], g.n[s]));  // :142-148
   } else {
     rho = 0.0;  // :47
     for (int s = 0; s < g.nspecies; s++) {
-      double t = red_value(g, s * g.nx + j);
+      double t = red_value(g, s * g.nx + j, parity);
       if (!g.deltaf) t = dsub(t, ddiv(dmul(g.n[s], g.lx), g.rnx));  // :67
       rho = dadd(rho, dmul(g.Z[s], t));                              // VecAXPY :71
     }
@@ -168,9 +196,10 @@ __device__ __forceinline__ double finalize_rho(const GridArgs &g, int j) {
 }
 
 __global__ void __launch_bounds__(128) k_finalize_rho(const GridArgs g) {
-  const bool ok = g.p2p_nranks ? p2p_wait(g) : true;
+  const unsigned long long epoch = g.p2p_nranks ? *g.p2p_epoch_dev : 0;  // stored by the reduce kernel before this launch
+  const bool ok = g.p2p_nranks ? p2p_wait(g, epoch) : true;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < g.nx) g.rho[j] = ok ? finalize_rho(g, j) : __longlong_as_double(0x7ff8000000000000LL);
+  if (j < g.nx) g.rho[j] = ok ? finalize_rho(g, j, (int)(epoch & 1)) : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 // Single CTA, 1024 threads.  smem: rho[nx] + 2*nmode mode values.
@@ -184,11 +213,12 @@ __global__ void __launch_bounds__(1024) k_field_solve(const GridArgs g) {
   double *s_re = smem + g.nx;
   double *s_im = s_re + g.nmode;
   const int M = g.nmode, nx = g.nx;
-  const bool p2p_ok = (FINALIZE && g.p2p_nranks) ? p2p_wait(g) : true;
+  const unsigned long long epoch = (FINALIZE && g.p2p_nranks) ? *g.p2p_epoch_dev : 0;
+  const bool p2p_ok = (FINALIZE && g.p2p_nranks) ? p2p_wait(g, epoch) : true;
   for (int j = threadIdx.x; j < nx; j += blockDim.x) {
     double r;
     if (FINALIZE) {
-      r = p2p_ok ? finalize_rho(g, j) : __longlong_as_double(0x7ff8000000000000LL);
+      r = p2p_ok ? finalize_rho(g, j, (int)(epoch & 1)) : __longlong_as_double(0x7ff8000000000000LL);
       g.rho[j] = r;
     } else {
       r = g.rho[j];

@@ -28,6 +28,7 @@
 #include "optimize_kernels.cuh"
 #include "particle_kernels.cuh"
 #include "push_tables.hpp"
+#include "rng_kernels.cuh"
 
 using namespace pic1dp;
 
@@ -115,6 +116,7 @@ struct pic1dp_gpu {
   double *d_E = nullptr, *d_rho = nullptr, *d_mre = nullptr, *d_mim = nullptr;
   double *d_Fre = nullptr, *d_Fim = nullptr, *d_ginv = nullptr;
   double *d_partial = nullptr, *d_red = nullptr, *d_energy = nullptr;
+  void *d_kiss_tab = nullptr;   // KissTables: jump-ahead tables of the device KISS64 (allocated on first use)
   unsigned long long *d_noob = nullptr;
   std::vector<double> h_Fre, h_Fim, h_ginv;
   // diagnostics scratch (allocated on first use)
@@ -143,9 +145,19 @@ struct pic1dp_gpu {
   unsigned long long *peer_base[8] = {};      // mapped buffers of all ranks (peer_base[rank] == d_xchg)
   unsigned int *d_p2p_counter = nullptr;
   unsigned long long *d_p2p_timeouts = nullptr;
+  unsigned long long *d_p2p_epoch = nullptr;  // all-reduce epoch, advanced on the device by k_reduce_charge
+  unsigned long long *h_p2p_timeouts = nullptr;  // pinned mirror of d_p2p_timeouts, refreshed by synchronising calls
+  unsigned long long *d_p2p_stamps = nullptr; // rendezvous trace ring (pic1dp_gpu_p2p_trace), 3 stamps per epoch
+  int p2p_stamp_cap = 0;
   bool p2p_ready = false;
-  unsigned long long p2p_epoch = 0;
   int64_t p2p_calls = 0;
+  // one timestep {push, reduce, solve} x 2 captured as a CUDA graph (pic1dp_gpu_step): valid for the marker counts and
+  // buffer rotation it was captured with
+  cudaGraphExec_t step_graph = nullptr;
+  bool graph_enabled = true;
+  int graph_cur[PIC1DP_MAX_SPECIES] = {};
+  int64_t graph_np[PIC1DP_MAX_SPECIES] = {};
+  int64_t graph_launches = 0, graph_nccl = 0, graph_p2p = 0, graph_replays = 0;
   int64_t launches = 0, nccl_calls = 0, h2d = 0, d2h = 0;
   std::string err;
 };
@@ -297,9 +309,9 @@ static int validate(const pic1dp_params *p, std::string &err) {
       err = "mass and temperatures must be positive";
       return PIC1DP_EINVAL;
     }
-  if (p->deposit_mode < 0 || p->deposit_mode > 3 || p->field_mode < 0 || p->field_mode > 1 || p->load_path < 0 ||
-      p->load_path > 3) {
-    err = "bad deposit_mode / field_mode / load_path";
+  if (p->deposit_mode < 0 || p->deposit_mode > 4 || p->field_mode < 0 || p->field_mode > 1 || p->load_path < 0 ||
+      p->load_path > 3 || p->arith_mode < 0 || p->arith_mode > 1) {
+    err = "bad deposit_mode / field_mode / load_path / arith_mode";
     return PIC1DP_EINVAL;
   }
   return PIC1DP_OK;
@@ -329,11 +341,16 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
       else free(h->stage[q]);
     }
   if (h->d_noob) cudaFree(h->d_noob);
+  if (h->d_kiss_tab) cudaFree(h->d_kiss_tab);
   for (int r = 0; r < 8; r++)
     if (h->peer_base[r] && h->peer_base[r] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
   if (h->d_xchg) cudaFree(h->d_xchg);
   if (h->d_p2p_counter) cudaFree(h->d_p2p_counter);
   if (h->d_p2p_timeouts) cudaFree(h->d_p2p_timeouts);
+  if (h->d_p2p_epoch) cudaFree(h->d_p2p_epoch);
+  if (h->h_p2p_timeouts) cudaFreeHost(h->h_p2p_timeouts);
+  if (h->d_p2p_stamps) cudaFree(h->d_p2p_stamps);
+  if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (cudaEvent_t e : h->pev)
@@ -360,6 +377,7 @@ static int create_impl(pic1dp_gpu_t *h) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, p.device));
   h->nsm = prop.multiProcessorCount;
+  h->graph_enabled = p.no_step_graph == 0 && !getenv("PIC1DP_NO_GRAPH");
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
@@ -608,6 +626,10 @@ int pic1dp_gpu_p2p_export(pic1dp_gpu_t *h, uint8_t handle[PIC1DP_IPC_HANDLE_BYTE
     CK(cudaMemset(h->d_p2p_counter, 0, 4));
     CK(cudaMalloc(&h->d_p2p_timeouts, 8));
     CK(cudaMemset(h->d_p2p_timeouts, 0, 8));
+    CK(cudaMalloc(&h->d_p2p_epoch, 8));
+    CK(cudaMemset(h->d_p2p_epoch, 0, 8));
+    CK(cudaMallocHost(&h->h_p2p_timeouts, 8));
+    *h->h_p2p_timeouts = 0;
   }
   static_assert(sizeof(cudaIpcMemHandle_t) == PIC1DP_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
   cudaIpcMemHandle_t ipc;
@@ -632,6 +654,22 @@ int pic1dp_gpu_p2p_import(pic1dp_gpu_t *h, const uint8_t *all_handles) {
     h->peer_base[r] = (unsigned long long *)ptr;
   }
   h->p2p_ready = true;
+  return PIC1DP_OK;
+}
+
+// A peer whose flag never arrives makes the gather side fill rho / E with NaN and bump d_p2p_timeouts.  Every call that
+// synchronises queues a copy of that counter before its sync and turns a non-zero count into PIC1DP_ENCCL, so a dead
+// peer is reported by the next get_field / output_* / sync instead of silently poisoning the markers.
+static void p2p_queue_timeout_read(pic1dp_gpu_t *h) {
+  if (h->p2p_ready && h->h_p2p_timeouts)
+    cudaMemcpyAsync(h->h_p2p_timeouts, h->d_p2p_timeouts, 8, cudaMemcpyDeviceToHost, h->stream);
+}
+static int p2p_check_timeouts(pic1dp_gpu_t *h, const char *who) {
+  if (h->p2p_ready && h->h_p2p_timeouts && *h->h_p2p_timeouts != 0) {
+    h->err = std::string(who) + ": the peer-memory density all-reduce timed out (" + std::to_string(*h->h_p2p_timeouts) +
+             " flag waits expired: a peer rank died or never reached the substep); rho and E hold NaN";
+    return PIC1DP_ENCCL;
+  }
   return PIC1DP_OK;
 }
 
@@ -673,24 +711,26 @@ int pic1dp_gpu_set_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, const doubl
   return upload_species(h, isp, np, x, v, p, w);
 }
 
-static int load_markers_impl(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
-                             const double *rand_x, double v_max, int32_t init_nmode, const int32_t *init_mode,
-                             const double *init_mode_cos, const double *init_mode_sin, int imarker) {
-  if (!h || isp < 0 || isp >= h->p.nspecies || np < 0 || nparticle_init < 1 || !rand_v || !rand_x || !(v_max > 0.0) ||
+static int load_check_args(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, double v_max,
+                           int32_t init_nmode, const int32_t *init_mode, const double *init_mode_cos,
+                           const double *init_mode_sin) {
+  if (!h || isp < 0 || isp >= h->p.nspecies || np < 0 || nparticle_init < 1 || !(v_max > 0.0) ||
       init_nmode < 0 || init_nmode > 8 || (init_nmode > 0 && (!init_mode || !init_mode_cos || !init_mode_sin))) {
     if (h) h->err = "load_markers: bad argument (at most 8 initial modes)";
     return PIC1DP_EINVAL;
   }
   if (np > h->p.capacity) { h->err = "load_markers: np exceeds capacity"; return PIC1DP_ECAPACITY; }
-  CK(cudaSetDevice(h->p.device));
+  return PIC1DP_OK;
+}
+
+// the loader arithmetic on the uniforms (or Gaussians) that already sit in v[0] and x[0] of the species
+static int load_markers_finish(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, double v_max,
+                               int32_t init_nmode, const int32_t *init_mode, const double *init_mode_cos,
+                               const double *init_mode_sin, int imarker) {
   Species &S = h->sp[isp];
   S.cur = 0;
   S.bak = 0;
   S.np = np;
-  const size_t b = (size_t)np * 8;
-  CK(cudaMemcpyAsync(S.v[0], rand_v, b, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(S.x[0], rand_x, b, cudaMemcpyHostToDevice, h->stream));
-  h->h2d += 2 * (int64_t)b;
   LoadArgs a;
   memset(&a, 0, sizeof(a));
   a.x = S.x[0];
@@ -717,6 +757,120 @@ static int load_markers_impl(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t n
   CK(cudaStreamSynchronize(h->stream));  // host buffers are only borrowed for the call
   S.loaded = true;
   return invalidate_partials(h);
+}
+
+static int load_markers_impl(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
+                             const double *rand_x, double v_max, int32_t init_nmode, const int32_t *init_mode,
+                             const double *init_mode_cos, const double *init_mode_sin, int imarker) {
+  int rc = load_check_args(h, isp, np, nparticle_init, v_max, init_nmode, init_mode, init_mode_cos, init_mode_sin);
+  if (rc) return rc;
+  if (!rand_v || !rand_x) { h->err = "load_markers: NULL stream"; return PIC1DP_EINVAL; }
+  CK(cudaSetDevice(h->p.device));
+  Species &S = h->sp[isp];
+  const size_t b = (size_t)np * 8;
+  CK(cudaMemcpyAsync(S.v[0], rand_v, b, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(S.x[0], rand_x, b, cudaMemcpyHostToDevice, h->stream));
+  h->h2d += 2 * (int64_t)b;
+  return load_markers_finish(h, isp, np, nparticle_init, v_max, init_nmode, init_mode, init_mode_cos, init_mode_sin,
+                             imarker);
+}
+
+// ---- device-side random streams (rng_kernels.cuh) ----
+static int kiss_tables(pic1dp_gpu_t *h) {
+  if (h->d_kiss_tab) return PIC1DP_OK;
+  KissTables *t = new KissTables;
+  memcpy(t->lcg, kiss_lcg_jump, sizeof(t->lcg));
+  memcpy(t->mwc, kiss_mwc_jump, sizeof(t->mwc));
+  memcpy(t->xs, kiss_xs_jump, sizeof(t->xs));
+  cudaError_t e = cudaMalloc(&h->d_kiss_tab, sizeof(KissTables));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_kiss_tab, t, sizeof(KissTables), cudaMemcpyHostToDevice);
+  delete t;
+  if (e != cudaSuccess) { h->err = std::string("kiss tables: ") + cudaGetErrorString(e); return PIC1DP_ECUDA; }
+  return PIC1DP_OK;
+}
+
+static int kiss64_fill_device(pic1dp_gpu_t *h, const uint64_t seeds[4], int64_t offset, int64_t n, double *d_out) {
+  int rc = kiss_tables(h);
+  if (rc) return rc;
+  if (n == 0) return PIC1DP_OK;
+  Kiss64 s0 = {seeds[0], seeds[1], seeds[2], seeds[3]};
+  const int chunk = 512;
+  const int64_t nchunks = (n + chunk - 1) / chunk;
+  int blocks = (int)((nchunks + 255) / 256);
+  if (blocks > h->nsm * 8) blocks = h->nsm * 8;
+  k_kiss64_fill<<<blocks, 256, 0, h->stream>>>(s0, (uint64_t)offset, n, chunk, (const KissTables *)h->d_kiss_tab, d_out);
+  CKL(h);
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_load_markers_kiss64(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init,
+                                   const uint64_t seeds[4], int64_t offset_v, int64_t offset_x, double v_max,
+                                   int32_t init_nmode, const int32_t *init_mode, const double *init_mode_cos,
+                                   const double *init_mode_sin) {
+  int rc = load_check_args(h, isp, np, nparticle_init, v_max, init_nmode, init_mode, init_mode_cos, init_mode_sin);
+  if (rc) return rc;
+  if (!seeds || offset_v < 0 || offset_x < 0) { h->err = "load_markers_kiss64: bad stream argument"; return PIC1DP_EINVAL; }
+  CK(cudaSetDevice(h->p.device));
+  Species &S = h->sp[isp];
+  if ((rc = kiss64_fill_device(h, seeds, offset_v, np, S.v[0]))) return rc;   // multirand_real_array(pv), :180
+  if ((rc = kiss64_fill_device(h, seeds, offset_x, np, S.x[0]))) return rc;   // multirand_real_array(px), :222
+  return load_markers_finish(h, isp, np, nparticle_init, v_max, init_nmode, init_mode, init_mode_cos, init_mode_sin, 2);
+}
+
+int pic1dp_gpu_load_markers_counter(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, uint64_t seed,
+                                    int64_t first_index, double v_max, int32_t init_nmode, const int32_t *init_mode,
+                                    const double *init_mode_cos, const double *init_mode_sin) {
+  int rc = load_check_args(h, isp, np, nparticle_init, v_max, init_nmode, init_mode, init_mode_cos, init_mode_sin);
+  if (rc) return rc;
+  if (first_index < 0) { h->err = "load_markers_counter: bad first_index"; return PIC1DP_EINVAL; }
+  CK(cudaSetDevice(h->p.device));
+  Species &S = h->sp[isp];
+  if (np > 0) {
+    k_counter_fill<<<h->nsm * 8, 256, 0, h->stream>>>(seed, (uint32_t)isp, (uint64_t)first_index, np, S.v[0], S.x[0]);
+    CKL(h);
+  }
+  return load_markers_finish(h, isp, np, nparticle_init, v_max, init_nmode, init_mode, init_mode_cos, init_mode_sin, 2);
+}
+
+int pic1dp_gpu_kiss64_uniforms(pic1dp_gpu_t *h, const uint64_t seeds[4], int64_t offset, int64_t n, double *out) {
+  if (!h || !seeds || offset < 0 || n < 0 || !out) { if (h) h->err = "kiss64_uniforms: bad argument"; return PIC1DP_EINVAL; }
+  if (n == 0) return PIC1DP_OK;
+  CK(cudaSetDevice(h->p.device));
+  double *d = nullptr;
+  CK(cudaMalloc(&d, (size_t)n * 8));
+  int rc = kiss64_fill_device(h, seeds, offset, n, d);
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    e = cudaMemcpyAsync(out, d, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    h->d2h += n * 8;
+  }
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) { h->err = std::string("kiss64_uniforms: ") + cudaGetErrorString(e); return PIC1DP_ECUDA; }
+  return PIC1DP_OK;
+}
+
+// the same generator on the host (no GPU): what a host does to keep its own multirand state in step with the numbers
+// the device consumed, and what the CPU tests use to check the jump tables
+int pic1dp_host_kiss64_jump(uint64_t seeds[4], int64_t n) {
+  if (!seeds || n < 0) return PIC1DP_EINVAL;
+  Kiss64 s = {seeds[0], seeds[1], seeds[2], seeds[3]};
+  kiss64_jump_host(s, (uint64_t)n);
+  seeds[0] = s.x; seeds[1] = s.xs; seeds[2] = s.z; seeds[3] = s.c;
+  return PIC1DP_OK;
+}
+
+int pic1dp_host_kiss64_fill(uint64_t seeds[4], int64_t n, double *out) {
+  if (!seeds || n < 0 || (n > 0 && !out)) return PIC1DP_EINVAL;
+  Kiss64 s = {seeds[0], seeds[1], seeds[2], seeds[3]};
+  for (int64_t i = 0; i < n; i++) out[i] = int2real64(kiss64_next(s));
+  seeds[0] = s.x; seeds[1] = s.xs; seeds[2] = s.z; seeds[3] = s.c;
+  return PIC1DP_OK;
+}
+
+void pic1dp_host_counter_uniforms(uint64_t seed, int32_t stream, int64_t first_index, int64_t n, double *u_v, double *u_x) {
+  for (int64_t i = 0; i < n; i++) counter_uniforms(seed, (uint32_t)stream, (uint64_t)(first_index + i), u_v[i], u_x[i]);
 }
 
 int pic1dp_gpu_load_markers(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t nparticle_init, const double *rand_v,
@@ -782,14 +936,15 @@ static void fill_grid_args(pic1dp_gpu_t *h, GridArgs &g) {
   g.a_re = 1.0 / (double)p.nx;
   g.nx_over_lx = (double)p.nx / p.lx;
   g.energy = h->d_energy;
-  if (p.nranks > 1 && h->p2p_ready) {  // current all-reduce epoch (advanced by reduce_charge)
+  if (p.nranks > 1 && h->p2p_ready) {
     g.p2p_nranks = p.nranks;
     g.p2p_rank = p.rank;
-    g.p2p_epoch = h->p2p_epoch;
-    g.p2p_parity = (int)(h->p2p_epoch & 1);
     for (int r = 0; r < p.nranks; r++) g.p2p_peer[r] = h->peer_base[r];
     g.p2p_counter = h->d_p2p_counter;
     g.p2p_timeouts = h->d_p2p_timeouts;
+    g.p2p_epoch_dev = h->d_p2p_epoch;
+    g.p2p_stamps = h->d_p2p_stamps;
+    g.p2p_stamp_cap = h->p2p_stamp_cap;
   }
 }
 
@@ -881,7 +1036,6 @@ int pic1dp_gpu_get_shape_x(pic1dp_gpu_t *h, int32_t isp, int32_t *indexes, doubl
 
 // sum of the private grids (+ species charge), all-reduce over ranks, optionally rho = ... (k_finalize_rho)
 static int reduce_charge(pic1dp_gpu_t *h, bool finalize) {
-  if (h->p.nranks > 1 && h->p2p_ready) h->p2p_epoch++;  // a new all-reduce
   GridArgs g;
   fill_grid_args(h, g);
   k_reduce_charge<<<(h->p.nx + 31) / 32, 256, 0, h->stream>>>(g);
@@ -1029,21 +1183,95 @@ int pic1dp_gpu_launch_timing_stop(pic1dp_gpu_t *h, double ms_sum[2], int64_t lau
   return PIC1DP_OK;
 }
 
-int pic1dp_gpu_step(pic1dp_gpu_t *h, int32_t nsteps) {
-  if (!h || nsteps < 0) return PIC1DP_EINVAL;
-  for (int it = 0; it < nsteps; it++)
-    for (int irk = 1; irk <= 2; irk++) {  // src/pic1dp.F90:79-90
-      int rc = pic1dp_gpu_push(h, irk);
-      if (rc) return rc;
-      if (h->p.iptclshape < 4) {
-        rc = pic1dp_gpu_compute_shape_x(h);
-        if (rc) return rc;
-      }
-      rc = collect_charge_impl(h, false);   // rho is formed inside the solve kernel: one launch less
-      if (rc) return rc;
-      rc = solve_field_impl(h, true);
+// one timestep with individual launches: src/pic1dp.F90:79-90
+static int step_direct(pic1dp_gpu_t *h) {
+  for (int irk = 1; irk <= 2; irk++) {
+    int rc = pic1dp_gpu_push(h, irk);
+    if (rc) return rc;
+    if (h->p.iptclshape < 4) {
+      rc = pic1dp_gpu_compute_shape_x(h);
       if (rc) return rc;
     }
+    rc = collect_charge_impl(h, false);   // rho is formed inside the solve kernel: one launch less
+    if (rc) return rc;
+    rc = solve_field_impl(h, true);
+    if (rc) return rc;
+  }
+  return PIC1DP_OK;
+}
+
+// The launches of one timestep are the same every step: the buffer rotation returns to its starting set after two
+// substeps, and the all-reduce epoch is device-resident.  They are captured once into a CUDA graph and replayed, which
+// removes ~6 launch gaps per step (decisive at the reference's default size, src/pic1dp_input.F90:113).  The graph
+// is re-captured when the marker counts or the rotation differ from the captured ones.
+static bool step_graph_usable(pic1dp_gpu_t *h) {
+  if (!h->graph_enabled || h->lt_on || h->partial_valid || h->p.fuse == 0) return false;
+  if (h->p.nranks > 1 && !h->p2p_ready) return false;   // ncclAllReduce between the kernels stays a direct launch
+  return true;
+}
+
+static bool step_graph_matches(pic1dp_gpu_t *h) {
+  if (!h->step_graph) return false;
+  for (int s = 0; s < h->p.nspecies; s++)
+    if (h->graph_cur[s] != h->sp[s].cur || h->graph_np[s] != h->sp[s].np) return false;
+  return true;
+}
+
+static int step_graph_capture(pic1dp_gpu_t *h) {
+  if (h->step_graph) {
+    cudaGraphExecDestroy(h->step_graph);
+    h->step_graph = nullptr;
+  }
+  const int64_t l0 = h->launches, n0 = h->nccl_calls, p0 = h->p2p_calls;
+  for (int s = 0; s < h->p.nspecies; s++) {
+    h->graph_cur[s] = h->sp[s].cur;
+    h->graph_np[s] = h->sp[s].np;
+  }
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = step_direct(h);   // records the launches; nothing executes
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  h->graph_launches = h->launches - l0;
+  h->graph_nccl = h->nccl_calls - n0;
+  h->graph_p2p = h->p2p_calls - p0;
+  h->launches = l0;
+  h->nccl_calls = n0;
+  h->p2p_calls = p0;
+  if (rc || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (!rc) h->err = std::string("step graph capture: ") + cudaGetErrorString(e);
+    return rc ? rc : PIC1DP_ECUDA;
+  }
+  const cudaError_t e2 = cudaGraphInstantiate(&h->step_graph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess) {
+    h->step_graph = nullptr;
+    h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2);
+    return PIC1DP_ECUDA;
+  }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_step(pic1dp_gpu_t *h, int32_t nsteps) {
+  if (!h || nsteps < 0) return PIC1DP_EINVAL;
+  if (nsteps == 0) return PIC1DP_OK;
+  int rc = check_loaded(h, "step");
+  if (rc) return rc;
+  CK(cudaSetDevice(h->p.device));
+  if (step_graph_usable(h)) {
+    if (!step_graph_matches(h) && (rc = step_graph_capture(h))) return rc;
+    for (int it = 0; it < nsteps; it++) {
+      CK(cudaGraphLaunch(h->step_graph, h->stream));
+      h->launches += h->graph_launches;
+      h->nccl_calls += h->graph_nccl;
+      h->p2p_calls += h->graph_p2p;
+      h->graph_replays++;
+    }
+    return PIC1DP_OK;   // the rotation is back at the captured set after a whole step
+  }
+  for (int it = 0; it < nsteps; it++)
+    if ((rc = step_direct(h))) return rc;
   return PIC1DP_OK;
 }
 
@@ -1080,8 +1308,9 @@ int pic1dp_gpu_get_field(pic1dp_gpu_t *h, double *electric, double *chargeden, d
   if (chargeden) { CK(cudaMemcpyAsync(chargeden, h->d_rho, nb, cudaMemcpyDeviceToHost, h->stream)); h->d2h += nb; }
   if (mode_re) { CK(cudaMemcpyAsync(mode_re, h->d_mre, mb, cudaMemcpyDeviceToHost, h->stream)); h->d2h += mb; }
   if (mode_im) { CK(cudaMemcpyAsync(mode_im, h->d_mim, mb, cudaMemcpyDeviceToHost, h->stream)); h->d2h += mb; }
+  p2p_queue_timeout_read(h);
   CK(cudaStreamSynchronize(h->stream));
-  return PIC1DP_OK;
+  return p2p_check_timeouts(h, "get_field");
 }
 
 int pic1dp_gpu_set_field(pic1dp_gpu_t *h, const double *electric, const double *chargeden) {
@@ -1112,9 +1341,10 @@ int pic1dp_gpu_field_energy(pic1dp_gpu_t *h, double *energy) {
   k_field_energy<<<1, 1024, 0, h->stream>>>(g);
   CKL(h);
   CK(cudaMemcpyAsync(energy, h->d_energy, 8, cudaMemcpyDeviceToHost, h->stream));
+  p2p_queue_timeout_read(h);
   CK(cudaStreamSynchronize(h->stream));
   h->d2h += 8;
-  return PIC1DP_OK;
+  return p2p_check_timeouts(h, "field_energy");
 }
 
 static int allreduce_inplace(pic1dp_gpu_t *h, double *buf, size_t count) {
@@ -1184,7 +1414,9 @@ int pic1dp_gpu_output_field(pic1dp_gpu_t *h, double *scalars) {
   double sums[3 * PIC1DP_MAX_SPECIES];
   CK(cudaMemcpyAsync(sums, h->d_diag_sums, (size_t)3 * p.nspecies * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(&scalars[0], h->d_energy, 8, cudaMemcpyDeviceToHost, h->stream));
+  p2p_queue_timeout_read(h);
   CK(cudaStreamSynchronize(h->stream));
+  if ((rc = p2p_check_timeouts(h, "output_field"))) return rc;
   h->d2h += 8 + 3 * p.nspecies * 8;
   for (int s = 0; s < p.nspecies; s++) {
     const double vv = sums[3 * s], vvp = sums[3 * s + 1], vvw = sums[3 * s + 2];
@@ -1455,11 +1687,44 @@ int64_t pic1dp_host_particle_split(int64_t np, int64_t capacity, double *x, doub
   return hostopt::split(m, np, capacity, dist, nv, v_max, thsh, ngroup, dv_sig_frac, deltaf, gauss, rng_ctx);
 }
 
+int pic1dp_gpu_p2p_trace(pic1dp_gpu_t *h, int32_t capacity) {
+  if (!h || capacity < 0 || capacity > (1 << 20)) return PIC1DP_EINVAL;
+  if (!h->p2p_ready) { h->err = "p2p_trace: the peer-memory all-reduce is not set up"; return PIC1DP_ESTATE; }
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->d_p2p_stamps) cudaFree(h->d_p2p_stamps);
+  h->d_p2p_stamps = nullptr;
+  h->p2p_stamp_cap = 0;
+  if (h->step_graph) {  // the captured kernels hold the old trace pointer
+    cudaGraphExecDestroy(h->step_graph);
+    h->step_graph = nullptr;
+  }
+  if (capacity > 0) {
+    CK(cudaMalloc(&h->d_p2p_stamps, (size_t)capacity * 3 * 8));
+    CK(cudaMemset(h->d_p2p_stamps, 0, (size_t)capacity * 3 * 8));
+    h->p2p_stamp_cap = capacity;
+  }
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_p2p_trace_read(pic1dp_gpu_t *h, uint64_t *stamps, int64_t *last_epoch) {
+  if (!h || !stamps || !last_epoch) return PIC1DP_EINVAL;
+  if (!h->d_p2p_stamps) { h->err = "p2p_trace_read: tracing is off"; return PIC1DP_ESTATE; }
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaStreamSynchronize(h->stream));
+  unsigned long long ep = 0;
+  CK(cudaMemcpy(&ep, h->d_p2p_epoch, 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(stamps, h->d_p2p_stamps, (size_t)h->p2p_stamp_cap * 3 * 8, cudaMemcpyDeviceToHost));
+  *last_epoch = (int64_t)ep;
+  return PIC1DP_OK;
+}
+
 int pic1dp_gpu_sync(pic1dp_gpu_t *h) {
   if (!h) return PIC1DP_EINVAL;
   CK(cudaSetDevice(h->p.device));
+  p2p_queue_timeout_read(h);
   CK(cudaStreamSynchronize(h->stream));
-  return PIC1DP_OK;
+  return p2p_check_timeouts(h, "sync");
 }
 
 int pic1dp_gpu_timer_start(pic1dp_gpu_t *h) {
@@ -1500,6 +1765,7 @@ int pic1dp_gpu_get_counters(pic1dp_gpu_t *h, pic1dp_counters *c) {
   c->grid_ctas = h->grid;
   c->cta_threads = h->threads;
   c->smem_bytes = h->smem_push;
+  c->graph_replays = h->graph_replays;
   return PIC1DP_OK;
 }
 

@@ -132,6 +132,45 @@ class Pic1dGpu:
         self._ck(self.L.pic1dp_gpu_load_markers(self._h, isp, n, int(nparticle_init), pv, px, float(v_max), nm, im, ic, isn),
                  "load_markers")
 
+    def load_markers_kiss64(self, isp: int, n: int, seeds, offset_v: int, offset_x: int, nparticle_init: int,
+                            v_max: float = 8.0, init_mode=(1,), init_cos=(0.0,), init_sin=(1e-5,)):
+        """Device-side particle_load with the device KISS64 stream (multirand_al_int = 1), bit-exact to multirand.
+        seeds: multirand_seeds(0:3) after multirand_init; offsets: outputs consumed before pv / px of this rank."""
+        nm = len(init_mode)
+        im = (C.c_int32 * nm)(*init_mode)
+        ic = (C.c_double * nm)(*init_cos)
+        isn = (C.c_double * nm)(*init_sin)
+        sd = (C.c_uint64 * 4)(*[int(v) & 0xFFFFFFFFFFFFFFFF for v in seeds])
+        self._ck(self.L.pic1dp_gpu_load_markers_kiss64(self._h, isp, int(n), int(nparticle_init), sd, int(offset_v),
+                                                       int(offset_x), float(v_max), nm, im, ic, isn), "load_markers_kiss64")
+
+    def load_markers_counter(self, isp: int, n: int, seed: int, first_index: int, nparticle_init: int,
+                             v_max: float = 8.0, init_mode=(1,), init_cos=(0.0,), init_sin=(1e-5,)):
+        """Device-side particle_load with the counter-based generator (synthetic markers, no reference stream)."""
+        nm = len(init_mode)
+        im = (C.c_int32 * nm)(*init_mode)
+        ic = (C.c_double * nm)(*init_cos)
+        isn = (C.c_double * nm)(*init_sin)
+        self._ck(self.L.pic1dp_gpu_load_markers_counter(self._h, isp, int(n), int(nparticle_init), int(seed),
+                                                        int(first_index), float(v_max), nm, im, ic, isn),
+                 "load_markers_counter")
+
+    def kiss64_uniforms(self, seeds, offset: int, n: int) -> np.ndarray:
+        sd = (C.c_uint64 * 4)(*[int(v) & 0xFFFFFFFFFFFFFFFF for v in seeds])
+        out = np.empty(n)
+        self._ck(self.L.pic1dp_gpu_kiss64_uniforms(self._h, sd, int(offset), int(n), _dp(out)), "kiss64_uniforms")
+        return out
+
+    def p2p_trace(self, capacity: int):
+        self._ck(self.L.pic1dp_gpu_p2p_trace(self._h, int(capacity)), "p2p_trace")
+
+    def p2p_trace_read(self, capacity: int):
+        buf = np.zeros(capacity * 3, dtype=np.uint64)
+        ep = C.c_int64()
+        self._ck(self.L.pic1dp_gpu_p2p_trace_read(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(ep)),
+                 "p2p_trace_read")
+        return buf.reshape(capacity, 3), ep.value
+
     def load_markers_maxwellian(self, isp: int, gauss_v, rand_x, nparticle_init: int, init_mode=(1,), init_cos=(0.0,),
                                 init_sin=(1e-5,)):
         """Device-side particle_load for input_imarker = 1 (Gaussian v stream, iptcldist = 0)."""
@@ -460,3 +499,29 @@ class Pic1dpModules:
 
     def interaction_push_particle(self):
         self._call(self.gpu.push, self.global_irk)
+
+
+# ---- host-side generator helpers (no GPU): the same code the device runs ----
+def host_kiss64_jump(seeds, n: int):
+    """multirand_seeds(0:3) advanced by n outputs (O(log n) table steps)."""
+    sd = (C.c_uint64 * 4)(*[int(v) & 0xFFFFFFFFFFFFFFFF for v in seeds])
+    rc = _capi.load().pic1dp_host_kiss64_jump(sd, int(n))
+    if rc:
+        raise Pic1dpError(rc, "pic1dp_host_kiss64_jump", "bad argument")
+    return [int(v) for v in sd]
+
+
+def host_kiss64_fill(seeds, n: int):
+    """(n uniforms of multirand_real_array, state afterwards)."""
+    sd = (C.c_uint64 * 4)(*[int(v) & 0xFFFFFFFFFFFFFFFF for v in seeds])
+    out = np.empty(n)
+    rc = _capi.load().pic1dp_host_kiss64_fill(sd, int(n), _dp(out))
+    if rc:
+        raise Pic1dpError(rc, "pic1dp_host_kiss64_fill", "bad argument")
+    return out, [int(v) for v in sd]
+
+
+def host_counter_uniforms(seed: int, stream: int, first_index: int, n: int):
+    u_v, u_x = np.empty(n), np.empty(n)
+    _capi.load().pic1dp_host_counter_uniforms(int(seed), int(stream), int(first_index), int(n), _dp(u_v), _dp(u_x))
+    return u_v, u_x
