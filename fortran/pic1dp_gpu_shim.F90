@@ -17,7 +17,7 @@ implicit none
 private
 
 integer(c_int), parameter, public :: PIC1DP_MAX_SPECIES = 4, PIC1DP_MAX_MODES = 64
-integer(c_int), parameter, public :: PIC1DP_ABI_VERSION = 1
+integer(c_int), parameter, public :: PIC1DP_ABI_VERSION = 2
 
 ! mirrors struct pic1dp_params (include/pic1dp_gpu.h); field order and types must match exactly
 type, bind(c), public :: pic1dp_params

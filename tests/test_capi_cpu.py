@@ -60,7 +60,7 @@ def test_defaults_are_the_reference_input_file(capi):
     assert p.lx == 2.0 * 3.1415926535897932384626 / 0.36 and p.dt == 0.05
     assert (p.charge[0], p.mass[0], p.temperature[0], p.temperature2[0], p.density[0], p.v0[0]) == (-1.0, 1.0, 1.0, 1.0, 0.9, 5.0)
     assert (p.iptcldist, p.deltaf, p.linear, p.iptclshape) == (3, 1, 0, 4)
-    assert p.capacity == 6400000 and capi.pic1dp_gpu_abi_version() == p.abi_version == 1
+    assert p.capacity == 6400000 and capi.pic1dp_gpu_abi_version() == p.abi_version == 2
     assert p.struct_bytes == C.sizeof(P.Params)
 
 
@@ -73,7 +73,7 @@ def test_error_strings(capi):
 @pytest.mark.parametrize("bad", [dict(nx=1), dict(nmode=0), dict(nmode=65), dict(nspecies=5), dict(lx=-1.0),
                                  dict(iptcldist=4), dict(iptclshape=0), dict(linear=1, deltaf=0), dict(capacity=0),
                                  dict(rank=2, nranks=2), dict(mass=[0.0]), dict(modes=[0]), dict(deposit_mode=7),
-                                 dict(abi_version=2)])
+                                 dict(abi_version=1), dict(arith_mode=2)])
 def test_create_rejects_invalid_parameters_before_touching_the_gpu(bad):
     """input_init-style validation (src/pic1dp_input.F90:287-308) -> PIC1DP_EINVAL, no exception across the ABI."""
     import pic1dp_b200 as P
