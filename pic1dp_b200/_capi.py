@@ -14,7 +14,8 @@ UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 
 OK, EINVAL, ECUDA, ENCCL, ENOMEM, ESTATE, ECAPACITY, ENODEVICE, EUNSUPPORTED = range(9)
-DEPOSIT_AUTO, DEPOSIT_SMEM_ATOMIC, DEPOSIT_GLOBAL_RED, DEPOSIT_WARP_PRIVATE = range(4)
+DEPOSIT_AUTO, DEPOSIT_SMEM_ATOMIC, DEPOSIT_GLOBAL_RED, DEPOSIT_WARP_PRIVATE, DEPOSIT_FIXED = range(5)
+ARITH_STRICT, ARITH_TOLERANCE = range(2)
 FIELD_TREE, FIELD_SEQUENTIAL = range(2)
 LOAD_AUTO, LOAD_DIRECT, LOAD_TMA, LOAD_CPASYNC = range(4)
 

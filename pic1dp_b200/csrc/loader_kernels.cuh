@@ -68,6 +68,15 @@ __global__ void __launch_bounds__(256) k_load_markers(const LoadArgs a) {
   }
 }
 
+// high word of max |src[i]| (the scale source of the fixed-point deposit), raised into *out with atomicMax
+__global__ void __launch_bounds__(256) k_absmax_hi(const double *__restrict__ src, const int64_t np, unsigned *out) {
+  unsigned m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, (unsigned)__double2hiint(src[i]) & 0x7fffffffu);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 // weights of the current x, exported for parity checks (particle_shape_x_indexes / _values of iptclshape 3,
 // src/pic1dp_particle.F90:331-332)
 __global__ void __launch_bounds__(256) k_shape_x(const ParticleArgs a, int *ix, double *sl, double *sr) {

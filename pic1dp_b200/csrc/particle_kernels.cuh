@@ -168,6 +168,10 @@ struct ParticleArgs {
   double lx, rlx, rnx, dt; // rlx = RN(1/lx); dt is already halved at irk == 1 (src/pic1dp_interaction.F90:179)
   SpeciesConst c;
   int deltaf, linear, right_frac;
+  // fixed-point deposit (DEP_FIXED): high word of max |deposit source| seen so far for this species (device-resident so
+  // that a captured step graph can be replayed; raised with atomicMax by the kernels), and the overflow counter
+  unsigned *dep_wmax_hi;
+  unsigned long long *dep_overflow;
 };
 
 // ---- periodic wrap: px = mod(px, lx); if (px < 0) px = px + lx  (src/pic1dp_interaction.F90:102-104) ----
@@ -487,10 +491,14 @@ __device__ __forceinline__ void push_n(const ParticleArgs &a, const double *sE, 
 // ------------------------------------------------------------------------------------------------------------
 // Deposit strategies.  Each adds (sl*w) to cell ix and (sr*w) to cell ixr of an on-chip grid.
 // ------------------------------------------------------------------------------------------------------------
-enum { DEP_SMEM_ATOMIC = 1, DEP_GLOBAL_RED = 2, DEP_WARP_PRIVATE = 3 };
+enum { DEP_SMEM_ATOMIC = 1, DEP_GLOBAL_RED = 2, DEP_WARP_PRIVATE = 3, DEP_FIXED = 4 };
 
 template <int DEP>
 struct Depositor;
+
+// every depositor: prescale(q) is applied to the deposit source before the weights (identity except DEP_FIXED)
+#define PIC1DP_DEP_NO_PRESCALE \
+  __device__ __forceinline__ double prescale(double q) { return q; }
 
 // per-CTA shared grid of pairs {sum of left weights landing in cell j, sum of right weights of markers whose LEFT
 // cell is j}: both contributions of a marker go to one 16-byte slot, so one ATOMS.CAS.128 loop replaces two 64-bit
@@ -498,6 +506,7 @@ struct Depositor;
 template <>
 struct Depositor<DEP_SMEM_ATOMIC> {
   double *g;  // pair grid, 2*nx doubles
+  PIC1DP_DEP_NO_PRESCALE
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     (void)ixr;
     if (!valid) return;
@@ -525,6 +534,7 @@ struct Depositor<DEP_SMEM_ATOMIC> {
 template <>
 struct Depositor<DEP_GLOBAL_RED> {
   double *g;
+  PIC1DP_DEP_NO_PRESCALE
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     if (valid) {
       atomicAdd(&g[ix], a);  // result unused -> REDG.E.ADD.F64
@@ -540,6 +550,7 @@ struct Depositor<DEP_GLOBAL_RED> {
 template <>
 struct Depositor<DEP_WARP_PRIVATE> {
   double *g;  // this warp's grid
+  PIC1DP_DEP_NO_PRESCALE
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
@@ -563,6 +574,103 @@ struct Depositor<DEP_WARP_PRIVATE> {
   }
 };
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fixed-point deposit: bitwise reproducible for every grid the pair layout fits (nx <= ~9600), at the speed of the
+// 128-bit CAS deposit.  Same {left, right} pair slots, but the contributions are converted to 64-bit integers
+// (value * 2^e, round to nearest) and added as integers inside the CAS loop: integer addition is associative, so the
+// slot sums do not depend on the order in which the warps arrive.  The reference's own deposit is sequential, hence
+// deterministic (src/pic1dp_interaction.F90:96-114); this is the order-independent counterpart.
+//   scale   : 2^e with e chosen per launch from the running maximum of |deposit source| (max|w| so far, kept on the
+//             device) so that a contribution is below 2^47 with >= 4x headroom for growth within the substep;
+//             quantum = 2^-e <= 2^-45 max|w|: the rounding of one contribution is ~3e-14 max|w|, far below the
+//             summation-order noise of fp64 accumulation and 1e-12 of max|rho|.
+//   windows : a slot component can receive at most 2*blockDim contributions per tile step, so after
+//             FIXED_WINDOW = 2^16 / (2*blockDim) tile steps (|sum| < 2^63) the CTA flushes its integer grid -- exact
+//             int64 sums converted to double, descaled (exact power of two) and accumulated into the CTA's private
+//             global grid in window order.  Windows cover fixed marker sets (static tile -> CTA mapping), so the
+//             whole chain marker -> slot -> window -> CTA grid -> reduce kernel is order-independent or fixed-order.
+//   overflow: |source| >= 2^51 / 2^e (growth by > 64x inside one substep) cannot be converted; it is counted in
+//             dep_overflow and reported by the next synchronising call.
+// ------------------------------------------------------------------------------------------------------------
+template <>
+struct Depositor<DEP_FIXED> {
+  double *g;      // pair grid, 2*nx int64 viewed as doubles by dep_setup
+  double scale;   // 2^e
+  double inv;     // 2^-e
+  unsigned bound_hi;  // high word of 2^51 / 2^e: sources at or above it overflow the conversion
+  unsigned seen_hi;   // high word of the largest |source| this thread has deposited
+  __device__ __forceinline__ double prescale(double q) {
+    seen_hi = max(seen_hi, (unsigned)__double2hiint(q) & 0x7fffffffu);
+    return dmul(q, scale);  // exact (power of two)
+  }
+  // a, b = weight * prescaled source: RN(weight * source) * 2^e exactly, then rounded to the nearest integer
+  __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
+    (void)ixr;
+    if (!valid) return;
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: the integer lands in the low mantissa bits
+    const long long ia = __double_as_longlong(dadd(a, magic)) - __double_as_longlong(magic);
+    const long long ib = __double_as_longlong(dadd(b, magic)) - __double_as_longlong(magic);
+    longlong2 *slot = reinterpret_cast<longlong2 *>(g) + ix;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
+    longlong2 old = *slot;
+    for (;;) {
+      const unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
+      const unsigned long long d0 = e0 + (unsigned long long)ia, d1 = e1 + (unsigned long long)ib;
+      unsigned long long f0, f1;
+      asm volatile(
+          "{\n\t.reg .b128 c, d, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
+          "atom.shared.cas.b128 o, [%6], c, d;\n\tmov.b128 {%0, %1}, o;\n\t}"
+          : "=l"(f0), "=l"(f1)
+          : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "r"(addr)
+          : "memory");
+      if (f0 == e0 && f1 == e1) break;
+      old.x = (long long)f0;
+      old.y = (long long)f1;
+    }
+  }
+};
+
+// scale of this launch from the running maximum (high word of max|source|): source bound 2^(E+3) with E the unbiased
+// exponent of the maximum (>= 4x headroom), contribution * 2^e < 2^47
+__device__ __forceinline__ void fixed_scale(Depositor<DEP_FIXED> &dep, const unsigned wmax_hi) {
+  int ex = (int)((wmax_hi >> 20) & 0x7ff);   // biased exponent of the maximum
+  if (ex < 100) ex = 100;                     // all-zero / denormal sources: any scale works, keep 2^e finite
+  const int se = 2090 - ex;                   // biased exponent of 2^e, e = 47 - (ex - 1023 + 3)
+  dep.seen_hi = 0;
+  dep.scale = __hiloint2double(se << 20, 0);
+  dep.inv = __hiloint2double((2046 - se) << 20, 0);
+  dep.bound_hi = (unsigned)((1023 + 51 - (se - 1023)) << 20);
+}
+
+// end of the kernel: publish the largest source seen (the next launch scales by it) and count conversion overflows
+__device__ __forceinline__ void fixed_finish(const Depositor<DEP_FIXED> &dep, unsigned *wmax_hi, unsigned long long *overflow) {
+  const unsigned m = __reduce_max_sync(0xffffffffu, dep.seen_hi);
+  if ((threadIdx.x & 31) == 0) {
+    if (m) atomicMax(wmax_hi, m);
+    if (m >= dep.bound_hi) atomicAdd(overflow, 1ULL);
+  }
+}
+
+// tile steps between two flushes of the integer grid: 2^16 contributions of < 2^47 stay below 2^63
+__device__ __forceinline__ int fixed_window(void) { return (1 << 16) / (2 * (int)blockDim.x); }
+
+// flush of the integer pair grid into the CTA's global grid (store on the first window, accumulate afterwards) and
+// clearing for the next window; called by every thread of the CTA
+__device__ __forceinline__ void fixed_flush(double *pairs, int nx, double *my_partial, const double inv, const bool first) {
+  __syncthreads();
+  const longlong2 *sl = reinterpret_cast<const longlong2 *>(pairs);
+  for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+    const int jl = (j == 0) ? nx - 1 : j - 1;  // right weights of the cell to the left (periodic, :111-112)
+    const long long sum = sl[j].x + sl[jl].y;  // exact
+    const double val = dmul((double)sum, inv);
+    my_partial[j] = first ? val : dadd(my_partial[j], val);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * nx; j += blockDim.x) pairs[j] = 0.0;
+  __syncthreads();
+}
+
 // Marker arrays are touched once per substep.  Measured on B200 (profiles/r01_ab_experiments.md): the default cache
 // policy beats the streaming hints (.cs evict-first loads/stores cost ~3% of the step; .cg is on par with default).
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
@@ -576,8 +684,8 @@ __device__ __forceinline__ void prefetch_l2(const double *p) { asm volatile("pre
 // (16-byte alignment of the pair grid for the 128-bit CAS)
 template <int DEP>
 __device__ __forceinline__ double *dep_setup(double *smem_after_E, int nx, double *my_partial) {
-  if (DEP == DEP_SMEM_ATOMIC) {
-    for (int j = threadIdx.x; j < 2 * nx; j += blockDim.x) smem_after_E[j] = 0.0;
+  if (DEP == DEP_SMEM_ATOMIC || DEP == DEP_FIXED) {
+    for (int j = threadIdx.x; j < 2 * nx; j += blockDim.x) smem_after_E[j] = 0.0;   // +0.0 is integer 0 as well
     return smem_after_E;
   } else if (DEP == DEP_WARP_PRIVATE) {
     const int nw = blockDim.x >> 5;
@@ -647,7 +755,7 @@ __device__ __forceinline__ bool push_pair_fast(const ParticleArgs &a, const doub
   }
   if (FUSED) {
     // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
-    const double q0 = deltaf ? awo[0] : p.x, q1 = deltaf ? awo[1] : p.y;
+    const double q0 = dep.prescale(deltaf ? awo[0] : p.x), q1 = dep.prescale(deltaf ? awo[1] : p.y);
     dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0), !rare);  // :110, :113
     dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
     noob += (!rare && od[0]) + (!rare && od[1]);
@@ -713,7 +821,7 @@ __device__ __forceinline__ void push_pair_slow(const ParticleArgs &a, const doub
     if (deltaf) st1(a.w_out + i, wo.x);
   }
   if (FUSED) {
-    const double q0 = deltaf ? wo.x : p.x, q1 = deltaf ? wo.y : p.y;
+    const double q0 = dep.prescale(deltaf ? wo.x : p.x), q1 = dep.prescale(deltaf ? wo.y : p.y);
     dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0), v0ok);  // :110, :113
     dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), v1ok);
     noob += (v0ok && od[0]) + (v1ok && od[1]);
@@ -754,10 +862,13 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   double *my_partial = FUSED ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
   Depositor<DEP> dep;
   dep.g = FUSED ? dep_setup<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial) : nullptr;
+  if constexpr (DEP == DEP_FIXED) fixed_scale(dep, FUSED ? *a.dep_wmax_hi : 0u);
   __syncthreads();
 
   const int64_t tile = (int64_t)blockDim.x * 2;
   unsigned long long noob = 0;
+  int win = 0;          // DEP_FIXED: tile steps since the last flush of the integer grid
+  bool win_first = true;
   const bool deltaf_pf = Cfg<CFG>::deltaf(a.deltaf);
   // register-staged v of the next tile step: the fast body starts with the v-only work (both exponentials), so v is
   // the one load whose latency nothing hides; it is issued one iteration ahead (4 registers)
@@ -799,8 +910,20 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
       redo = push_pair_fast<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
     }
     push_pair_redo<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, redo);
+    if constexpr (DEP == DEP_FIXED && FUSED) {
+      if (++win == fixed_window()) {  // CTA-uniform: the loop bounds depend on blockIdx only
+        fixed_flush(smem + ((a.nx + 1) & ~1), a.nx, my_partial, dep.inv, win_first);
+        win = 0;
+        win_first = false;
+      }
+    }
   }
-  if (FUSED) dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
+  if constexpr (DEP == DEP_FIXED && FUSED) {
+    fixed_flush(smem + ((a.nx + 1) & ~1), a.nx, my_partial, dep.inv, win_first);
+    fixed_finish(dep, a.dep_wmax_hi, a.dep_overflow);
+  } else if (FUSED) {
+    dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
+  }
   if (FUSED && noob) atomicAdd(a.noob, noob);
 }
 
@@ -1006,9 +1129,12 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
   double *my_partial = DEPOSIT ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
   Depositor<DEP> dep;
   dep.g = DEPOSIT ? dep_setup<DEP>(smem, a.nx, my_partial) : nullptr;
+  if constexpr (DEP == DEP_FIXED) fixed_scale(dep, DEPOSIT ? *a.dep_wmax_hi : 0u);  // set by k_absmax_hi before this launch
   __syncthreads();
   const int64_t tile = (int64_t)blockDim.x * 2;
   unsigned long long noob = 0;
+  int win = 0;
+  bool win_first = true;
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
     const bool v0ok = i < a.np, v1ok = i + 1 < a.np;
@@ -1029,14 +1155,27 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
     }
     if (DEPOSIT) {
       bool o0 = false, o1 = false;
+      const double q0 = dep.prescale(q.x), q1 = dep.prescale(q.y);
       const Shape s0 = shape_of(xw.x, a.lx, a.rlx, a.rnx, a.nx, a.right_frac, o0);
-      dep.add(s0.ix, s0.ixr, dmul(s0.sl, q.x), dmul(s0.sr, q.x), v0ok);
+      dep.add(s0.ix, s0.ixr, dmul(s0.sl, q0), dmul(s0.sr, q0), v0ok);
       const Shape s1 = shape_of(xw.y, a.lx, a.rlx, a.rnx, a.nx, a.right_frac, o1);
-      dep.add(s1.ix, s1.ixr, dmul(s1.sl, q.y), dmul(s1.sr, q.y), v1ok);
+      dep.add(s1.ix, s1.ixr, dmul(s1.sl, q1), dmul(s1.sr, q1), v1ok);
       noob += (v0ok && o0) + (v1ok && o1);
+      if constexpr (DEP == DEP_FIXED) {
+        if (++win == fixed_window()) {
+          fixed_flush(smem, a.nx, my_partial, dep.inv, win_first);
+          win = 0;
+          win_first = false;
+        }
+      }
     }
   }
-  if (DEPOSIT) dep_flush<DEP>(smem, a.nx, my_partial);
+  if constexpr (DEP == DEP_FIXED && DEPOSIT) {
+    fixed_flush(smem, a.nx, my_partial, dep.inv, win_first);
+    fixed_finish(dep, a.dep_wmax_hi, a.dep_overflow);
+  } else if (DEPOSIT) {
+    dep_flush<DEP>(smem, a.nx, my_partial);
+  }
   if (DEPOSIT && noob) atomicAdd(a.noob, noob);
 }
 

@@ -100,6 +100,7 @@ struct Species {
   int bak = 0;       // buffer set holding the start-of-step state (valid between irk=1 and irk=2)
   int64_t np = 0;
   bool loaded = false;
+  bool wmax_valid = false;   // d_wmax_hi[s] covers the current deposit source (fixed-point deposit)
   SpeciesConst c;
 };
 
@@ -118,6 +119,8 @@ struct pic1dp_gpu {
   double *d_partial = nullptr, *d_red = nullptr, *d_energy = nullptr;
   void *d_kiss_tab = nullptr;   // KissTables: jump-ahead tables of the device KISS64 (allocated on first use)
   unsigned long long *d_noob = nullptr;
+  unsigned *d_wmax_hi = nullptr;              // [species] running max |deposit source| (high words), DEP_FIXED
+  unsigned long long *d_dep_overflow = nullptr, *h_dep_overflow = nullptr;  // conversion overflows (+ pinned mirror)
   std::vector<double> h_Fre, h_Fim, h_ginv;
   // diagnostics scratch (allocated on first use)
   double *d_diag_part = nullptr, *d_diag_sums = nullptr, *d_hist = nullptr, *d_hist_out = nullptr;
@@ -234,12 +237,15 @@ static PushKernel pick_deposit(int dep, bool deposit) {
   switch (dep) {
     case DEP_SMEM_ATOMIC: return k_deposit<DEP_SMEM_ATOMIC, true>;
     case DEP_GLOBAL_RED: return k_deposit<DEP_GLOBAL_RED, true>;
+    case DEP_FIXED: return k_deposit<DEP_FIXED, true>;
     default: return k_deposit<DEP_WARP_PRIVATE, true>;
   }
 }
 
 // shared-memory deposit grids of nx doubles each (the atomic deposit keeps one grid of {left, right} pairs)
-static int dep_grids(int dep, int threads) { return dep == DEP_WARP_PRIVATE ? threads / 32 : (dep == DEP_SMEM_ATOMIC ? 2 : 0); }
+static int dep_grids(int dep, int threads) {
+  return dep == DEP_WARP_PRIVATE ? threads / 32 : ((dep == DEP_SMEM_ATOMIC || dep == DEP_FIXED) ? 2 : 0);
+}
 
 // ---- public API -----------------------------------------------------------------------------------------
 extern "C" {
@@ -342,6 +348,9 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
     }
   if (h->d_noob) cudaFree(h->d_noob);
   if (h->d_kiss_tab) cudaFree(h->d_kiss_tab);
+  if (h->d_wmax_hi) cudaFree(h->d_wmax_hi);
+  if (h->d_dep_overflow) cudaFree(h->d_dep_overflow);
+  if (h->h_dep_overflow) cudaFreeHost(h->h_dep_overflow);
   for (int r = 0; r < 8; r++)
     if (h->peer_base[r] && h->peer_base[r] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
   if (h->d_xchg) cudaFree(h->d_xchg);
@@ -409,10 +418,9 @@ static int create_impl(pic1dp_gpu_t *h) {
     else
       dep = DEP_GLOBAL_RED;
   }
-  if (dep == DEP_WARP_PRIVATE && warp_private_threads() < 256) {
-    h->err = "WARP_PRIVATE deposit needs one nx-sized shared-memory grid per warp: fewer than 8 warps fit for this nx";
-    return PIC1DP_EUNSUPPORTED;
-  }
+  // the warp-private deposit needs one nx-sized shared-memory grid per warp; when fewer than 8 warps fit (nx >~ 2900)
+  // the request degrades to the other bitwise-deterministic strategy, the fixed-point pair grid, instead of failing
+  if (dep == DEP_WARP_PRIVATE && warp_private_threads() < 256) dep = DEP_FIXED;
   // atomic deposits: one CTA of 1024 threads per SM measured 0.7% faster than 2 x 512 at nx = 1024 (half as many
   // private grids to reduce); small grids keep 2 x 512 to halve the contention on each shared grid
   h->threads = (dep == DEP_WARP_PRIVATE) ? warp_private_threads()
@@ -421,7 +429,7 @@ static int create_impl(pic1dp_gpu_t *h) {
   if (dep != DEP_WARP_PRIVATE &&
       2 * (smem_need(dep, h->threads) + 1024) > (size_t)prop.sharedMemPerMultiprocessor)
     h->threads = PIC1DP_MAXTHREADS;
-  if (p.load_path == PIC1DP_LOAD_TMA && dep != DEP_WARP_PRIVATE && h->threads > 512)
+  if (p.load_path == PIC1DP_LOAD_TMA && dep != DEP_WARP_PRIVATE && dep != DEP_FIXED && h->threads > 512)
     h->threads = 512;  // the TMA-ring kernels are 512-thread CTAs and share the persistent grid with the direct ones
   if (const char *e = getenv("PIC1DP_EXP_THREADS")) {  // experiment hook: CTA size of the atomic-deposit kernels
     const int t = atoi(e);
@@ -451,7 +459,7 @@ static int create_impl(pic1dp_gpu_t *h) {
     // TMA-pipelined variant (2-stage ring of 2*threads markers): usable when it reaches the same residency.
     // load_path TMA uses it for both substeps, AUTO only where it measured faster (profiles/r01_ab_experiments.md).
     h->use_tma[0] = h->use_tma[1] = false;
-    if (h->cfg == 1 && p.load_path != PIC1DP_LOAD_DIRECT && dep != DEP_WARP_PRIVATE && h->threads == 512) {
+    if (h->cfg == 1 && p.load_path != PIC1DP_LOAD_DIRECT && dep != DEP_WARP_PRIVATE && dep != DEP_FIXED && h->threads == 512) {
       const int tthr = 512;
       for (int irk2 = 0; irk2 < 2; irk2++) {
         const size_t ring = (size_t)2 * (irk2 ? 7 : 4) * (2 * tthr) * 8 + 64;
@@ -479,7 +487,7 @@ static int create_impl(pic1dp_gpu_t *h) {
     }
     // cp.async-staged variant: same CTA shape as the direct kernel plus a ring of 2 stages x NARR x threads x 16 B
     h->use_cpa[0] = h->use_cpa[1] = false;
-    if (h->cfg == 1 && (p.load_path == PIC1DP_LOAD_CPASYNC || p.load_path == PIC1DP_LOAD_AUTO)) {
+    if (h->cfg == 1 && dep != DEP_FIXED && (p.load_path == PIC1DP_LOAD_CPASYNC || p.load_path == PIC1DP_LOAD_AUTO)) {
       for (int irk2 = 0; irk2 < 2; irk2++) {
         const size_t ring = (size_t)2 * (irk2 ? 7 : 4) * h->threads * 16;
         const size_t need = 8 * (((size_t)(nx + 1) & ~(size_t)1) + (((size_t)nx * dep_grids(dep, h->threads) + 1) & ~(size_t)1)) + ring;
@@ -539,6 +547,12 @@ static int create_impl(pic1dp_gpu_t *h) {
   CK(cudaMalloc(&h->d_red, (size_t)h->nred * nx * 8));
   CK(cudaMalloc(&h->d_energy, 8));
   CK(cudaMalloc(&h->d_noob, 8));
+  CK(cudaMalloc(&h->d_wmax_hi, PIC1DP_MAX_SPECIES * 4));
+  CK(cudaMemsetAsync(h->d_wmax_hi, 0, PIC1DP_MAX_SPECIES * 4, h->stream));
+  CK(cudaMalloc(&h->d_dep_overflow, 8));
+  CK(cudaMemsetAsync(h->d_dep_overflow, 0, 8, h->stream));
+  CK(cudaMallocHost(&h->h_dep_overflow, 8));
+  *h->h_dep_overflow = 0;
   CK(cudaMemsetAsync(h->d_E, 0, (size_t)nx * 8, h->stream));
   CK(cudaMemsetAsync(h->d_rho, 0, (size_t)nx * 8, h->stream));
   CK(cudaMemsetAsync(h->d_mre, 0, (size_t)M * 8, h->stream));
@@ -663,8 +677,16 @@ int pic1dp_gpu_p2p_import(pic1dp_gpu_t *h, const uint8_t *all_handles) {
 static void p2p_queue_timeout_read(pic1dp_gpu_t *h) {
   if (h->p2p_ready && h->h_p2p_timeouts)
     cudaMemcpyAsync(h->h_p2p_timeouts, h->d_p2p_timeouts, 8, cudaMemcpyDeviceToHost, h->stream);
+  if (h->dep == DEP_FIXED)
+    cudaMemcpyAsync(h->h_dep_overflow, h->d_dep_overflow, 8, cudaMemcpyDeviceToHost, h->stream);
 }
 static int p2p_check_timeouts(pic1dp_gpu_t *h, const char *who) {
+  if (h->dep == DEP_FIXED && *h->h_dep_overflow != 0) {
+    h->err = std::string(who) + ": fixed-point deposit overflow -- the deposit source grew by more than 64x within one "
+             "substep (" + std::to_string(*h->h_dep_overflow) + " warps); rho is invalid.  Use another deposit_mode for "
+             "this input";
+    return PIC1DP_ESTATE;
+  }
   if (h->p2p_ready && h->h_p2p_timeouts && *h->h_p2p_timeouts != 0) {
     h->err = std::string(who) + ": the peer-memory density all-reduce timed out (" + std::to_string(*h->h_p2p_timeouts) +
              " flag waits expired: a peer rank died or never reached the substep); rho and E hold NaN";
@@ -698,6 +720,7 @@ static int upload_species(pic1dp_gpu_t *h, int isp, int64_t np, const double *x,
   CK(cudaStreamSynchronize(h->stream));  // host buffers are only borrowed for the call
   h->h2d += 4 * (int64_t)b;
   S.loaded = true;
+  S.wmax_valid = false;
   return invalidate_partials(h);
 }
 
@@ -756,6 +779,7 @@ static int load_markers_finish(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t
   CKL(h);
   CK(cudaStreamSynchronize(h->stream));  // host buffers are only borrowed for the call
   S.loaded = true;
+  S.wmax_valid = false;
   return invalidate_partials(h);
 }
 
@@ -956,6 +980,8 @@ static void fill_particle_args(pic1dp_gpu_t *h, int s, ParticleArgs &a) {
   a.E = h->d_E;
   a.partial = h->d_partial + (size_t)s * h->grid * p.nx;
   a.noob = h->d_noob;
+  a.dep_wmax_hi = h->d_wmax_hi + s;
+  a.dep_overflow = h->d_dep_overflow;
   a.np = S.np;
   a.nx = p.nx;
   a.lx = p.lx;
@@ -976,8 +1002,29 @@ static int check_loaded(pic1dp_gpu_t *h, const char *who) {
   return PIC1DP_OK;
 }
 
+// fixed-point deposit: the scale of a launch comes from the running maximum of |deposit source| (w for delta-f, p for
+// full-f).  The fused kernels keep it up to date; after the markers were replaced it is recomputed here.
+static int ensure_wmax(pic1dp_gpu_t *h) {
+  if (h->dep != DEP_FIXED) return PIC1DP_OK;
+  for (int s = 0; s < h->p.nspecies; s++) {
+    Species &S = h->sp[s];
+    if (S.wmax_valid || !S.loaded) continue;
+    CK(cudaMemsetAsync(h->d_wmax_hi + s, 0, 4, h->stream));
+    if (S.np > 0) {
+      k_absmax_hi<<<h->nsm * 8, 256, 0, h->stream>>>(h->p.deltaf ? S.w[S.cur] : S.p, S.np, h->d_wmax_hi + s);
+      CKL(h);
+    }
+    S.wmax_valid = true;
+  }
+  return PIC1DP_OK;
+}
+
 // wrap (+ deposit) pass over all species
 static int run_deposit_pass(pic1dp_gpu_t *h, bool deposit) {
+  if (deposit) {
+    const int rc = ensure_wmax(h);
+    if (rc) return rc;
+  }
   PushKernel k = pick_deposit(h->dep, deposit);
   for (int s = 0; s < h->p.nspecies; s++) {
     Species &S = h->sp[s];
@@ -1102,6 +1149,7 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
   CK(cudaSetDevice(h->p.device));
   const pic1dp_params &p = h->p;
   const bool fused = p.fuse != 0;
+  if (fused && (rc = ensure_wmax(h))) return rc;
   if (fused && h->partial_valid && h->dep == DEP_GLOBAL_RED)  // a previous fused deposit was never collected
     CK(cudaMemsetAsync(h->d_partial, 0, (size_t)p.nspecies * h->grid * p.nx * 8, h->stream));
   for (int s = 0; s < p.nspecies; s++) {
@@ -1259,6 +1307,7 @@ int pic1dp_gpu_step(pic1dp_gpu_t *h, int32_t nsteps) {
   int rc = check_loaded(h, "step");
   if (rc) return rc;
   CK(cudaSetDevice(h->p.device));
+  if ((rc = ensure_wmax(h))) return rc;   // outside the captured graph
   if (step_graph_usable(h)) {
     if (!step_graph_matches(h) && (rc = step_graph_capture(h))) return rc;
     for (int it = 0; it < nsteps; it++) {

@@ -15,6 +15,7 @@ PushKernel pick_dep(int dep) {
   switch (dep) {
     case DEP_SMEM_ATOMIC: return k_push<DIST, IRK2, DEP_SMEM_ATOMIC, true, CFG>;
     case DEP_GLOBAL_RED: return k_push<DIST, IRK2, DEP_GLOBAL_RED, true, CFG>;
+    case DEP_FIXED: return k_push<DIST, IRK2, DEP_FIXED, true, CFG>;
     default: return k_push<DIST, IRK2, DEP_WARP_PRIVATE, true, CFG>;
   }
 }

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_SUM = 1e-12   # rho, E, modes: relative to max|.|
 TOL_W = 1e-14     # w after one substep, relative to max|w|
-DEPOSITS = [P.DEPOSIT_SMEM_ATOMIC, P.DEPOSIT_GLOBAL_RED, P.DEPOSIT_WARP_PRIVATE]
+DEPOSITS = [P.DEPOSIT_SMEM_ATOMIC, P.DEPOSIT_GLOBAL_RED, P.DEPOSIT_WARP_PRIVATE, P.DEPOSIT_FIXED]
 
 
 def _gpu(gp):
@@ -540,7 +540,7 @@ def test_randomized_configurations_two_steps():
         nx = int(rng.choice([2, 7, 64, 192, 333, 1024, 2048]))
         nmode = int(rng.integers(1, 4)) if nx >= 16 else 1
         modes = sorted(rng.choice(np.arange(1, max(2, min(9, nx // 2 + 1))), size=nmode, replace=False).tolist())
-        dep = int(rng.choice([P.DEPOSIT_AUTO, P.DEPOSIT_SMEM_ATOMIC, P.DEPOSIT_GLOBAL_RED, P.DEPOSIT_WARP_PRIVATE]))
+        dep = int(rng.choice([P.DEPOSIT_AUTO, P.DEPOSIT_SMEM_ATOMIC, P.DEPOSIT_GLOBAL_RED, P.DEPOSIT_WARP_PRIVATE, P.DEPOSIT_FIXED]))
         n = int(rng.choice([1, 33, 1000, 4097, 20001]))
         kw = dict(nx=nx, nmode=nmode, modes=modes, iptcldist=dist, deltaf=deltaf, linear=linear,
                   iptclshape=int(rng.choice([1, 2, 3, 4])), deposit_mode=dep, fuse=int(rng.integers(0, 2)),
