@@ -134,9 +134,13 @@ template <int CFG> struct Cfg {
   static __device__ __forceinline__ bool deltaf(const int a) { return CFG < 0 ? a != 0 : (CFG & 1) != 0; }
   static __device__ __forceinline__ bool linear(const int a) { return CFG < 0 ? a != 0 : (CFG & 2) != 0; }
   static __device__ __forceinline__ bool right_frac(const int a) { return CFG < 0 ? a != 0 : (CFG & 4) != 0; }
-  static __device__ __forceinline__ bool pow2(const int a) { return CFG < 0 ? a != 0 : (CFG & 8) != 0; }
+  // (the TOLERANCE configurations keep this switch at run time: only the strict v update still divides by m)
+  static __device__ __forceinline__ bool pow2(const int a) { return (CFG < 0 || (CFG & 32)) ? a != 0 : (CFG & 8) != 0; }
   // bit 4 (with bit 3): T/m = T2/m = m = T = 1, so x / c == x for those divisors and only 2T/m = 2 remains
   static constexpr bool unit = CFG >= 0 && (CFG & 16) != 0;
+  // bit 5: PIC1DP_ARITH_TOLERANCE -- the w path (tmp2 and the w update) in the algebraically reduced form below;
+  // index, weights, gather, x and v keep the reference's operation order
+  static constexpr bool tol = CFG >= 0 && (CFG & 32) != 0;
 };
 
 // Per-species constants, all evaluated on the host in IEEE double exactly as the Fortran compiler folds them.
@@ -150,6 +154,10 @@ struct SpeciesConst {
   double i_m, i_T, i_Tm, i_T2m, i_twoTm, i_twoT2m, i_sqTm, i_sqT2m;
   int pow2;  // every divisor above is a power of two
   int unit;  // m = T = T/m = T2/m = 1 (so 2T/m = 2T2/m = 2)
+  // PIC1DP_ARITH_TOLERANCE constants (host-evaluated): bump-on-tail tmp2 = (A v + B (v - v0) r) / (C + D r) with
+  // r = exp(v^2 h1 - (v - v0)^2 h2); two-stream2 tmp2 = (vp + vm r) / (1 + r) * mT with r = exp(v k2)
+  double tolA, tolB, tolC, tolD, tolh1, tolh2, tolk2, tolmT;
+  double Zm;  // Z / m
 };
 
 struct ParticleArgs {
@@ -444,6 +452,62 @@ __device__ __forceinline__ void dlnf0_impl_n(const SpeciesConst &c, const double
 #undef DIVC
 }
 
+// a / b without the correctly-rounded guarantee (<= ~1 ulp): reciprocal seed, two Newton steps, one residual correction.
+// TOLERANCE arithmetic only; operands far outside the normal range still raise the flag.
+template <int N>
+__device__ __forceinline__ void div_fast_n(const double (&a)[N], const double (&b)[N], double (&q)[N], bool &rare) {
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const unsigned eb = (unsigned)(__double2hiint(b[k]) & 0x7ff00000) - (523u << 20);
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b[k]));
+    double e = fma(-b[k], y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-b[k], y, 1.0);
+    y = fma(y, e, y);
+    const double q0 = a[k] * y;
+    q[k] = fma(fma(-q0, b[k], a[k]), y, q0);
+    rare = rare | (eb >= (1000u << 20)) | !(b[k] > 0.0);
+  }
+}
+
+// -d ln f0 / dv in PIC1DP_ARITH_TOLERANCE: numerator and denominator of src/pic1dp_interaction.F90:294-321 (bump-on-
+// tail) / :278-292 (two-stream2) divided through by the first exponential, so that ONE exponential of the difference
+// of the two arguments remains; all constant divisors are folded into host-evaluated coefficients and the sums are
+// fused multiply-adds.  Algebraically identical to the reference expression; differs from it by a few ulp.
+template <int DIST, int N>
+__device__ __forceinline__ void dlnf0_tol_n(const SpeciesConst &c, const double (&v)[N], double (&out)[N], bool &rare) {
+  double nd[N], r[N], num[N], den[N];
+  if (DIST == 3) {
+    double vm[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      vm[k] = v[k] - c.v0;
+      nd[k] = fma(vm[k] * vm[k], c.tolh2, -(v[k] * v[k]) * c.tolh1);  // -(v^2 h1 - vm^2 h2)
+    }
+    exp_fast_neg_n<N>(nd, r, rare);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      num[k] = fma(c.tolB * vm[k], r[k], c.tolA * v[k]);
+      den[k] = fma(c.tolD, r[k], c.tolC);
+    }
+    div_fast_n<N>(num, den, out, rare);
+  } else {  // DIST == 2
+#pragma unroll
+    for (int k = 0; k < N; k++) nd[k] = -(v[k] * c.tolk2);
+    exp_fast_neg_n<N>(nd, r, rare);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      num[k] = fma(v[k] - c.v0, r[k], v[k] + c.v0);
+      den[k] = r[k] + 1.0;
+    }
+    div_fast_n<N>(num, den, out, rare);
+#pragma unroll
+    for (int k = 0; k < N; k++) out[k] *= c.tolmT;
+  }
+}
+
 // gather + push of N markers (src/pic1dp_interaction.F90:250-338), lane by lane the same operations as push_one
 template <int DIST, int CFG, int N>
 __device__ __forceinline__ void push_n(const ParticleArgs &a, const double *sE, const double (&x)[N],
@@ -462,7 +526,16 @@ __device__ __forceinline__ void push_n(const ParticleArgs &a, const double *sE, 
     wo[k] = w[k];
     vo[k] = v[k];
   }
-  if (F::deltaf(a.deltaf)) {
+  if (F::tol && (DIST == 2 || DIST == 3)) {   // delta-f nonlinear by construction of the tolerance configurations
+    double tmp2[N];
+    dlnf0_tol_n<DIST, N>(a.c, v, tmp2, rare);
+    const double cz = a.dt * a.c.Zm;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double tmp1 = dmul(dsub(p[k], w[k]), electric[k]);   // :271, as written
+      wo[k] = fma(tmp1 * cz, tmp2[k], wb[k]);                    // :329-330 with dt Z / m folded and one rounding less
+    }
+  } else if (F::deltaf(a.deltaf)) {
     double tmp2[N];
     if (F::unit)
       dlnf0_impl_n<DIST, true, true, N>(a.c, v, tmp2, rare);

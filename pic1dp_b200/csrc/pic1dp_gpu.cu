@@ -220,6 +220,16 @@ static void species_const(const pic1dp_params &p, int s, SpeciesConst &c) {
   c.pow2 = all ? 1 : 0;
   c.unit = (c.m == 1.0 && c.T == 1.0 && c.Tm == 1.0 && c.T2m == 1.0 && c.twoTm == 2.0 && c.twoT2m == 2.0 &&
             c.sqTm == 1.0 && c.sqT2m == 1.0) ? 1 : 0;
+  // PIC1DP_ARITH_TOLERANCE coefficients
+  c.tolA = c.n / (c.Tm * c.sqTm);
+  c.tolB = c.omn / (c.T2m * c.sqT2m);
+  c.tolC = c.n / c.sqTm;
+  c.tolD = c.omn / c.sqT2m;
+  c.tolh1 = 1.0 / c.twoTm;
+  c.tolh2 = 1.0 / c.twoT2m;
+  c.tolk2 = 2.0 * c.v0 / c.Tm;
+  c.tolmT = c.m / c.T;
+  c.Zm = c.Z / c.m;
   c.i_m = 1.0 / c.m;
   c.i_T = 1.0 / c.T;
   c.i_Tm = 1.0 / c.Tm;
@@ -445,10 +455,10 @@ static int create_impl(pic1dp_gpu_t *h) {
   h->cfg = (p.deltaf == 1 && p.linear == 0 && p.iptclshape >= 3) ? 1 : -1;
   {
     int per_sm_min = 1 << 30;
-    const int cfgs[4] = {-1, 1, 9, 25};
+    const int cfgs[6] = {-1, 1, 9, 25, 33, 57};
     for (int irk2 = 0; irk2 < 2; irk2++)
       for (int fused = 0; fused < 2; fused++)
-        for (int ci = 0; ci < 4; ci++) {
+        for (int ci = 0; ci < 6; ci++) {
           PushKernel k = pick_push(p.iptcldist, dep, irk2 == 1, fused == 1, cfgs[ci]);
           CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_push));
           int per_sm = 0;
@@ -1174,7 +1184,9 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
     a.x_out = S.x[out];
     a.v_out = S.v[out];
     a.w_out = S.w[out];
-    const int cfg = (h->cfg == 1) ? (S.c.unit ? 25 : S.c.pow2 ? 9 : 1) : -1;
+    int cfg = (h->cfg == 1) ? (S.c.unit ? 25 : S.c.pow2 ? 9 : 1) : -1;
+    if (cfg > 0 && fused && p.arith_mode == PIC1DP_ARITH_TOLERANCE && (p.iptcldist == 2 || p.iptcldist == 3))
+      cfg = (S.c.unit ? 25 : 1) + 32;   // the tolerance form has no constant divisors left, so pow2 needs no variant
     const bool timed = h->lt_on && h->lt_irk.size() < 8192;
     if (timed) {
       if (h->lt_ev.size() < 2 * (h->lt_irk.size() + 1)) {

@@ -25,6 +25,10 @@ PushKernel pick_cfg(int dep, bool fused, int cfg) {
   if (cfg == 1) return pick_dep<IRK2, 1>(dep);
   if (cfg == 9) return pick_dep<IRK2, 9>(dep);
   if (cfg == 25) return pick_dep<IRK2, 25>(dep);
+#if PIC1DP_DIST == 2 || PIC1DP_DIST == 3
+  if (cfg == 33) return pick_dep<IRK2, 33>(dep);   // PIC1DP_ARITH_TOLERANCE
+  if (cfg == 57) return pick_dep<IRK2, 57>(dep);
+#endif
   return pick_dep<IRK2, -1>(dep);
 }
 template <bool IRK2, int CFG>

@@ -213,3 +213,67 @@ def test_counter_based_load_is_decomposition_independent():
         assert np.array_equal(np.concatenate([a[k], b[k]]), whole[k]), k
     u_v, u_x = H.host_counter_uniforms(77, 0, 0, n)
     assert np.array_equal(whole["x"], u_x * op.lx) and np.array_equal(whole["v"], (u_v - 0.5) * 2.0 * op.v_max)
+
+
+# ---- PIC1DP_ARITH_TOLERANCE ----
+
+@pytest.mark.parametrize("dist,consts", [(3, "unit"), (3, "nonpow2"), (3, "pow2"), (2, "unit"), (2, "nonpow2")])
+@pytest.mark.parametrize("dep", [P.DEPOSIT_SMEM_ATOMIC, P.DEPOSIT_FIXED])
+def test_tolerance_arithmetic_substeps_against_oracle(dist, consts, dep):
+    """arith_mode = TOLERANCE (one exponential of the argument difference, fused multiply-adds on the w path): with a
+    prescribed E both RK substeps give x, v BIT-EXACT (that path keeps the reference's operation order) and w within
+    1e-14 of max|w| of the strict oracle -- the same bar the STRICT mode meets (its exp is not glibc's either)."""
+    kw = dict(nx=256, iptcldist=dist, capacity=200_001, deposit_mode=dep, arith_mode=P.ARITH_TOLERANCE)
+    if consts == "nonpow2":
+        kw.update(temperature=[1.3], temperature2=[0.7], mass=[0.9])
+    elif consts == "pow2":
+        kw.update(temperature=[2.0], temperature2=[0.5], mass=[0.5])
+    op, gp = make_params(**kw)
+    n = 200_001
+    st = synth_markers(op, n, seed=40 + dist)
+    E = 1e-3 * np.sin(2 * np.pi * np.arange(op.nx) / op.nx + 0.3)
+    ref = OracleRun(op, [[copy_state(st)]])
+    ref.E = E.copy()
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        g.set_field(electric=E)
+        for irk in (1, 2):
+            ref.push(irk)
+            g.push(irk)
+            out = g.get_markers(0)
+            r = ref.st[0][0]
+            xr = r["x"].copy()
+            ref.o.shape(xr)   # the fused kernel also wraps
+            assert np.array_equal(out["x"], xr) and np.array_equal(out["v"], r["v"]), irk
+            assert rel_err(out["w"], r["w"]) < 1e-14, irk
+            r["w"][:] = out["w"]
+
+
+@pytest.mark.parametrize("dep", [P.DEPOSIT_AUTO, P.DEPOSIT_FIXED])
+def test_tolerance_arithmetic_ten_steps_within_north_star_bar(dep):
+    """Ten full steps of the default problem in TOLERANCE mode against the strict oracle: rho, E <= 1e-12 of max at
+    every substep, x, v, w <= 1e-12 at the end, cell indices identical at every substep."""
+    n = 400_000
+    op, gp = make_params(nx=256, capacity=n, deposit_mode=dep, arith_mode=P.ARITH_TOLERANCE)
+    st = synth_markers(op, n, seed=45)
+    ref = OracleRun(op, [[copy_state(st)]])
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        ref.init_field()
+        g.collect_charge()
+        g.solve_field()
+        for it in range(10):
+            for irk in (1, 2):
+                ref.push(irk)
+                ref.collect_charge()
+                ref.solve_field()
+                g.push(irk)
+                g.collect_charge()
+                g.solve_field()
+                f = g.get_field()
+                assert rel_err(f["chargeden"], ref.rho) < TOL_SUM, (it, irk)
+                assert rel_err(f["electric"], ref.E) < TOL_SUM, (it, irk)
+                assert np.array_equal(g.get_shape_x(0)[0], ref.o.shape(ref.st[0][0]["x"].copy())[0]), (it, irk)
+        out = g.get_markers(0)
+    for k in ("x", "v", "w"):
+        assert rel_err(out[k], ref.st[0][0][k]) < 1e-12, k
