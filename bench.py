@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "p2p"],
                     help="density all-reduce: NCCL or peer-memory exchange (auto = p2p when it can be set up)")
     ap.add_argument("--load-path", type=int, default=0, help="PIC1DP_LOAD_* (0 auto, 1 direct, 2 TMA ring)")
+    ap.add_argument("--arith", default="strict", choices=["strict", "tolerance"],
+                    help="PIC1DP_ARITH_*: strict = the reference's operation order everywhere; tolerance = w path with one "
+                         "exponential (x, v, cell index still bit-exact)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one (no CUDA graph replay)")
     ap.add_argument("--cpu-markers", type=float, default=2e7, help="markers of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -240,7 +244,8 @@ def main():
     import pic1dp_b200 as P
 
     n = int(args.markers)
-    gp = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit, load_path=args.load_path)
+    gp = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit, load_path=args.load_path,
+                          arith_mode=1 if args.arith == "tolerance" else 0, no_step_graph=1 if args.no_graph else 0)
     g = P.Pic1dGpu(gp)
     if world > 1:
         uid = [g.comm_unique_id() if rank == 0 else None]

@@ -347,6 +347,15 @@ int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int
                                double *total_v, double *pertb_v);
 
 /*
+ * output_all: what one call of output_all does on the marker side (src/pic1dp_output.F90:488-520: output_field, then
+ * output_ptcldist for every species) in ONE pass over x, v, p, w per species: the fused kernel accumulates the
+ * output_field sums and the x-v histograms together, so an output step reads each marker once.  scalars as in
+ * output_field (1 + 3*nspecies); dist = per species [markr_xv | total_xv | pertb_xv | markr_v | total_v | pertb_v]
+ * (3*nx_opd*nv_opd + 3*nv_opd doubles each), same definitions as output_ptcldist.
+ */
+int pic1dp_gpu_output_all(pic1dp_gpu_t *h, int32_t nx_opd, int32_t nv_opd, double v_max, double *scalars, double *dist);
+
+/*
  * ---- marker optimisation: particle_optimize's workers (src/pic1dp_particle.F90:356-746) ----
  * particle_optimize itself (:752-813) is schedule logic (input_tmerge / _tremove / _tsplit against global_time, only at
  * global_irk == 2, delta-f only) and stays in the host; it is called between push and collect_charge

@@ -92,7 +92,7 @@ EXPORTS = [
     "pic1dp_gpu_launch_timing_start", "pic1dp_gpu_launch_timing_stop",
     "pic1dp_gpu_load_markers_kiss64", "pic1dp_gpu_load_markers_counter", "pic1dp_gpu_kiss64_uniforms",
     "pic1dp_host_kiss64_jump", "pic1dp_host_kiss64_fill", "pic1dp_host_counter_uniforms",
-    "pic1dp_gpu_p2p_trace", "pic1dp_gpu_p2p_trace_read",
+    "pic1dp_gpu_p2p_trace", "pic1dp_gpu_p2p_trace_read", "pic1dp_gpu_output_all",
 ]
 
 # RNG call-backs of particle_remove / particle_split (pic1dp_real64_fn, pic1dp_gaussian_array_fn)
@@ -174,6 +174,7 @@ def load() -> C.CDLL:
     L.pic1dp_host_kiss64_fill.argtypes = [u64p, i64, dp]
     L.pic1dp_host_counter_uniforms.argtypes = [C.c_uint64, i32, i64, i64, dp, dp]
     L.pic1dp_host_counter_uniforms.restype = None
+    L.pic1dp_gpu_output_all.argtypes = [vp, i32, i32, dbl, dp, dp]
     L.pic1dp_gpu_p2p_trace.argtypes = [vp, i32]
     L.pic1dp_gpu_p2p_trace_read.argtypes = [vp, u64p, i64p]
     for name in EXPORTS:

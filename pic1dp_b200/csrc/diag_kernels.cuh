@@ -67,19 +67,26 @@ __global__ void __launch_bounds__(512) k_diag(const DiagArgs a) {
       const int c00 = iv * a.nx_opd + ix, c10 = (iv + 1) * a.nx_opd + ix;
       const int c01 = iv * a.nx_opd + ix2, c11 = (iv + 1) * a.nx_opd + ix2;
       const double w00 = dmul(sx, sv), w10 = dmul(sx, sv2), w01 = dmul(sx2, sv), w11 = dmul(sx2, sv2);
+      // iv + 1 == nv_opd happens when (v + v_max) / (2 v_max) rounds to 1 (v within an ulp of v_max): the reference
+      // writes out of bounds there; those two contributions (weight sv2 ~ 0) are dropped
+      const bool up = iv + 1 < a.nv_opd;
       atomicAdd(hm + c00, w00);  // results unused: RED.E.ADD.F64
-      atomicAdd(hm + c10, w10);
       atomicAdd(hm + c01, w01);
-      atomicAdd(hm + c11, w11);
       atomicAdd(ht + c00, dmul(w00, p));
-      atomicAdd(ht + c10, dmul(w10, p));
       atomicAdd(ht + c01, dmul(w01, p));
-      atomicAdd(ht + c11, dmul(w11, p));
+      if (up) {
+        atomicAdd(hm + c10, w10);
+        atomicAdd(hm + c11, w11);
+        atomicAdd(ht + c10, dmul(w10, p));
+        atomicAdd(ht + c11, dmul(w11, p));
+      }
       if (a.deltaf) {
         atomicAdd(hp + c00, dmul(w00, w));
-        atomicAdd(hp + c10, dmul(w10, w));
         atomicAdd(hp + c01, dmul(w01, w));
-        atomicAdd(hp + c11, dmul(w11, w));
+        if (up) {
+          atomicAdd(hp + c10, dmul(w10, w));
+          atomicAdd(hp + c11, dmul(w11, w));
+        }
       }
     }
   }
@@ -100,53 +107,93 @@ __global__ void __launch_bounds__(512) k_diag(const DiagArgs a) {
   }
 }
 
-// Shared-memory form of the histogram: the CTA accumulates {g, f} pairs with one ATOMS.CAS.128 per bilinear corner and
-// delta f with a 64-bit CAS loop in a private ncell*24-byte grid, then flushes it to one of the ncopies L2-resident
-// grids with RED.ADD.F64.  4x faster than 12 REDs per marker when the grid fits (64 x 64: 96 KB).
-__global__ void __launch_bounds__(512) k_diag_hist_smem(const DiagArgs a) {
+// Shared-memory form of the histogram, fused with the output_field sums: ONE pass over x, v, p, w per output step.
+// The CTA keeps a private grid of (nv_opd + 1) rows (the spare row takes the iv + 1 contributions of a velocity within
+// an ulp of v_max, where (v + v_max) / (2 v_max) rounds to 1 -- the reference indexes out of bounds there) and
+// accumulates with 128-bit CAS loops (sm_100a has no native 64-bit shared atomic add; the unit retires ~1 lane-atomic
+// per clock per SM, which is what bounds this kernel, not HBM):
+//   {g, f} pairs per cell            : 4 CAS.128 per marker (one per bilinear corner)
+//   delta f as {left, right} pairs   : 2 CAS.128 per marker (one per row; pertb[r][ix] = left[r][ix] + right[r][ix-1])
+// = 6 atomics per marker instead of the 8 of the round-1 kernel.  Both divisions use the exact-reciprocal form of the
+// push kernels (div_const: bit-identical to IEEE division, IEEE fallback inside).  The grid is flushed to one of the
+// ncopies L2-resident grids with RED.ADD.F64.
+template <bool SUMS>
+__global__ void __launch_bounds__(1024, 1) k_diag_fused(const DiagArgs a) {
   extern __shared__ __align__(16) double sh[];
-  const int ncell = a.nx_opd * a.nv_opd;
-  double2 *s_mt = reinterpret_cast<double2 *>(sh);  // {markr, total}
-  double *s_p = sh + 2 * (size_t)ncell;             // pertb
-  for (int j = threadIdx.x; j < 3 * ncell; j += blockDim.x) sh[j] = 0.0;
+  __shared__ double s_red[3][32];
+  const int nxo = a.nx_opd, ncell = nxo * a.nv_opd, ncell1 = nxo * (a.nv_opd + 1);
+  double *s_mt = sh;                          // {markr, total} pairs, ncell1 slots
+  double *s_pp = sh + 2 * (size_t)ncell1;     // pertb {left, right} pairs, ncell1 slots
+  for (int j = threadIdx.x; j < 4 * ncell1; j += blockDim.x) sh[j] = 0.0;
   __syncthreads();
-  const double rnx = (double)a.nx_opd, rnv = (double)(a.nv_opd - 1), two_vmax = dmul(a.v_max, 2.0);
-  Depositor<DEP_SMEM_ATOMIC> pairs;
-  pairs.g = sh;
+  const double rnx = (double)nxo, rnv = (double)(a.nv_opd - 1), two_vmax = dmul(a.v_max, 2.0);
+  const double rlx = 1.0 / a.lx, r2v = 1.0 / two_vmax;
+  Depositor<DEP_SMEM_ATOMIC> gf, pp;
+  gf.g = s_mt;
+  pp.g = s_pp;
+  double s_vv = 0.0, s_vvp = 0.0, s_vvw = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.np; i += (int64_t)gridDim.x * blockDim.x) {
-    const double v = __ldcs(a.v + i);
-    if (fabs(v) >= a.v_max) continue;  // :241
-    const double p = __ldcs(a.p + i), x = __ldcs(a.x + i);
+    const double v = __ldcs(a.v + i), p = __ldcs(a.p + i);
     const double w = a.deltaf ? __ldcs(a.w + i) : 0.0;
-    double sx = dmul(ddiv(x, a.lx), rnx);
+    if (SUMS) {
+      const double vv = dmul(v, v);  // VecPointwiseMult(tmp1, v, v)  :128
+      s_vv = dadd(s_vv, vv);
+      s_vvp = dadd(s_vvp, dmul(vv, p));  // :138
+      if (a.deltaf) s_vvw = dadd(s_vvw, dmul(vv, w));  // :147
+    }
+    if (a.nx_opd == 0 || fabs(v) >= a.v_max) continue;  // :241 (nx_opd == 0: sums only)
+    const double x = __ldcs(a.x + i);
+    double sx = dmul(div_const(x, a.lx, rlx), rnx);  // :243
     int ix = __double2int_rd(sx);
-    sx = dsub(1.0, dsub(sx, (double)ix));
-    double sv = dmul(ddiv(dadd(v, a.v_max), two_vmax), rnv);
+    sx = dsub(1.0, dsub(sx, (double)ix));  // :245
+    double sv = dmul(div_const(dadd(v, a.v_max), two_vmax, r2v), rnv);  // :247-248
     const int iv = __double2int_rd(sv);
-    sv = dsub(1.0, dsub(sv, (double)iv));
-    if ((unsigned)ix >= (unsigned)a.nx_opd) {
+    sv = dsub(1.0, dsub(sv, (double)iv));  // :250
+    if ((unsigned)ix >= (unsigned)nxo) {  // x == lx exactly (the reference would index out of bounds)
       ix = 0;
       sx = 1.0;
     }
     int ix2 = ix + 1;
-    if (ix2 > a.nx_opd - 1) ix2 = 0;
-    const double sx2 = dsub(1.0, sx), sv2 = dsub(1.0, sv);
-    const int c[4] = {iv * a.nx_opd + ix, (iv + 1) * a.nx_opd + ix, iv * a.nx_opd + ix2, (iv + 1) * a.nx_opd + ix2};
-    const double wt[4] = {dmul(sx, sv), dmul(sx, sv2), dmul(sx2, sv), dmul(sx2, sv2)};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      pairs.add(c[q], 0, wt[q], dmul(wt[q], p), true);
-      if (a.deltaf) atomicAdd(s_p + c[q], dmul(wt[q], w));
+    if (ix2 > nxo - 1) ix2 = 0;  // :272
+    const double sx2 = dsub(1.0, sx), sv2 = dsub(1.0, sv);  // :273
+    const int r0 = iv * nxo, r1 = r0 + nxo;
+    const double w00 = dmul(sx, sv), w10 = dmul(sx, sv2), w01 = dmul(sx2, sv), w11 = dmul(sx2, sv2);
+    gf.add(r0 + ix, 0, w00, dmul(w00, p), true);
+    gf.add(r1 + ix, 0, w10, dmul(w10, p), true);
+    gf.add(r0 + ix2, 0, w01, dmul(w01, p), true);
+    gf.add(r1 + ix2, 0, w11, dmul(w11, p), true);
+    if (a.deltaf) {
+      pp.add(r0 + ix, 0, dmul(w00, w), dmul(w01, w), true);
+      pp.add(r1 + ix, 0, dmul(w10, w), dmul(w11, w), true);
     }
   }
   __syncthreads();
-  double *hm = a.hist + (size_t)(blockIdx.x % a.ncopies) * 3 * ncell;
-  for (int j = threadIdx.x; j < ncell; j += blockDim.x) {
-    const double2 mt = s_mt[j];
-    if (mt.x != 0.0) atomicAdd(hm + j, mt.x);
-    if (mt.y != 0.0) atomicAdd(hm + ncell + j, mt.y);
-    const double pp = s_p[j];
-    if (pp != 0.0) atomicAdd(hm + 2 * ncell + j, pp);
+  if (a.nx_opd > 0) {
+    double *hm = a.hist + (size_t)(blockIdx.x % a.ncopies) * 3 * ncell;
+    const double2 *mt2 = reinterpret_cast<const double2 *>(s_mt), *pp2 = reinterpret_cast<const double2 *>(s_pp);
+    for (int j = threadIdx.x; j < ncell; j += blockDim.x) {   // the spare row (j >= ncell) is dropped
+      const double2 mt = mt2[j];
+      if (mt.x != 0.0) atomicAdd(hm + j, mt.x);
+      if (mt.y != 0.0) atomicAdd(hm + ncell + j, mt.y);
+      const int ixj = j % nxo, jl = (ixj == 0) ? j + nxo - 1 : j - 1;  // periodic left neighbour in the same row
+      const double pv = dadd(pp2[j].x, pp2[jl].y);
+      if (pv != 0.0) atomicAdd(hm + 2 * ncell + j, pv);
+    }
+  }
+  if (SUMS) {  // fixed-shape block reduction, one partial per CTA, summed in CTA order by k_diag_sums_final
+    double r[3] = {s_vv, s_vvp, s_vvw};
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r[q] = dadd(r[q], __shfl_xor_sync(0xffffffffu, r[q], o));
+      if ((threadIdx.x & 31) == 0) s_red[q][threadIdx.x >> 5] = r[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = s_red[threadIdx.x][0];
+      for (int k = 1; k < (int)(blockDim.x >> 5); k++) t = dadd(t, s_red[threadIdx.x][k]);
+      a.sum_partial[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
+    }
   }
 }
 

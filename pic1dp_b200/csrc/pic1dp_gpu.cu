@@ -124,7 +124,9 @@ struct pic1dp_gpu {
   std::vector<double> h_Fre, h_Fim, h_ginv;
   // diagnostics scratch (allocated on first use)
   double *d_diag_part = nullptr, *d_diag_sums = nullptr, *d_hist = nullptr, *d_hist_out = nullptr;
-  int diag_grid = 0, hist_cells = 0, hist_copies = 16, hist_smem_set = -1, hist_per_sm = 1;
+  int diag_grid = 0, hist_cells = 0, hist_copies = 16, hist_smem_set = -1;
+  double *d_hist_all = nullptr;   // output_all: reduced histograms of all species
+  size_t hist_all_cap = 0;
   // marker optimisation (allocated on first use): device scratch of compute_dist_pertb_abs_v, its host copy
   // particle_dist_pertb_abs_v(ispecies, 0:nv-1), and the pinned staging arrays of merge / remove / split
   double *d_dist_part = nullptr;
@@ -348,7 +350,7 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
     if (S.p) cudaFree(S.p);
   }
   double *bufs[] = {h->d_E, h->d_rho, h->d_mre, h->d_mim, h->d_Fre, h->d_Fim, h->d_ginv, h->d_partial, h->d_red, h->d_energy,
-                    h->d_diag_part, h->d_diag_sums, h->d_hist, h->d_hist_out, h->d_dist_part};
+                    h->d_diag_part, h->d_diag_sums, h->d_hist, h->d_hist_out, h->d_dist_part, h->d_hist_all};
   for (double *b : bufs)
     if (b) cudaFree(b);
   for (int q = 0; q < 4; q++)
@@ -1450,6 +1452,25 @@ static void fill_diag_args(pic1dp_gpu_t *h, int s, DiagArgs &a) {
   a.ncopies = h->hist_copies;
 }
 
+// scalars of output_field from the per-species device sums (src/pic1dp_output.F90:126-172)
+static void output_field_scalars(const pic1dp_params &p, const double *sums, double *scalars) {
+  for (int s = 0; s < p.nspecies; s++) {
+    const double vv = sums[3 * s], vvp = sums[3 * s + 1], vvw = sums[3 * s + 2];
+    scalars[1 + 3 * s] = vv;       // :135
+    scalars[2 + 3 * s] = vvp;      // :143
+    double energy;
+    if (p.deltaf == 1) {
+      energy = vvw;                                              // :150
+      if (p.linear == 1) scalars[2 + 3 * s] = vvp + energy;      // :154
+    } else {
+      energy = vvp;  // "at this point energy is total energy"   // :157
+      if (p.iptcldist == 1) energy = energy - 3.0 * p.density[s] * p.lx;                                   // :160
+      else if (p.iptcldist == 0) energy = energy - p.temperature[s] / p.mass[s] * p.density[s] * p.lx;     // :166-168
+    }
+    scalars[3 + 3 * s] = energy;   // :171
+  }
+}
+
 int pic1dp_gpu_output_field(pic1dp_gpu_t *h, double *scalars) {
   if (!h || !scalars) return PIC1DP_EINVAL;
   int rc = check_loaded(h, "output_field");
@@ -1479,71 +1500,56 @@ int pic1dp_gpu_output_field(pic1dp_gpu_t *h, double *scalars) {
   CK(cudaStreamSynchronize(h->stream));
   if ((rc = p2p_check_timeouts(h, "output_field"))) return rc;
   h->d2h += 8 + 3 * p.nspecies * 8;
-  for (int s = 0; s < p.nspecies; s++) {
-    const double vv = sums[3 * s], vvp = sums[3 * s + 1], vvw = sums[3 * s + 2];
-    scalars[1 + 3 * s] = vv;       // src/pic1dp_output.F90:135
-    scalars[2 + 3 * s] = vvp;      // :143
-    double energy;
-    if (p.deltaf == 1) {
-      energy = vvw;                                              // :150
-      if (p.linear == 1) scalars[2 + 3 * s] = vvp + energy;      // :154
-    } else {
-      energy = vvp;  // "at this point energy is total energy"   // :157
-      if (p.iptcldist == 1) energy = energy - 3.0 * p.density[s] * p.lx;                                   // :160
-      else if (p.iptcldist == 0) energy = energy - p.temperature[s] / p.mass[s] * p.density[s] * p.lx;     // :166-168
-    }
-    scalars[3 + 3 * s] = energy;   // :171
-  }
+  output_field_scalars(p, sums, scalars);
   return PIC1DP_OK;
 }
 
-int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int32_t nv_opd, double v_max,
-                               double *markr_xv, double *total_xv, double *pertb_xv, double *markr_v,
-                               double *total_v, double *pertb_v) {
-  if (!h || isp < 0 || isp >= h->p.nspecies || nx_opd < 1 || nv_opd < 2 || !(v_max > 0.0) ||
-      (int64_t)nx_opd * nv_opd > (1 << 22)) {
-    if (h) h->err = "output_ptcldist: bad argument";
-    return PIC1DP_EINVAL;
-  }
-  int rc = check_loaded(h, "output_ptcldist");
-  if (rc) return rc;
-  CK(cudaSetDevice(h->p.device));
+// histogram pass of one species into d_hist_out[3][ncell] (+ the output_field sums into d_diag_sums[3 isp] when
+// with_sums): one fused kernel when the private grid fits in shared memory, RED.ADD.F64 to L2 otherwise
+static int launch_hist(pic1dp_gpu_t *h, int isp, int nx_opd, int nv_opd, double v_max, bool with_sums, double *d_out) {
   const int ncell = nx_opd * nv_opd;
-  rc = diag_setup(h, ncell);
-  if (rc) return rc;
-  const pic1dp_params &p = h->p;
   DiagArgs a;
   fill_diag_args(h, isp, a);
   a.nx_opd = nx_opd;
   a.nv_opd = nv_opd;
   a.v_max = v_max;
-  {
-    const size_t hs = (size_t)3 * ncell * 8;
-    if (hs <= h->max_smem) {  // private shared-memory histogram per CTA, flushed with REDs
-      if (h->hist_smem_set != (int)hs) {
-        CK(cudaFuncSetAttribute(k_diag_hist_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
-        int per_sm = 1;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diag_hist_smem, 512, hs));
-        h->hist_per_sm = per_sm < 1 ? 1 : per_sm;
-        h->hist_smem_set = (int)hs;
-      }
-      k_diag_hist_smem<<<h->nsm * h->hist_per_sm, 512, hs, h->stream>>>(a);
-    } else {
-      k_diag<false, true><<<h->diag_grid, 512, 0, h->stream>>>(a);
+  const size_t hs = (size_t)4 * nx_opd * (nv_opd + 1) * 8;
+  if (hs <= h->max_smem) {
+    if (h->hist_smem_set != (int)hs) {
+      CK(cudaFuncSetAttribute(k_diag_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+      CK(cudaFuncSetAttribute(k_diag_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+      h->hist_smem_set = (int)hs;
     }
+    // one 1024-thread CTA per SM (at most diag_grid CTAs: the sum partials are sized for that)
+    if (with_sums) k_diag_fused<true><<<h->nsm, 1024, hs, h->stream>>>(a);
+    else k_diag_fused<false><<<h->nsm, 1024, hs, h->stream>>>(a);
+    CKL(h);
+    if (with_sums) {
+      k_diag_sums_final<<<1, 32, 0, h->stream>>>(h->d_diag_part, h->nsm, h->d_diag_sums + 3 * isp);
+      CKL(h);
+    }
+  } else {
+    if (with_sums) {
+      k_diag<true, false><<<h->diag_grid, 512, 0, h->stream>>>(a);
+      CKL(h);
+      k_diag_sums_final<<<1, 32, 0, h->stream>>>(h->d_diag_part, h->diag_grid, h->d_diag_sums + 3 * isp);
+      CKL(h);
+    }
+    k_diag<false, true><<<h->diag_grid, 512, 0, h->stream>>>(a);
     CKL(h);
   }
-  // the private copies are laid out for hist_cells; only the first 3*ncell entries of each copy are used
-  // (stride between copies is 3*ncell of THIS call, see k_diag), so reduce with the same stride
-  k_diag_hist_final<<<(3 * ncell + 255) / 256, 256, 0, h->stream>>>(h->d_hist, h->hist_copies, 3 * ncell, h->d_hist_out);
+  // the private copies are laid out with stride 3*ncell of THIS call; the reduction also clears them for the next use
+  k_diag_hist_final<<<(3 * ncell + 255) / 256, 256, 0, h->stream>>>(h->d_hist, h->hist_copies, 3 * ncell, d_out);
   CKL(h);
-  rc = allreduce_inplace(h, h->d_hist_out, (size_t)3 * ncell);  // MPI_Reduce :333-357 (every rank gets the sum)
-  if (rc) return rc;
-  std::vector<double> raw((size_t)3 * ncell);
-  CK(cudaMemcpyAsync(raw.data(), h->d_hist_out, (size_t)3 * ncell * 8, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  h->d2h += (int64_t)3 * ncell * 8;
-  double *m_xv = raw.data(), *t_xv = m_xv + ncell, *p_xv = t_xv + ncell;
+  return PIC1DP_OK;
+}
+
+// host half of output_ptcldist (src/pic1dp_output.F90:297-455) on the reduced raw histograms raw[3][ncell]
+static void ptcldist_finish(const pic1dp_params &p, int isp, int nx_opd, int nv_opd, double v_max, double *raw,
+                            double *markr_xv, double *total_xv, double *pertb_xv, double *markr_v, double *total_v,
+                            double *pertb_v) {
+  const int ncell = nx_opd * nv_opd;
+  double *m_xv = raw, *t_xv = m_xv + ncell, *p_xv = t_xv + ncell;
   std::vector<double> m_v(nv_opd, 0.0), t_v(nv_opd, 0.0), p_v(nv_opd, 0.0);
   for (int iv = 0; iv < nv_opd; iv++)  // v-only histograms = sums over x of the x-v ones (sx + (1-sx) = 1)
     for (int ix = 0; ix < nx_opd; ix++) {
@@ -1594,6 +1600,74 @@ int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int
   if (markr_v) memcpy(markr_v, m_v.data(), (size_t)nv_opd * 8);
   if (total_v) memcpy(total_v, t_v.data(), (size_t)nv_opd * 8);
   if (pertb_v) memcpy(pertb_v, p_v.data(), (size_t)nv_opd * 8);
+}
+
+static int ptcldist_check(pic1dp_gpu_t *h, int32_t nx_opd, int32_t nv_opd, double v_max, const char *who) {
+  if (nx_opd < 1 || nv_opd < 2 || !(v_max > 0.0) || (int64_t)nx_opd * nv_opd > (1 << 22)) {
+    h->err = std::string(who) + ": bad argument";
+    return PIC1DP_EINVAL;
+  }
+  return check_loaded(h, who);
+}
+
+int pic1dp_gpu_output_ptcldist(pic1dp_gpu_t *h, int32_t isp, int32_t nx_opd, int32_t nv_opd, double v_max,
+                               double *markr_xv, double *total_xv, double *pertb_xv, double *markr_v,
+                               double *total_v, double *pertb_v) {
+  if (!h || isp < 0 || isp >= h->p.nspecies) { if (h) h->err = "output_ptcldist: bad species"; return PIC1DP_EINVAL; }
+  int rc = ptcldist_check(h, nx_opd, nv_opd, v_max, "output_ptcldist");
+  if (rc) return rc;
+  CK(cudaSetDevice(h->p.device));
+  const int ncell = nx_opd * nv_opd;
+  if ((rc = diag_setup(h, ncell))) return rc;
+  if ((rc = launch_hist(h, isp, nx_opd, nv_opd, v_max, false, h->d_hist_out))) return rc;
+  rc = allreduce_inplace(h, h->d_hist_out, (size_t)3 * ncell);  // MPI_Reduce :333-357 (every rank gets the sum)
+  if (rc) return rc;
+  std::vector<double> raw((size_t)3 * ncell);
+  CK(cudaMemcpyAsync(raw.data(), h->d_hist_out, (size_t)3 * ncell * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->d2h += (int64_t)3 * ncell * 8;
+  ptcldist_finish(h->p, isp, nx_opd, nv_opd, v_max, raw.data(), markr_xv, total_xv, pertb_xv, markr_v, total_v, pertb_v);
+  return PIC1DP_OK;
+}
+
+int pic1dp_gpu_output_all(pic1dp_gpu_t *h, int32_t nx_opd, int32_t nv_opd, double v_max, double *scalars, double *dist) {
+  if (!h || !scalars || !dist) { if (h) h->err = "output_all: NULL output"; return PIC1DP_EINVAL; }
+  int rc = ptcldist_check(h, nx_opd, nv_opd, v_max, "output_all");
+  if (rc) return rc;
+  CK(cudaSetDevice(h->p.device));
+  const pic1dp_params &p = h->p;
+  const int ncell = nx_opd * nv_opd;
+  if ((rc = diag_setup(h, ncell))) return rc;
+  if ((size_t)3 * ncell * p.nspecies > h->hist_all_cap) {   // reduced histograms of all species side by side
+    if (h->d_hist_all) cudaFree(h->d_hist_all);
+    h->d_hist_all = nullptr;
+    CK(cudaMalloc(&h->d_hist_all, (size_t)3 * ncell * p.nspecies * 8));
+    h->hist_all_cap = (size_t)3 * ncell * p.nspecies;
+  }
+  for (int s = 0; s < p.nspecies; s++)   // ONE pass over the markers of each species: sums + histograms
+    if ((rc = launch_hist(h, s, nx_opd, nv_opd, v_max, true, h->d_hist_all + (size_t)3 * ncell * s))) return rc;
+  if ((rc = allreduce_inplace(h, h->d_diag_sums, (size_t)3 * p.nspecies))) return rc;        // VecSum
+  if ((rc = allreduce_inplace(h, h->d_hist_all, (size_t)3 * ncell * p.nspecies))) return rc;  // MPI_Reduce :333-357
+  GridArgs g;
+  fill_grid_args(h, g);
+  k_field_energy<<<1, 1024, 0, h->stream>>>(g);
+  CKL(h);
+  double sums[3 * PIC1DP_MAX_SPECIES];
+  std::vector<double> raw((size_t)3 * ncell * p.nspecies);
+  CK(cudaMemcpyAsync(sums, h->d_diag_sums, (size_t)3 * p.nspecies * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&scalars[0], h->d_energy, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(raw.data(), h->d_hist_all, raw.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  p2p_queue_timeout_read(h);
+  CK(cudaStreamSynchronize(h->stream));
+  if ((rc = p2p_check_timeouts(h, "output_all"))) return rc;
+  h->d2h += 8 + 3 * p.nspecies * 8 + (int64_t)raw.size() * 8;
+  output_field_scalars(p, sums, scalars);
+  const size_t per = (size_t)3 * ncell + 3 * nv_opd;
+  for (int s = 0; s < p.nspecies; s++) {
+    double *o = dist + per * s;
+    ptcldist_finish(p, s, nx_opd, nv_opd, v_max, raw.data() + (size_t)3 * ncell * s, o, o + ncell, o + 2 * ncell,
+                    o + 3 * ncell, o + 3 * ncell + nv_opd, o + 3 * ncell + 2 * nv_opd);
+  }
   return PIC1DP_OK;
 }
 

@@ -262,6 +262,22 @@ class Pic1dGpu:
                  "output_ptcldist")
         return dict(zip(("markr_xv", "total_xv", "pertb_xv", "markr_v", "total_v", "pertb_v"), outs))
 
+    def output_all(self, nx_opd: int = 64, nv_opd: int = 64, v_max: float = 8.0):
+        """(output_field scalars, [output_ptcldist dict per species]) from one pass over the markers."""
+        nsp, nc = self.params.nspecies, nx_opd * nv_opd
+        sc = np.empty(1 + 3 * nsp)
+        per = 3 * nc + 3 * nv_opd
+        buf = np.empty(per * nsp)
+        self._ck(self.L.pic1dp_gpu_output_all(self._h, nx_opd, nv_opd, float(v_max), _dp(sc), _dp(buf)), "output_all")
+        names = ("markr_xv", "total_xv", "pertb_xv", "markr_v", "total_v", "pertb_v")
+        dists = []
+        for s in range(nsp):
+            o = buf[per * s: per * (s + 1)]
+            parts = [o[0:nc], o[nc:2 * nc], o[2 * nc:3 * nc], o[3 * nc:3 * nc + nv_opd],
+                     o[3 * nc + nv_opd:3 * nc + 2 * nv_opd], o[3 * nc + 2 * nv_opd:]]
+            dists.append({k: a.copy() for k, a in zip(names, parts)})
+        return sc, dists
+
     # ---- marker optimisation (src/pic1dp_particle.F90:356-746) ----
     def compute_dist_pertb_abs_v(self, nv: int = 128, v_max: float = 8.0) -> np.ndarray:
         """particle_dist_pertb_abs_v as [nspecies, nv], reduced on the device and over ranks."""

@@ -35,13 +35,13 @@ class OutputWriter:
 
     def output_all(self, time: float):
         """output_field + output_ptcldist (src/pic1dp_output.F90:100-189, :196-477) from device-side reductions."""
-        sc = self.gpu.output_field()
+        sc, dists = self.gpu.output_all(self.nx_opd, self.nv_opd, self.v_max)   # one pass over the markers
         np.asarray(np.concatenate([[time], sc]), dtype=">f8").tofile(self.f)
         fld = self.gpu.get_field()
         for k in ("mode_re", "mode_im", "electric", "chargeden"):
             self._vec(fld[k])
         for s in range(self.p.nspecies):
-            d = self.gpu.output_ptcldist(s, self.nx_opd, self.nv_opd, self.v_max)
+            d = dists[s]
             for k in ("markr_xv", "total_xv", "pertb_xv", "markr_v", "total_v", "pertb_v"):
                 np.asarray(d[k], dtype=">f8").tofile(self.f)
         return sc

@@ -14,7 +14,8 @@ def make_params(**over):
     """Matching (oracle params, GPU params) pair.  GPU-only keys: capacity, device, deposit_mode, field_mode, fuse,
     rank, nranks."""
     gpu_only = {k: over.pop(k) for k in list(over) if k in ("capacity", "device", "deposit_mode", "field_mode",
-                                                            "fuse", "rank", "nranks", "load_path")}
+                                                            "fuse", "rank", "nranks", "load_path", "arith_mode",
+                                                            "no_step_graph")}
     op = O.default_params(**over)
     loader_only = ("init_nmode", "init_mode", "init_mode_cos", "init_mode_sin", "v_max", "imarker")
     gp = P.default_params(**{k: v for k, v in over.items() if k not in loader_only}, **gpu_only)

@@ -102,3 +102,61 @@ def test_output_file_is_readable_by_the_reference_reader_layout(tmp_path):
     assert abs(gamma / 0.0838311 - 1.0) < 0.05
     # no marker array ever crossed PCIe after the initial load
     assert d2h < 61 * (3 * 64 * 64 + 4 * 192 + 64) * 8 * 2
+
+
+@pytest.mark.parametrize("case", ["deltaf", "fullf_maxwell", "two_species"])
+def test_output_all_single_pass_matches_oracle(case):
+    """pic1dp_gpu_output_all: the output_field sums and the x-v histograms of every species from ONE pass over the
+    markers (fused kernel), against the oracle and against the two separate entry points."""
+    kw, nsp = dict(nx=192, capacity=150000), 1
+    if case == "fullf_maxwell":
+        kw.update(deltaf=0, iptcldist=0, density=[1.0], v0=[0.5], temperature=[1.2])
+    elif case == "two_species":
+        nsp = 2
+        kw.update(nspecies=2, charge=[-1.0, 1.0], mass=[1.0, 4.0], temperature=[1.0, 0.5], temperature2=[1.0, 0.5],
+                  density=[0.9, 1.0], v0=[5.0, 0.0])
+    op, gp = make_params(**kw)
+    sts = [synth_markers(op, 150000 - 13 * s, seed=65 + s, isp=s) for s in range(nsp)]
+    for st in sts:
+        st["v"][:50] = np.linspace(-9.0, 9.0, 50)
+        st["x"][50] = op.lx
+        st["v"][51] = np.nextafter(8.0, 0.0)    # (v + v_max) / (2 v_max) rounds to 1: iv + 1 == nv_opd (spare row)
+        st["v"][52] = -8.0                       # |v| >= v_max is skipped
+    ref = OracleRun(op, [[copy_state(s)] for s in sts])
+    ref.init_field()
+    with P.Pic1dGpu(gp) as g:
+        for s, st in enumerate(sts):
+            g.set_markers(s, st["x"], st["v"], st["p"], st["w"])
+        g.collect_charge()
+        g.solve_field()
+        sc, dists = g.output_all(64, 64, 8.0)
+        sc_sep = g.output_field()
+        sc2, dists2 = g.output_all(64, 64, 8.0)     # repeatable (private copies are cleared by the reduction)
+        sc_ref = ref.o.output_field(ref.st, ref.E)
+        assert np.allclose(sc, sc_ref, rtol=1e-11, atol=0) or np.max(np.abs(sc - sc_ref)) < 1e-12 * np.max(np.abs(sc_ref))
+        assert np.max(np.abs(sc - sc_sep)) <= 1e-12 * np.max(np.abs(sc_sep))
+        assert np.array_equal(sc[:1], sc2[:1])
+        for s in range(nsp):
+            dr = ref.o.output_ptcldist(ref.st, s, 64, 64, 8.0)
+            dsep = g.output_ptcldist(s, 64, 64, 8.0)
+            for k in dr:
+                scale = np.max(np.abs(dr["total_xv" if k.endswith("xv") else "total_v"])) if "pertb" in k and op.deltaf == 0 \
+                    else np.max(np.abs(dr[k]))
+                # the oracle (like the reference) adds the iv + 1 row of the v ~ v_max marker out of bounds; its weight
+                # 1 - sv is 0 there, so the arrays still agree
+                assert rel_err(dists[s][k], dr[k], scale) < 1e-11, (case, s, k)
+                assert rel_err(dists[s][k], dsep[k], scale) < 1e-11, (case, s, k)
+                assert rel_err(dists2[s][k], dists[s][k], scale) < 1e-11, (case, s, k)
+
+
+def test_output_all_odd_histogram_grids():
+    op, gp = make_params(nx=192, capacity=60000)
+    st = synth_markers(op, 60000, seed=71)
+    ref = OracleRun(op, [[copy_state(st)]])
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        for nxo, nvo, vm in ((64, 64, 8.0), (16, 8, 4.0), (100, 33, 8.0), (1, 2, 8.0), (300, 200, 8.0)):
+            _, dists = g.output_all(nxo, nvo, vm)       # 300 x 200 does not fit in shared memory: RED fallback
+            dr = ref.o.output_ptcldist(ref.st, 0, nxo, nvo, vm)
+            for k in dr:
+                assert rel_err(dists[0][k], dr[k]) < 1e-11, (nxo, nvo, k)
