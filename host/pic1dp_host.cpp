@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -283,18 +284,36 @@ struct Generator {
     const int nseed = al == 2 ? 312 : al == 3 ? 20635 : 4;
     std::fill(s.begin(), s.end(), 0);
     bool seeded = false;
-    if (seed_type == 3) {
+    if (seed_type == 3) {  // :256-300: /dev/urandom, re-reading the words that must not be zero
       FILE *f = fopen("/dev/urandom", "rb");
       if (f && fread(s.data(), 8, nseed, f) == (size_t)nseed) {
         seeded = true;
-        if (al == 3 && s[20634] == 0) s[20634] = 521288629546311ULL;
-        if (al == 1 && s[1] == 0) s[1] = 362436362436362436ULL;
+        auto again = [&](uint64_t &word) { return fread(&word, 8, 1, f) == 1; };
+        if (al == 1) {
+          while (seeded && s[1] == 0) seeded = again(s[1]);
+          while (seeded && s[0] == 0 && s[3] == 0) seeded = again(s[0]) && again(s[3]);
+        } else if (al == 3) {
+          while (seeded && s[20634] == 0) seeded = again(s[20634]);
+        }
       }
       if (f) fclose(f);
+      if (!seeded) {  // the reference falls back to system_clock seeds with a warning (:257-276)
+        fprintf(stderr, "[multirand_init] Warning: /dev/urandom unusable, falling back to system_clock seeds\n");
+        seed_type = 2;
+        std::fill(s.begin(), s.end(), 0);
+      }
     }
-    if (!seeded) {  // constant seeds, rank dependent (:301-350)
+    if (!seeded) {  // clock (seed_type 2, :303) or constant (seed_type 1, :305) seeds, rank dependent (:301-350)
       auto iabs = [](int64_t a) { return a < 0 ? -a : a; };
-      const int64_t clock = primes1[1];
+      int64_t clock = primes1[1];
+      if (seed_type == 2) {  // system_clock(count): a monotonic tick counter
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        clock = (int64_t)ts.tv_sec * 1000 + ts.tv_nsec / 1000000;
+      } else if (seed_type != 1) {
+        fprintf(stderr, "[multirand_init] Error: seed_type must be 1 (constant), 2 (system_clock) or 3 (/dev/urandom)\n");
+        exit(1);
+      }
       int64_t k4[4];
       for (int i = 0; i < 4; i++) k4[i] = clock + primes1[iabs(clock + primes2[iabs(clock) % 100] * mype) % 100] * mype;
       for (int i = 0; i < 4; i++) k4[i] += primes2[iabs(k4[i] + primes1[iabs(clock) % 100] * i) % 100] * i;

@@ -297,22 +297,48 @@ class Pic1dGpu:
     def particle_remove(self, thsh: float, typeremove: int, remove_frac: float, real64):
         """real64: callable returning the next multirand_real64() of this rank's generator."""
         n = self._np_out()
-        cb = _capi.REAL64_FN(lambda _ctx: float(real64()))
-        self._ck(self.L.pic1dp_gpu_particle_remove(self._h, float(thsh), typeremove, float(remove_frac), cb, None, n),
-                 "particle_remove")
+        # ctypes swallows an exception raised inside a call-back (the C loop would go on with garbage): keep it,
+        # feed harmless values for the rest of the call and re-raise once the C call has returned
+        err = []
+
+        def dice(_ctx):
+            if err:
+                return 1.0
+            try:
+                return float(real64())
+            except BaseException as e:  # noqa: BLE001
+                err.append(e)
+                return 1.0
+        cb = _capi.REAL64_FN(dice)
+        rc = self.L.pic1dp_gpu_particle_remove(self._h, float(thsh), typeremove, float(remove_frac), cb, None, n)
+        if err:
+            raise RuntimeError("particle_remove: the real64 call-back raised; the markers on the device are invalid") from err[0]
+        self._ck(rc, "particle_remove")
         return list(n)
 
     def particle_split(self, thsh: float, ngroup: int, dv_sig_frac: float, gaussian_array):
         """gaussian_array: callable n -> array of n draws, like multirand_gaussian_array."""
         n = self._np_out()
 
+        err = []
+
         def fill(_ctx, a, k):
-            g = gaussian_array(k)
-            for i in range(k):
-                a[i] = g[i]
+            try:
+                if err:
+                    raise err[0]
+                g = gaussian_array(k)
+                for i in range(k):
+                    a[i] = g[i]
+            except BaseException as e:  # noqa: BLE001 -- see particle_remove
+                if not err:
+                    err.append(e)
+                for i in range(k):
+                    a[i] = 0.0
         cb = _capi.GAUSSIAN_ARRAY_FN(fill)
-        self._ck(self.L.pic1dp_gpu_particle_split(self._h, float(thsh), ngroup, float(dv_sig_frac), cb, None, n),
-                 "particle_split")
+        rc = self.L.pic1dp_gpu_particle_split(self._h, float(thsh), ngroup, float(dv_sig_frac), cb, None, n)
+        if err:
+            raise RuntimeError("particle_split: the gaussian_array call-back raised; the markers on the device are invalid") from err[0]
+        self._ck(rc, "particle_split")
         return list(n)
 
     # ---- instrumentation ----
