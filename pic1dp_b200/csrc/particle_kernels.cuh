@@ -180,6 +180,8 @@ struct ParticleArgs {
   // that a captured step graph can be replayed; raised with atomicMax by the kernels), and the overflow counter
   unsigned *dep_wmax_hi;
   unsigned long long *dep_overflow;
+  unsigned long long *dep_spill;   // [gridDim.x][2 * nx][2]: 128-bit spill accumulators of the int64 slots (all zero between launches)
+  unsigned dep_spill_th;           // spill threshold in units of 2^32 (0x40000000 = 2^62)
 };
 
 // ---- periodic wrap: px = mod(px, lx); if (px < 0) px = px + lx  (src/pic1dp_interaction.F90:102-104) ----
@@ -655,17 +657,35 @@ struct Depositor<DEP_WARP_PRIVATE> {
 // slot sums do not depend on the order in which the warps arrive.  The reference's own deposit is sequential, hence
 // deterministic (src/pic1dp_interaction.F90:96-114); this is the order-independent counterpart.
 //   scale   : 2^e with e chosen per launch from the running maximum of |deposit source| (max|w| so far, kept on the
-//             device) so that a contribution is below 2^47 with >= 4x headroom for growth within the substep;
-//             quantum = 2^-e <= 2^-45 max|w|: the rounding of one contribution is ~3e-14 max|w|, far below the
+//             device) so that a contribution is below 2^50 with >= 4x headroom for growth within the substep;
+//             quantum = 2^-e <= 2^-47 max|w|: the rounding of one contribution is ~7e-15 max|w|, far below the
 //             summation-order noise of fp64 accumulation and 1e-12 of max|rho|.
-//   windows : a slot component can receive at most 2*blockDim contributions per tile step, so after
-//             FIXED_WINDOW = 2^16 / (2*blockDim) tile steps (|sum| < 2^63) the CTA flushes its integer grid -- exact
-//             int64 sums converted to double, descaled (exact power of two) and accumulated into the CTA's private
-//             global grid in window order.  Windows cover fixed marker sets (static tile -> CTA mapping), so the
-//             whole chain marker -> slot -> window -> CTA grid -> reduce kernel is order-independent or fixed-order.
+//   spill   : an int64 slot could overflow only if one cell of one CTA received > 2^12 maximal contributions.  Instead
+//             of bounding that with periodic CTA-wide flushes (barriers inside the persistent loop cost 30 % of the
+//             kernel: the warps drift many iterations apart and the laggards then run alone), every CAS attempt
+//             checks |old| < 2^62; a thread that sees a slot beyond it swaps the slot to zero and adds the old value
+//             to a 128-bit integer accumulator of that slot in global memory (two native 64-bit atomic adds with
+//             carry).  Integer all the way, so the total is exact and independent of when spills happen.  The final
+//             flush adds the accumulators of a CTA that spilled.  (Never taken with physical marker distributions;
+//             tests lower the threshold to exercise it.)
 //   overflow: |source| >= 2^51 / 2^e (growth by > 64x inside one substep) cannot be converted; it is counted in
 //             dep_overflow and reported by the next synchronising call.
 // ------------------------------------------------------------------------------------------------------------
+struct FixedSpill {
+  unsigned long long *acc;   // this CTA's accumulators: [2 * nx][2] = {low word, high word} of a 128-bit integer
+  int *flag;                 // shared-memory flag: this CTA has spilled
+  unsigned th;               // spill when |slot| >= th * 2^32 (2^62 unless a test lowers it)
+};
+
+// adds the signed 64-bit v to the 128-bit accumulator at acc[0..1]; order-independent
+__device__ __noinline__ void fixed_spill_add(unsigned long long *acc, long long v) {
+  const unsigned long long u = (unsigned long long)v;
+  const unsigned long long old = atomicAdd(acc, u);
+  const unsigned long long carry = (old + u < old) ? 1ULL : 0ULL;
+  const unsigned long long hi = (v < 0 ? ~0ULL : 0ULL) + carry;
+  if (hi) atomicAdd(acc + 1, hi);
+}
+
 template <>
 struct Depositor<DEP_FIXED> {
   double *g;      // pair grid, 2*nx int64 viewed as doubles by dep_setup
@@ -673,6 +693,7 @@ struct Depositor<DEP_FIXED> {
   double inv;     // 2^-e
   unsigned bound_hi;  // high word of 2^51 / 2^e: sources at or above it overflow the conversion
   unsigned seen_hi;   // high word of the largest |source| this thread has deposited
+  FixedSpill sp;
   __device__ __forceinline__ double prescale(double q) {
     seen_hi = max(seen_hi, (unsigned)__double2hiint(q) & 0x7fffffffu);
     return dmul(q, scale);  // exact (power of two)
@@ -689,7 +710,9 @@ struct Depositor<DEP_FIXED> {
     longlong2 old = *slot;
     for (;;) {
       const unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
-      const unsigned long long d0 = e0 + (unsigned long long)ia, d1 = e1 + (unsigned long long)ib;
+      // |old| >= th * 2^32 in either component: move the slot's content to its 128-bit accumulator first
+      const bool full = ((unsigned)(e0 >> 32) + sp.th >= 2 * sp.th) | ((unsigned)(e1 >> 32) + sp.th >= 2 * sp.th);
+      const unsigned long long d0 = full ? 0ULL : e0 + (unsigned long long)ia, d1 = full ? 0ULL : e1 + (unsigned long long)ib;
       unsigned long long f0, f1;
       asm volatile(
           "{\n\t.reg .b128 c, d, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
@@ -697,7 +720,16 @@ struct Depositor<DEP_FIXED> {
           : "=l"(f0), "=l"(f1)
           : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "r"(addr)
           : "memory");
-      if (f0 == e0 && f1 == e1) break;
+      const bool won = (f0 == e0) & (f1 == e1);
+      if (__builtin_expect(won & full, 0)) {   // this thread emptied the slot: it owns the old content
+        fixed_spill_add(sp.acc + 4 * (size_t)ix, (long long)e0);
+        fixed_spill_add(sp.acc + 4 * (size_t)ix + 2, (long long)e1);
+        *sp.flag = 1;
+        old.x = 0;
+        old.y = 0;
+        continue;
+      }
+      if (won) break;
       old.x = (long long)f0;
       old.y = (long long)f1;
     }
@@ -705,15 +737,15 @@ struct Depositor<DEP_FIXED> {
 };
 
 // scale of this launch from the running maximum (high word of max|source|): source bound 2^(E+3) with E the unbiased
-// exponent of the maximum (>= 4x headroom), contribution * 2^e < 2^47
+// exponent of the maximum (>= 4x headroom), contribution * 2^e < 2^50
 __device__ __forceinline__ void fixed_scale(Depositor<DEP_FIXED> &dep, const unsigned wmax_hi) {
   int ex = (int)((wmax_hi >> 20) & 0x7ff);   // biased exponent of the maximum
   if (ex < 100) ex = 100;                     // all-zero / denormal sources: any scale works, keep 2^e finite
-  const int se = 2090 - ex;                   // biased exponent of 2^e, e = 47 - (ex - 1023 + 3)
+  const int se = 2093 - ex;                   // biased exponent of 2^e, e = 50 - (ex - 1023 + 3)
   dep.seen_hi = 0;
   dep.scale = __hiloint2double(se << 20, 0);
   dep.inv = __hiloint2double((2046 - se) << 20, 0);
-  dep.bound_hi = (unsigned)((1023 + 51 - (se - 1023)) << 20);
+  dep.bound_hi = (unsigned)((2097 - se) << 20);
 }
 
 // end of the kernel: publish the largest source seen (the next launch scales by it) and count conversion overflows
@@ -725,23 +757,50 @@ __device__ __forceinline__ void fixed_finish(const Depositor<DEP_FIXED> &dep, un
   }
 }
 
-// tile steps between two flushes of the integer grid: 2^16 contributions of < 2^47 stay below 2^63
-__device__ __forceinline__ int fixed_window(void) { return (1 << 16) / (2 * (int)blockDim.x); }
+// (high : low) 128-bit two's-complement integer -> double through its magnitude: for |value| < 2^64 this is the
+// correctly rounded value, i.e. exactly what (double)(int64) gives when the value fits in 64 bits
+__device__ __forceinline__ double int128_to_double(unsigned long long lo, long long hi) {
+  const bool neg = hi < 0;
+  if (neg) {
+    lo = ~lo + 1ULL;
+    hi = ~hi + (lo == 0ULL ? 1 : 0);
+  }
+  const double m = dadd(dmul((double)(unsigned long long)hi, 18446744073709551616.0), (double)lo);
+  return neg ? -m : m;
+}
 
-// flush of the integer pair grid into the CTA's global grid (store on the first window, accumulate afterwards) and
-// clearing for the next window; called by every thread of the CTA
-__device__ __forceinline__ void fixed_flush(double *pairs, int nx, double *my_partial, const double inv, const bool first) {
+// flush of the integer pair grid into the CTA's global grid; called by every thread of the CTA after the marker loop.
+// rho[j] = left[j] + right[j-1], summed as integers and converted once; a CTA that spilled adds the 128-bit
+// accumulators first.  Both branches round the same exact integer, so the result does not depend on whether (or when)
+// a slot was spilled.
+__device__ __forceinline__ void fixed_flush(double *pairs, int nx, double *my_partial, const double inv, const FixedSpill &sp) {
   __syncthreads();
   const longlong2 *sl = reinterpret_cast<const longlong2 *>(pairs);
+  const bool spilled = *sp.flag != 0;   // CTA-uniform after the barrier
   for (int j = threadIdx.x; j < nx; j += blockDim.x) {
     const int jl = (j == 0) ? nx - 1 : j - 1;  // right weights of the cell to the left (periodic, :111-112)
-    const long long sum = sl[j].x + sl[jl].y;  // exact
-    const double val = dmul((double)sum, inv);
-    my_partial[j] = first ? val : dadd(my_partial[j], val);
+    const long long L = sl[j].x, R = sl[jl].y;
+    if (!spilled) {
+      my_partial[j] = dmul((double)(L + R), inv);   // exact sum (|L|, |R| < 2^62), one rounding
+    } else {
+      const unsigned long long *aL = sp.acc + 4 * (size_t)j, *aR = sp.acc + 4 * (size_t)jl + 2;
+      unsigned long long lo = aL[0];
+      long long hi = (long long)aL[1];
+      const unsigned long long add[3] = {(unsigned long long)L, aR[0], (unsigned long long)R};
+      const long long addh[3] = {L < 0 ? -1LL : 0LL, (long long)aR[1], R < 0 ? -1LL : 0LL};
+#pragma unroll
+      for (int q = 0; q < 3; q++) {   // 128-bit additions
+        const unsigned long long t = lo + add[q];
+        hi += addh[q] + (t < lo ? 1 : 0);
+        lo = t;
+      }
+      my_partial[j] = dmul(int128_to_double(lo, hi), inv);
+    }
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < 2 * nx; j += blockDim.x) pairs[j] = 0.0;
-  __syncthreads();
+  if (spilled) {   // the accumulators are all zero between launches
+    __syncthreads();
+    for (int j = threadIdx.x; j < 4 * nx; j += blockDim.x) sp.acc[j] = 0ULL;
+  }
 }
 
 // Marker arrays are touched once per substep.  Measured on B200 (profiles/r01_ab_experiments.md): the default cache
@@ -935,13 +994,18 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   double *my_partial = FUSED ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
   Depositor<DEP> dep;
   dep.g = FUSED ? dep_setup<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial) : nullptr;
-  if constexpr (DEP == DEP_FIXED) fixed_scale(dep, FUSED ? *a.dep_wmax_hi : 0u);
+  __shared__ int s_spill;
+  if constexpr (DEP == DEP_FIXED) {
+    fixed_scale(dep, FUSED ? *a.dep_wmax_hi : 0u);
+    dep.sp.acc = a.dep_spill + (size_t)blockIdx.x * 4 * a.nx;
+    dep.sp.flag = &s_spill;
+    dep.sp.th = a.dep_spill_th;
+    if (threadIdx.x == 0) s_spill = 0;
+  }
   __syncthreads();
 
   const int64_t tile = (int64_t)blockDim.x * 2;
   unsigned long long noob = 0;
-  int win = 0;          // DEP_FIXED: tile steps since the last flush of the integer grid
-  bool win_first = true;
   const bool deltaf_pf = Cfg<CFG>::deltaf(a.deltaf);
   // register-staged v of the next tile step: the fast body starts with the v-only work (both exponentials), so v is
   // the one load whose latency nothing hides; it is issued one iteration ahead (4 registers)
@@ -983,16 +1047,9 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
       redo = push_pair_fast<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
     }
     push_pair_redo<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, redo);
-    if constexpr (DEP == DEP_FIXED && FUSED) {
-      if (++win == fixed_window()) {  // CTA-uniform: the loop bounds depend on blockIdx only
-        fixed_flush(smem + ((a.nx + 1) & ~1), a.nx, my_partial, dep.inv, win_first);
-        win = 0;
-        win_first = false;
-      }
-    }
   }
   if constexpr (DEP == DEP_FIXED && FUSED) {
-    fixed_flush(smem + ((a.nx + 1) & ~1), a.nx, my_partial, dep.inv, win_first);
+    fixed_flush(smem + ((a.nx + 1) & ~1), a.nx, my_partial, dep.inv, dep.sp);
     fixed_finish(dep, a.dep_wmax_hi, a.dep_overflow);
   } else if (FUSED) {
     dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
@@ -1202,12 +1259,17 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
   double *my_partial = DEPOSIT ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
   Depositor<DEP> dep;
   dep.g = DEPOSIT ? dep_setup<DEP>(smem, a.nx, my_partial) : nullptr;
-  if constexpr (DEP == DEP_FIXED) fixed_scale(dep, DEPOSIT ? *a.dep_wmax_hi : 0u);  // set by k_absmax_hi before this launch
+  __shared__ int s_spill;
+  if constexpr (DEP == DEP_FIXED) {
+    fixed_scale(dep, DEPOSIT ? *a.dep_wmax_hi : 0u);  // set by k_absmax_hi before this launch
+    dep.sp.acc = a.dep_spill + (size_t)blockIdx.x * 4 * a.nx;
+    dep.sp.flag = &s_spill;
+    dep.sp.th = a.dep_spill_th;
+    if (threadIdx.x == 0) s_spill = 0;
+  }
   __syncthreads();
   const int64_t tile = (int64_t)blockDim.x * 2;
   unsigned long long noob = 0;
-  int win = 0;
-  bool win_first = true;
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
     const bool v0ok = i < a.np, v1ok = i + 1 < a.np;
@@ -1234,17 +1296,10 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
       const Shape s1 = shape_of(xw.y, a.lx, a.rlx, a.rnx, a.nx, a.right_frac, o1);
       dep.add(s1.ix, s1.ixr, dmul(s1.sl, q1), dmul(s1.sr, q1), v1ok);
       noob += (v0ok && o0) + (v1ok && o1);
-      if constexpr (DEP == DEP_FIXED) {
-        if (++win == fixed_window()) {
-          fixed_flush(smem, a.nx, my_partial, dep.inv, win_first);
-          win = 0;
-          win_first = false;
-        }
-      }
     }
   }
   if constexpr (DEP == DEP_FIXED && DEPOSIT) {
-    fixed_flush(smem, a.nx, my_partial, dep.inv, win_first);
+    fixed_flush(smem, a.nx, my_partial, dep.inv, dep.sp);
     fixed_finish(dep, a.dep_wmax_hi, a.dep_overflow);
   } else if (DEPOSIT) {
     dep_flush<DEP>(smem, a.nx, my_partial);

@@ -46,8 +46,8 @@ def test_deterministic_deposit_on_large_grids(nx, req):
 
 
 def test_fixed_deposit_is_independent_of_the_launch_geometry():
-    """Integer sums do not depend on which warp adds first; with one flush window per CTA the per-CTA grids are exact,
-    so standalone deposits of the same markers agree to the last bit with the fused kernel's deposit of the same x, w."""
+    """Integer sums do not depend on which warp adds first and the per-CTA grids are exact, so standalone deposits
+    of the same markers agree to the last bit with the fused kernel's deposit of the same x, w."""
     n = 300_000
     op, gp = make_params(nx=2048, capacity=n, deposit_mode=P.DEPOSIT_FIXED)
     st = synth_markers(op, n, seed=22)
@@ -66,17 +66,25 @@ def test_fixed_deposit_is_independent_of_the_launch_geometry():
     assert np.array_equal(rhos[0], rhos[1])
 
 
-def test_fixed_deposit_flushes_windows_on_long_cta_loops():
-    """More than FIXED_WINDOW (32) tile steps per CTA: the integer grid is flushed several times per launch."""
-    n = 148 * 2048 * 40 + 777
-    op, gp = make_params(nx=1024, capacity=n, deposit_mode=P.DEPOSIT_FIXED)
+def test_fixed_deposit_spills_full_slots_exactly(monkeypatch):
+    """An int64 slot that approaches overflow is emptied into a 128-bit accumulator (never needed with physical
+    markers: it takes > 4096 maximal contributions to one cell of one CTA).  With the threshold lowered to 2^51 nearly
+    every contribution spills; the density must be bit-identical to the run that never spills, and to itself."""
+    n = 148 * 2048 * 3 + 777
+    op, gp = make_params(nx=512, capacity=n, deposit_mode=P.DEPOSIT_FIXED)
     st = synth_markers(op, n, seed=23)
+    st["x"][: n // 4] = 0.37 * op.lx          # a quarter of all markers in one cell: a heavily loaded slot
     ref = OracleRun(op, [[copy_state(st)]])
     ref.init_field()
     ref.step()
+    plain = _run(gp, st, 1)
+    monkeypatch.setenv("PIC1DP_EXP_SPILL_BITS", "51")
     a = _run(gp, st, 1)
     b = _run(gp, st, 1)
-    assert np.array_equal(a[0]["chargeden"], b[0]["chargeden"])
+    monkeypatch.delenv("PIC1DP_EXP_SPILL_BITS")
+    for k in ("chargeden", "electric"):
+        assert np.array_equal(a[0][k], b[0][k]) and np.array_equal(a[0][k], plain[0][k]), k
+    assert np.array_equal(a[1]["w"], plain[1]["w"])
     assert rel_err(a[0]["chargeden"], ref.rho) < TOL_SUM and rel_err(a[0]["electric"], ref.E) < TOL_SUM
 
 
@@ -246,7 +254,8 @@ def test_tolerance_arithmetic_substeps_against_oracle(dist, consts, dep):
             ref.o.shape(xr)   # the fused kernel also wraps
             assert np.array_equal(out["x"], xr) and np.array_equal(out["v"], r["v"]), irk
             assert rel_err(out["w"], r["w"]) < 1e-14, irk
-            r["w"][:] = out["w"]
+            r["x"][:] = xr            # the reference wraps here too (collect_charge) before the next push
+            r["w"][:] = out["w"]      # continue from identical state so irk = 2 isolates one substep
 
 
 @pytest.mark.parametrize("dep", [P.DEPOSIT_AUTO, P.DEPOSIT_FIXED])
