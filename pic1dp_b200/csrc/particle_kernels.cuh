@@ -678,7 +678,7 @@ struct FixedSpill {
 };
 
 // adds the signed 64-bit v to the 128-bit accumulator at acc[0..1]; order-independent
-__device__ __noinline__ void fixed_spill_add(unsigned long long *acc, long long v) {
+static __device__ __noinline__ void fixed_spill_add(unsigned long long *acc, long long v) {
   const unsigned long long u = (unsigned long long)v;
   const unsigned long long old = atomicAdd(acc, u);
   const unsigned long long carry = (old + u < old) ? 1ULL : 0ULL;
