@@ -7,12 +7,15 @@
 A "step" is one full timestep input_dt of the reference time loop (src/pic1dp.F90:79-93): 2 RK substeps, each
 = gather + push(x, w, v) + wrap + deposit, plus 2 field solves and 2 density all-reduces.  1 particle-step = 1 marker
 advanced one step.  Workload: BASELINE.json configs[3] -- bump-on-tail delta-f, 1e8 markers per GPU, nx=1024,
-weak scaling; markers are synthetic (numpy PCG64, seed = 1234 + rank) with the loader's distribution.
+weak scaling (default) -- or configs[4] with --scaling strong: 1e9 markers in total, nx=8192.  Markers are synthetic:
+particle_load's distribution from the device-side KISS64 stream (multirand_al_int = 1) of a rank-dependent seed.
 
 Keys of the JSON line: see the measurement contract in DESIGN.md.  `value` = device-timed (CUDA events on the
-library's stream), markers resident in HBM; `e2e` = same metric through the C ABI with host (pinned) buffers:
-set_markers H2D inside the timed region, get_field D2H after every step and the output step at the reference's
-cadence (every 10 steps, src/pic1dp_input.F90:250 / src/pic1dp.F90:98-108) and at the end.
+library's stream), markers resident in HBM; `sustained` = the same over >= 500 further steps (the clock settles under
+the power cap); `e2e` = same metric through the C ABI as the reference driver uses it, host wall clock: particle_load
+(seeds from the host, streams generated on the device), get_field to pinned host memory after every step, and the output
+step at the reference's cadence (every 10 steps, src/pic1dp_input.F90:250 / src/pic1dp.F90:98-108) and at the end.
+With --gpus N > 1 a parity pre-flight (N ranks vs the oracle's N emulated ranks) runs first: `parity_check`.
 """
 from __future__ import annotations
 
@@ -41,8 +44,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--markers", type=float, default=1e8, help="markers per GPU")
-    ap.add_argument("--nx", type=int, default=1024)
+    ap.add_argument("--markers", type=float, default=1e8, help="markers per GPU (weak scaling)")
+    ap.add_argument("--nx", type=int, default=None, help="grid cells (default 1024; 8192 with --scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: configs[3], --markers per GPU; strong: configs[4], --total-markers split over the GPUs")
+    ap.add_argument("--total-markers", type=float, default=1e9, help="markers of the whole job (strong scaling)")
+    ap.add_argument("--sustained-steps", type=int, default=500, help="steps of the additional sustained region (0 = off)")
+    ap.add_argument("--e2e-extras", action="store_true", help="also time the host-stream and host-refresh e2e variants")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--deposit", type=int, default=0, help="PIC1DP_DEPOSIT_* (0 = auto)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "p2p"],
                     help="density all-reduce: NCCL or peer-memory exchange (auto = p2p when it can be set up)")
@@ -54,7 +63,10 @@ def parse():
     ap.add_argument("--cpu-markers", type=float, default=2e7, help="markers of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.nx is None:
+        args.nx = 8192 if args.scaling == "strong" else 1024
+    return args
 
 
 def fill_markers(x, v, p, w, lx, seed, chunk=1 << 24):
@@ -159,10 +171,10 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_run(nx, n_markers, steps, warmup, nthreads):
+def cpu_reference_run(nx, n_markers, steps, warmup, nthreads, repeats=1):
     """The reference's algorithm for this path on host cores: oracle port with the reference's structure
     (separate push / deposit passes, backup copies, per-rank private grids summed in rank order), one emulated
-    MPI rank per thread.  Returns particle-steps/s."""
+    MPI rank per thread.  Returns (median particle-steps/s over `repeats` timed runs, its seconds, all values)."""
     from oracle import oracle as O
     op = O.default_params(nx=nx)
     orc = O.Oracle(op)
@@ -177,8 +189,14 @@ def cpu_reference_run(nx, n_markers, steps, warmup, nthreads):
     if warmup > 0:
         r = orc.run([parts], warmup, E0, nthreads=nthreads)
         E0 = r["E"]
-    r = orc.run([parts], steps, E0, nthreads=nthreads)
-    return n * steps / r["seconds"], r["seconds"]
+    runs = []
+    for _ in range(repeats):
+        r = orc.run([parts], steps, E0, nthreads=nthreads)
+        E0 = r["E"]
+        runs.append((n * steps / r["seconds"], r["seconds"]))
+    runs.sort()
+    val, secs = runs[len(runs) // 2]
+    return val, secs, [v for v, _ in runs]
 
 
 def run_reference(args):
@@ -187,13 +205,20 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     n = int(args.cpu_markers)
-    value, secs = cpu_reference_run(args.nx, n, args.steps, args.warmup, cores)
-    sample = f"{n} markers x {args.steps} steps, nx={args.nx}, {cores} emulated MPI ranks (one per host thread)"
+    value, secs, vals = cpu_reference_run(args.nx, n, args.steps, args.warmup, cores, repeats=3)
+    sample = (f"{n} markers x {args.steps} steps, nx={args.nx}, {cores} emulated MPI ranks (one per host thread); "
+              f"median of 3 timed runs {['%.3g' % v for v in vals]}")
+    cfg = workload_config(args, args.gpus)
+    # this arm runs a bounded sample of the workload: say what it ran, next to what the GPU arm runs
+    cfg["gpu_arm_markers_per_gpu"], cfg["gpu_arm_markers_total"] = cfg["markers_per_gpu"], cfg["markers_total"]
+    cfg["markers_per_gpu"] = cfg["markers_total"] = n
+    cfg["l2"] = "CPU sample: %d markers, %.2f GB of marker state" % (n, n * 80 / 1e9)
+    cfg["parallelism"] = f"{cores} emulated MPI ranks on host threads, per-rank private grids summed in rank order"
     line = {
         "impl": "reference", "metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "CPU restatement of the reference loops (oracle/), not the PETSc binary: no "
                                  "Fortran/MPI/PETSc toolchain exists in this image"},
@@ -203,15 +228,98 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def markers_per_gpu(args, world):
+    if args.scaling == "strong":
+        return int(args.total_markers) // world
+    return int(args.markers)
+
+
 def workload_config(args, n_gpus):
-    n = int(args.markers)
-    return {"workload": "configs[3]: bump-on-tail delta-f nonlinear, weak scaling 1e8 markers per GPU, nx=1024, "
-                        "1 mode, dt=0.05, iptclshape=4",
-            "markers_per_gpu": n, "markers_total": n * n_gpus, "nx": args.nx, "nmode": 1,
-            "bytes_per_particle_step": BYTES_STEP,
+    n = markers_per_gpu(args, n_gpus)
+    if args.scaling == "strong":
+        name = ("configs[4]: bump-on-tail delta-f nonlinear, strong scaling %.3g markers in total, nx=%d, 1 mode, "
+                "dt=0.05, iptclshape=4" % (args.total_markers, args.nx))
+    else:
+        name = ("configs[3]: bump-on-tail delta-f nonlinear, weak scaling %.3g markers per GPU, nx=%d, 1 mode, dt=0.05, "
+                "iptclshape=4" % (n, args.nx))
+    return {"workload": name, "markers_per_gpu": n, "markers_total": n * n_gpus, "nx": args.nx, "nmode": 1,
+            "bytes_per_particle_step": BYTES_STEP, "arith_mode": args.arith,
             "l2": "inputs larger than L2: %.1f GB of marker state streamed per step per GPU" % (n * BYTES_STEP / 1e9),
             "parallelism": f"particle-decomposition x{n_gpus}, replicated grid, density all-reduce per substep "
                            "(peer-memory exchange over NVLink, NCCL fallback)"}
+
+
+def rank_seeds(rank):
+    """multirand_seeds(0:3) of this rank as multirand_init leaves them for seed_type = 3 (four random 64-bit words,
+    src/multirand.F90:275-300; here from a fixed-seed host generator so that runs repeat) after the warm-up of
+    5 x 4 outputs (:376-381)."""
+    from pic1dp_b200 import host as H
+    words = [int(w) for w in np.random.default_rng(1234 + rank).integers(1, 2**63, size=4, dtype=np.int64)]
+    return H.host_kiss64_jump(words, 20)
+
+
+def setup_comm(P, dist, g, args, rank, world):
+    """NCCL communicator + (when possible) the peer-memory exchange buffers; returns 'p2p' or 'nccl'."""
+    uid = [g.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g.comm_init(uid[0])
+    if args.allreduce in ("auto", "p2p") and world <= 8:
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, g.p2p_export())
+            g.p2p_import(handles)
+            return "p2p"
+        except Exception as e:  # keep NCCL
+            if args.allreduce == "p2p":
+                raise
+            print(f"[rank {rank}] peer-memory all-reduce unavailable, using NCCL: {e}", file=sys.stderr)
+    return "nccl"
+
+
+def parity_preflight(P, dist, torch, args, rank, world, local):
+    """tests/mgpu_worker.py's comparison inside the bench run, so that every multi-GPU line carries its own parity
+    evidence: 4e5 markers split by the PETSC_DECIDE rule over the N ranks, 5 steps through the same all-reduce path the
+    timed region uses, against the oracle's N emulated ranks (rank 0 compares; the oracle is only the checker)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import OracleRun, make_params, rel_err, synth_markers
+    n, nx, nsteps = 400003, 256, 5
+    op, gp = make_params(nx=nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit,
+                         arith_mode=1 if args.arith == "tolerance" else 0)
+    st = synth_markers(op, n, seed=99)
+    lo, hi = P.petsc_decide(n, world, rank)
+    g = P.Pic1dGpu(gp)
+    path = setup_comm(P, dist, g, args, rank, world)
+    g.set_markers(0, *(np.ascontiguousarray(st[k][lo:hi]) for k in ("x", "v", "p", "w")))
+    g.collect_charge()
+    g.solve_field()
+    g.step(nsteps)
+    f = g.get_field()
+    mk = g.get_markers(0)
+    c = g.counters()
+    E_all = [torch.zeros(nx, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(E_all, torch.from_numpy(f["electric"].copy()))
+    same = all(torch.equal(E_all[0], e) for e in E_all)
+    parts = [None] * world
+    dist.all_gather_object(parts, {k: mk[k] for k in ("x", "v", "w")})
+    g.close()
+    res = [None]
+    if rank == 0:
+        states = []
+        for r in range(world):
+            a, b = P.petsc_decide(n, world, r)
+            states.append({k: st[k][a:b].copy() for k in st})
+        ref = OracleRun(op, [states])
+        ref.init_field()
+        for _ in range(nsteps):
+            ref.step()
+        e_rho, e_E = rel_err(f["chargeden"], ref.rho), rel_err(f["electric"], ref.E)
+        e_mk = max(rel_err(parts[r][k], ref.st[0][r][k]) for r in range(world) for k in ("x", "v", "w"))
+        ok = bool(same and e_rho < 1e-12 and e_E < 1e-12 and e_mk < 1e-12 and c.p2p_timeouts == 0)
+        res[0] = {"ranks": world, "markers": n, "steps": nsteps, "allreduce": path, "rho": e_rho, "E": e_E, "markers_xvw": e_mk,
+                  "replicated_equal": bool(same), "tolerance": 1e-12, "pass": ok,
+                  "against": "oracle with %d emulated MPI ranks (PETSC_DECIDE blocks, grids summed in rank order)" % world}
+    dist.broadcast_object_list(res, src=0)
+    return res[0]
 
 
 def main():
@@ -243,33 +351,29 @@ def main():
         dist.barrier()
     import pic1dp_b200 as P
 
-    n = int(args.markers)
+    # ---- multi-GPU parity pre-flight: N ranks vs the oracle's N emulated ranks ----
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = parity_preflight(P, dist, torch, args, rank, world, local)
+        if not parity["pass"]:
+            if rank == 0:
+                print(json.dumps({"parity_check": parity}), flush=True)
+            raise SystemExit("multi-GPU parity pre-flight failed: " + json.dumps(parity))
+
+    n = markers_per_gpu(args, world)
+    ntotal = n * world
     gp = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit, load_path=args.load_path,
                           arith_mode=1 if args.arith == "tolerance" else 0, no_step_graph=1 if args.no_graph else 0)
     g = P.Pic1dGpu(gp)
     if world > 1:
-        uid = [g.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        g.comm_init(uid[0])
-        if args.allreduce in ("auto", "p2p") and world <= 8:
-            try:
-                handles = [None] * world
-                dist.all_gather_object(handles, g.p2p_export())
-                g.p2p_import(handles)
-            except Exception as e:  # keep NCCL
-                if args.allreduce == "p2p":
-                    raise
-                print(f"[rank {rank}] peer-memory all-reduce unavailable, using NCCL: {e}", file=sys.stderr)
+        setup_comm(P, dist, g, args, rank, world)
 
-    # ---- synthetic inputs in pinned host memory: the two uniform streams particle_load draws (RNG stays on the
-    # host, like multirand); x, v, p, w host buffers receive the loaded markers for the host-refresh variants ----
-    host = {k: torch.empty(n, dtype=torch.float64, pin_memory=True) for k in ("x", "v", "p", "w", "u_v", "u_x")}
-    hv = {k: t.numpy() for k, t in host.items()}
-    fill_uniforms(hv["u_v"], hv["u_x"], seed=1234 + rank)
-    ptr = {k: t.data_ptr() for k, t in host.items()}
+    # ---- synthetic inputs: particle_load with the device-side KISS64 stream of this rank's seeds (no marker-sized
+    # host-to-device copy; the host supplies 32 bytes of generator state) ----
+    seeds = rank_seeds(rank)
 
-    def load_from_host():  # particle_load through the C ABI: 16 B/marker H2D + the loader arithmetic on the device
-        g.load_markers(0, (ptr["u_v"], n), (ptr["u_x"], n), n * world, v_max=8.0)
+    def load_from_host():  # particle_load through the C ABI: pv is drawn first, then px (src/pic1dp_particle.F90:180, :222)
+        g.load_markers_kiss64(0, n, seeds, 0, n, ntotal, v_max=8.0)
     nx = args.nx
     hf = {k: torch.empty(m, dtype=torch.float64, pin_memory=True) for k, m in (("E", nx), ("rho", nx), ("re", 1), ("im", 1))}
 
@@ -292,7 +396,10 @@ def main():
         g.collect_charge()
         g.solve_field()
         g.step(1)
-        bad = float(g.counters().p2p_timeouts > 0 or not np.isfinite(g.field_energy()))
+        try:
+            bad = float(g.counters().p2p_timeouts > 0 or not np.isfinite(g.field_energy()))
+        except P.Pic1dpError:
+            bad = 1.0
         bad = max_over_ranks(bad)
         if bad > 0:
             if args.allreduce == "p2p":
@@ -307,9 +414,8 @@ def main():
 
     # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local)
-    sampler.start()   # started well before the timed region: nvidia-smi needs a few hundred ms to deliver samples
+    sampler.start()   # started well before the timed region: the sampler needs a few hundred ms to deliver samples
     load_from_host()
-    g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], p=ptr["p"], w=ptr["w"])   # host copies for the host-refresh variants
     g.collect_charge()
     g.solve_field()
     g.step(args.warmup)
@@ -326,10 +432,28 @@ def main():
     clocks = sampler.stop(t0, t1)
     c1 = g.counters()
     ms = max_over_ranks(ms)
-    value = n * world * args.steps / (ms * 1e-3)
+    value = ntotal * args.steps / (ms * 1e-3)
     energy = g.field_energy()
-    g.output_field()                     # one-time scratch allocations of the diagnostics happen here, untimed
-    g.output_ptcldist(0, 64, 64, 8.0)
+
+    # ---- sustained: the same loop for >= 500 further steps (graph replay, no per-launch events) ----
+    sustained = None
+    if args.sustained_steps > 0:
+        s2 = ClockSampler(local)
+        s2.start()
+        time.sleep(0.05)
+        barrier()
+        ts0 = time.time()
+        g.timer_start()
+        g.step(args.sustained_steps)
+        ms_s = g.timer_stop()
+        barrier()
+        ts1 = time.time()
+        ms_s = max_over_ranks(ms_s)
+        sustained = {"steps": args.sustained_steps, "value": ntotal * args.sustained_steps / (ms_s * 1e-3),
+                     "unit": "particle-steps/s", "ms_per_step": ms_s / args.sustained_steps,
+                     "step_roofline_frac": n * BYTES_STEP / (ms_s / args.sustained_steps * 1e-3) / 1e9 / measured_peak()[0],
+                     "clocks": s2.stop(ts0, ts1), "graph_replays": int(g.counters().graph_replays)}
+    g.output_all(64, 64, 8.0)            # one-time scratch allocations of the diagnostics happen here, untimed
 
     # ---- roofline of the dominant kernel, CUDA events around each launch ----
     prof = np.array([g.profile_step() for _ in range(5)])[1:].mean(axis=0)  # ms: push1, collect1, field1, push2, ...
@@ -338,11 +462,11 @@ def main():
     if lt[0][1] > 0 and lt[1][1] > 0:
         prof[0], prof[3] = lt[0][0] / lt[0][1], lt[1][0] / lt[1][1]
     peak, peak_src = measured_peak()
-    # dram__bytes_read + dram__bytes_write of this kernel from the committed `ncu --set full` capture, scaled per marker
+    # dram__bytes_read + dram__bytes_write of this kernel from the committed `ncu --set full` capture at the bench size
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if int(c1.deposit_mode) == 1 and args.nx == 1024:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if int(c1.deposit_mode) == tj.get("deposit_mode", 1) and args.nx == tj.get("nx", 1024):
             traffic = tj["irk2"]["dram_bytes_per_marker"] * n
             traffic_src = tj["source"] + "; per-marker DRAM bytes x markers of this launch"
     except Exception:
@@ -365,89 +489,92 @@ def main():
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
-        def e2e_run(mode, k):
-            """set_markers from pinned host memory + k steps; every step the fields come back to the host; every
-            OUTPUT_EVERY steps (and at the end) the output step runs: mode 'device' = output_field + output_ptcldist
-            reduced on the GPU (a few KB of D2H), mode 'host' = get_markers(x, v, w) so that the Fortran host's own
-            output code can run on fresh Vecs (24 B/marker of D2H)."""
+        def e2e_run(k, load):
+            """particle_load + k steps as the reference driver runs them (src/pic1dp.F90:63-109): every step the fields
+            come back to pinned host memory; every OUTPUT_EVERY steps (and at the end) output_all runs on the device
+            (one fused pass, a few KB of D2H)."""
             barrier()
             cc0 = g.counters()
             t_0 = time.perf_counter()
-            if mode == "device":
-                load_from_host()   # particle_load: uniform streams H2D (16 B/marker), loader arithmetic on the device
-            else:
-                g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])   # host-loaded markers, 32 B/marker
+            load()
             g.collect_charge()
             g.solve_field()
             for it in range(1, k + 1):
                 g.step(1)
                 g.get_field_ptr(hf["E"].data_ptr(), hf["rho"].data_ptr(), hf["re"].data_ptr(), hf["im"].data_ptr())
                 if it % OUTPUT_EVERY == 0 or it == k:                        # output_all cadence
-                    if mode == "device":
-                        g.output_field()
-                        g.output_ptcldist(0, 64, 64, 8.0)
-                    else:
-                        g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], w=ptr["w"])
+                    g.output_all(64, 64, 8.0)
             g.sync()
             tw = max_over_ranks(time.perf_counter() - t_0)
             cc = g.counters()
-            return {"value": n * world * k / tw, "unit": "particle-steps/s", "steps": k, "ms_per_step": 1e3 * tw / k,
+            return {"value": ntotal * k / tw, "unit": "particle-steps/s", "steps": k, "ms_per_step": 1e3 * tw / k,
                     "h2d_bytes_per_step": (cc.h2d_bytes - cc0.h2d_bytes) / k,
                     "d2h_bytes_per_step": (cc.d2h_bytes - cc0.d2h_bytes) / k}
 
-        e2e = e2e_run("device", args.steps)
+        e2e = e2e_run(args.steps, load_from_host)
         e2e["definition"] = ("reference driver loop through the C ABI, host wall clock, max over ranks: particle_load as "
-                             "pic1dp_gpu_load_markers (the two uniform RNG streams from pinned host memory, 16 B/marker "
-                             "H2D, loader arithmetic on the device) + K steps, get_field (E, rho, modes) to the host "
-                             f"after every step, output_all every {OUTPUT_EVERY} steps and at the end (reference "
-                             "cadence, src/pic1dp.F90:98-108) as pic1dp_gpu_output_field + pic1dp_gpu_output_ptcldist "
-                             "(device-side reductions, results to the host)")
-        e2e["host_refresh_outputs"] = e2e_run("host", args.steps)
-        e2e["host_refresh_outputs"]["definition"] = ("same with host-loaded markers (set_markers, 32 B/marker H2D) and each "
-                                                     "output step done as get_markers(x, v, w) to pinned host memory")
-        # worst case: markers live on the host and make the round trip every step
-        k2 = min(args.steps, 3)
-        barrier()
-        tw0 = time.perf_counter()
-        for it in range(k2):
-            g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])
-            g.collect_charge()
-            g.solve_field()
-            g.step(1)
-            g.get_field_ptr(hf["E"].data_ptr(), hf["rho"].data_ptr(), hf["re"].data_ptr(), hf["im"].data_ptr())
-            g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], w=ptr["w"])
-        tw2 = max_over_ranks(time.perf_counter() - tw0)
-        e2e["roundtrip_every_step"] = {"value": n * world * k2 / tw2, "steps": k2,
-                                       "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n + (2 * nx + 2) * 8}
-        # device time of one output step
+                             "pic1dp_gpu_load_markers_kiss64 (the host passes multirand's 32-byte KISS64 state, the device "
+                             "generates both uniform streams bit-exactly and applies the loader arithmetic) + K steps, "
+                             "get_field (E, rho, modes) to pinned host memory after every step, output_all every "
+                             f"{OUTPUT_EVERY} steps and at the end (reference cadence, src/pic1dp.F90:98-108) as "
+                             "pic1dp_gpu_output_all (one fused device pass, results to the host)")
+        if sustained is not None:   # the same loop at the sustained length: start-up costs amortised as in a real run
+            ks = min(args.sustained_steps, 200)
+            e2e["sustained"] = e2e_run(ks, load_from_host)
+        if args.e2e_extras and n <= 200_000_000:
+            host = {k: torch.empty(n, dtype=torch.float64, pin_memory=True) for k in ("x", "v", "p", "w", "u_v", "u_x")}
+            hv = {k: t.numpy() for k, t in host.items()}
+            fill_uniforms(hv["u_v"], hv["u_x"], seed=1234 + rank)
+            ptr = {k: t.data_ptr() for k, t in host.items()}
+            e2e["host_stream_load"] = e2e_run(args.steps, lambda: g.load_markers(0, (ptr["u_v"], n), (ptr["u_x"], n), ntotal, v_max=8.0))
+            e2e["host_stream_load"]["definition"] = ("same with the two uniform streams generated by the host (SuperKISS64 / "
+                                                     "MT19937-64 have no device form): 16 B/marker of H2D in the load")
+            g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], p=ptr["p"], w=ptr["w"])
+            k2 = min(args.steps, 3)   # worst case: markers live on the host and make the round trip every step
+            barrier()
+            tw0 = time.perf_counter()
+            for it in range(k2):
+                g.set_markers_ptr(0, n, ptr["x"], ptr["v"], ptr["p"], ptr["w"])
+                g.collect_charge()
+                g.solve_field()
+                g.step(1)
+                g.get_field_ptr(hf["E"].data_ptr(), hf["rho"].data_ptr(), hf["re"].data_ptr(), hf["im"].data_ptr())
+                g.get_markers_ptr(0, x=ptr["x"], v=ptr["v"], w=ptr["w"])
+            tw2 = max_over_ranks(time.perf_counter() - tw0)
+            e2e["roundtrip_every_step"] = {"value": ntotal * k2 / tw2, "steps": k2,
+                                           "h2d_bytes_per_step": 4 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n + (2 * nx + 2) * 8}
+        # device time of one output step, and of the load
         g.timer_start()
-        g.output_field()
-        t_of = g.timer_stop()
+        g.output_all(64, 64, 8.0)
+        t_oa = g.timer_stop()
         g.timer_start()
-        g.output_ptcldist(0, 64, 64, 8.0)
-        t_op = g.timer_stop()
-        e2e["output_step_ms"] = {"output_field": t_of, "output_ptcldist": t_op}
+        load_from_host()
+        t_ld = g.timer_stop()
+        e2e["output_step_ms"] = {"output_all": t_oa}
+        e2e["particle_load_ms"] = t_ld
 
     # ---- CPU baseline beside it (rank 0, bounded sample) ----
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         ncpu = int(args.cpu_markers)
-        csteps = max(5, int(round(10.0 * 2e8 * cores / 16 / max(ncpu, 1))))  # ~10 s at ~1.2e7 particle-steps/s/core
-        val, secs = cpu_reference_run(args.nx, ncpu, csteps, 1, cores)
+        csteps = max(3, int(round(4.0 * 2e8 * cores / 16 / max(ncpu, 1))))  # ~4 s per run at ~1.2e7 particle-steps/s/core
+        val, secs, vals = cpu_reference_run(args.nx, ncpu, csteps, 1, cores, repeats=3)
         cpu = {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-               "sample": f"{ncpu} markers x {csteps} steps (+1 warm-up), nx={args.nx}, {cores} emulated MPI ranks; {secs:.1f} s",
+               "sample": f"{ncpu} markers x {csteps} steps (+1 warm-up), nx={args.nx}, {cores} emulated MPI ranks; median of 3 "
+                         f"runs {['%.3g' % v for v in vals]}, {secs:.1f} s each",
                "note": "CPU restatement of the reference loops (oracle/), not the PETSc binary"}
 
     if rank == 0:
         line = {
             "metric": "particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
+            "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
             "nccl_calls": int(c1.nccl_calls - c0.nccl_calls),
             "p2p_allreduces": int(c1.p2p_allreduces - c0.p2p_allreduces), "p2p_timeouts": int(c1.p2p_timeouts),
+            "parity_check": parity,
             "roofline": roofline, "roofline_detail": roofline_detail, "cpu_baseline": cpu,
             "deposit_mode": int(c1.deposit_mode), "grid_ctas": int(c1.grid_ctas), "cta_threads": int(c1.cta_threads),
             "smem_bytes": int(c1.smem_bytes), "oob_markers": int(c1.oob_markers), "field_energy": energy,

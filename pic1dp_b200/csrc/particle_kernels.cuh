@@ -574,6 +574,24 @@ struct Depositor;
 // every depositor: prescale(q) is applied to the deposit source before the weights (identity except DEP_FIXED)
 #define PIC1DP_DEP_NO_PRESCALE \
   __device__ __forceinline__ double prescale(double q) { return q; }
+// add2: the two markers of a thread in one call (same validity); the CAS depositors overlap the two round trips
+#define PIC1DP_DEP_ADD2_SERIAL                                                                                     \
+  __device__ __forceinline__ void add2(int ix0, int ixr0, double a0, double b0, int ix1, int ixr1, double a1, double b1, \
+                                       bool valid) {                                                               \
+    add(ix0, ixr0, a0, b0, valid);                                                                                 \
+    add(ix1, ixr1, a1, b1, valid);                                                                                 \
+  }
+
+// 128-bit compare-and-swap on a shared-memory slot: returns the previous content in (f0, f1)
+__device__ __forceinline__ void cas128(unsigned addr, unsigned long long e0, unsigned long long e1, unsigned long long d0,
+                                       unsigned long long d1, unsigned long long &f0, unsigned long long &f1) {
+  asm volatile(
+      "{\n\t.reg .b128 c, d, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
+      "atom.shared.cas.b128 o, [%6], c, d;\n\tmov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(f0), "=l"(f1)
+      : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "r"(addr)
+      : "memory");
+}
 
 // per-CTA shared grid of pairs {sum of left weights landing in cell j, sum of right weights of markers whose LEFT
 // cell is j}: both contributions of a marker go to one 16-byte slot, so one ATOMS.CAS.128 loop replaces two 64-bit
@@ -603,6 +621,36 @@ struct Depositor<DEP_SMEM_ATOMIC> {
       old.y = __longlong_as_double(f1);
     }
   }
+  // Both markers of a thread: the two slot loads, then the two CAS, are issued back to back so that their shared-memory
+  // round trips overlap (the serial form exposes LDS -> DADD -> CAS -> compare twice: 22 % of the stall samples of the
+  // irk = 1 kernel); a failed first attempt falls into the ordinary retry loop.  Equal slots are fine: the second CAS
+  // then fails against the first one's update and retries.
+  __device__ __forceinline__ void add2(int ix0, int ixr0, double a0, double b0, int ix1, int ixr1, double a1, double b1,
+                                       bool valid) {
+    (void)ixr0;
+    (void)ixr1;
+    if (!valid) return;
+    double2 *s0 = reinterpret_cast<double2 *>(g) + ix0, *s1 = reinterpret_cast<double2 *>(g) + ix1;
+    const unsigned ad0 = (unsigned)__cvta_generic_to_shared(s0), ad1 = (unsigned)__cvta_generic_to_shared(s1);
+    const double2 o0 = *s0, o1 = *s1;
+    unsigned long long e00 = __double_as_longlong(o0.x), e01 = __double_as_longlong(o0.y);
+    unsigned long long e10 = __double_as_longlong(o1.x), e11 = __double_as_longlong(o1.y);
+    unsigned long long f00, f01, f10, f11;
+    cas128(ad0, e00, e01, __double_as_longlong(dadd(o0.x, a0)), __double_as_longlong(dadd(o0.y, b0)), f00, f01);
+    cas128(ad1, e10, e11, __double_as_longlong(dadd(o1.x, a1)), __double_as_longlong(dadd(o1.y, b1)), f10, f11);
+    while (!(f00 == e00 && f01 == e01)) {
+      e00 = f00;
+      e01 = f01;
+      cas128(ad0, e00, e01, __double_as_longlong(dadd(__longlong_as_double(e00), a0)),
+             __double_as_longlong(dadd(__longlong_as_double(e01), b0)), f00, f01);
+    }
+    while (!(f10 == e10 && f11 == e11)) {
+      e10 = f10;
+      e11 = f11;
+      cas128(ad1, e10, e11, __double_as_longlong(dadd(__longlong_as_double(e10), a1)),
+             __double_as_longlong(dadd(__longlong_as_double(e11), b1)), f10, f11);
+    }
+  }
 };
 
 // fire-and-forget RED.ADD.F64 into this CTA's private global (L2-resident) grid
@@ -610,6 +658,7 @@ template <>
 struct Depositor<DEP_GLOBAL_RED> {
   double *g;
   PIC1DP_DEP_NO_PRESCALE
+  PIC1DP_DEP_ADD2_SERIAL
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     if (valid) {
       atomicAdd(&g[ix], a);  // result unused -> REDG.E.ADD.F64
@@ -626,6 +675,7 @@ template <>
 struct Depositor<DEP_WARP_PRIVATE> {
   double *g;  // this warp's grid
   PIC1DP_DEP_NO_PRESCALE
+  PIC1DP_DEP_ADD2_SERIAL
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
@@ -698,41 +748,63 @@ struct Depositor<DEP_FIXED> {
     seen_hi = max(seen_hi, (unsigned)__double2hiint(q) & 0x7fffffffu);
     return dmul(q, scale);  // exact (power of two)
   }
+  // |content| >= th * 2^32 in either component of a slot
+  __device__ __forceinline__ bool is_full(unsigned long long e0, unsigned long long e1) const {
+    return ((unsigned)(e0 >> 32) + sp.th >= 2 * sp.th) | ((unsigned)(e1 >> 32) + sp.th >= 2 * sp.th);
+  }
+  // one CAS attempt at adding (ia, ib) to the slot whose content was last seen as (e0, e1); a full slot is swapped to
+  // zero instead (its old content then belongs to the winner, who spills it).  Returns true when the add went in.
+  __device__ __forceinline__ bool attempt(unsigned addr, int ix, unsigned long long &e0, unsigned long long &e1, long long ia,
+                                          long long ib) {
+    const bool full = is_full(e0, e1);
+    unsigned long long f0, f1;
+    cas128(addr, e0, e1, full ? 0ULL : e0 + (unsigned long long)ia, full ? 0ULL : e1 + (unsigned long long)ib, f0, f1);
+    const bool won = (f0 == e0) & (f1 == e1);
+    if (__builtin_expect(won & full, 0)) {   // this thread emptied the slot: it owns the old content
+      fixed_spill_add(sp.acc + 4 * (size_t)ix, (long long)e0);
+      fixed_spill_add(sp.acc + 4 * (size_t)ix + 2, (long long)e1);
+      *sp.flag = 1;
+      e0 = 0;
+      e1 = 0;
+      return false;
+    }
+    e0 = f0;
+    e1 = f1;
+    return won;
+  }
+  // double -> int64, round to nearest: the integer lands in the low mantissa bits of x + 1.5 * 2^52
+  static __device__ __forceinline__ long long to_fixed(double x) {
+    const double magic = 6755399441055744.0;
+    return __double_as_longlong(dadd(x, magic)) - __double_as_longlong(magic);
+  }
   // a, b = weight * prescaled source: RN(weight * source) * 2^e exactly, then rounded to the nearest integer
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     (void)ixr;
     if (!valid) return;
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: the integer lands in the low mantissa bits
-    const long long ia = __double_as_longlong(dadd(a, magic)) - __double_as_longlong(magic);
-    const long long ib = __double_as_longlong(dadd(b, magic)) - __double_as_longlong(magic);
+    const long long ia = to_fixed(a), ib = to_fixed(b);
     longlong2 *slot = reinterpret_cast<longlong2 *>(g) + ix;
     const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
-    longlong2 old = *slot;
-    for (;;) {
-      const unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
-      // |old| >= th * 2^32 in either component: move the slot's content to its 128-bit accumulator first
-      const bool full = ((unsigned)(e0 >> 32) + sp.th >= 2 * sp.th) | ((unsigned)(e1 >> 32) + sp.th >= 2 * sp.th);
-      const unsigned long long d0 = full ? 0ULL : e0 + (unsigned long long)ia, d1 = full ? 0ULL : e1 + (unsigned long long)ib;
-      unsigned long long f0, f1;
-      asm volatile(
-          "{\n\t.reg .b128 c, d, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
-          "atom.shared.cas.b128 o, [%6], c, d;\n\tmov.b128 {%0, %1}, o;\n\t}"
-          : "=l"(f0), "=l"(f1)
-          : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "r"(addr)
-          : "memory");
-      const bool won = (f0 == e0) & (f1 == e1);
-      if (__builtin_expect(won & full, 0)) {   // this thread emptied the slot: it owns the old content
-        fixed_spill_add(sp.acc + 4 * (size_t)ix, (long long)e0);
-        fixed_spill_add(sp.acc + 4 * (size_t)ix + 2, (long long)e1);
-        *sp.flag = 1;
-        old.x = 0;
-        old.y = 0;
-        continue;
-      }
-      if (won) break;
-      old.x = (long long)f0;
-      old.y = (long long)f1;
+    const longlong2 old = *slot;
+    unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
+    while (!attempt(addr, ix, e0, e1, ia, ib)) {
     }
+  }
+  // both markers of a thread with overlapped round trips (see Depositor<DEP_SMEM_ATOMIC>::add2)
+  __device__ __forceinline__ void add2(int ix0, int ixr0, double a0, double b0, int ix1, int ixr1, double a1, double b1,
+                                       bool valid) {
+    (void)ixr0;
+    (void)ixr1;
+    if (!valid) return;
+    const long long ia0 = to_fixed(a0), ib0 = to_fixed(b0), ia1 = to_fixed(a1), ib1 = to_fixed(b1);
+    longlong2 *s0 = reinterpret_cast<longlong2 *>(g) + ix0, *s1 = reinterpret_cast<longlong2 *>(g) + ix1;
+    const unsigned ad0 = (unsigned)__cvta_generic_to_shared(s0), ad1 = (unsigned)__cvta_generic_to_shared(s1);
+    const longlong2 o0 = *s0, o1 = *s1;
+    unsigned long long e00 = (unsigned long long)o0.x, e01 = (unsigned long long)o0.y;
+    unsigned long long e10 = (unsigned long long)o1.x, e11 = (unsigned long long)o1.y;
+    bool ok0 = attempt(ad0, ix0, e00, e01, ia0, ib0);
+    bool ok1 = attempt(ad1, ix1, e10, e11, ia1, ib1);
+    while (!ok0) ok0 = attempt(ad0, ix0, e00, e01, ia0, ib0);
+    while (!ok1) ok1 = attempt(ad1, ix1, e10, e11, ia1, ib1);
   }
 };
 
@@ -888,8 +960,8 @@ __device__ __forceinline__ bool push_pair_fast(const ParticleArgs &a, const doub
   if (FUSED) {
     // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
     const double q0 = dep.prescale(deltaf ? awo[0] : p.x), q1 = dep.prescale(deltaf ? awo[1] : p.y);
-    dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0), !rare);  // :110, :113
-    dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
+    dep.add2(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0),       // :110, :113
+             sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
     noob += (!rare && od[0]) + (!rare && od[1]);
   }
   return rare;
