@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--sustained-steps", type=int, default=500, help="steps of the additional sustained region (0 = off)")
     ap.add_argument("--e2e-extras", action="store_true", help="also time the host-stream and host-refresh e2e variants")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--p2p-trace", action="store_true",
+                    help="stamp %%globaltimer at publish / wait entry / wait exit of every peer-memory all-reduce of the "
+                         "timed region and report arrival skew vs exchange latency (adds 'p2p_trace' to the JSON line)")
     ap.add_argument("--deposit", type=int, default=0, help="PIC1DP_DEPOSIT_* (0 = auto)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "p2p"],
                     help="density all-reduce: NCCL or peer-memory exchange (auto = p2p when it can be set up)")
@@ -59,6 +62,9 @@ def parse():
     ap.add_argument("--arith", default="strict", choices=["strict", "tolerance"],
                     help="PIC1DP_ARITH_*: strict = the reference's operation order everywhere; tolerance = w path with one "
                          "exponential (x, v, cell index still bit-exact)")
+    ap.add_argument("--no-launch-timing", action="store_true",
+                    help="no per-launch CUDA events inside the timed region (the region then replays the step graph; the "
+                         "per-kernel times come from separately profiled steps) -- for small problems, where launch gaps matter")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one (no CUDA graph replay)")
     ap.add_argument("--cpu-markers", type=float, default=2e7, help="markers of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -276,6 +282,33 @@ def setup_comm(P, dist, g, args, rank, world):
     return "nccl"
 
 
+def analyse_trace(rows, nepochs, cap):
+    """rows[r] = (stamps[cap][3] = publish, wait entry, wait exit in rank r's own %globaltimer ns, last epoch).
+    Per all-reduce and rank: d = wait_exit - publish.  The rank that arrived last waits only for the kernel boundary and
+    the flag reads, so min over ranks of d is the exchange floor; what the other ranks wait beyond it is arrival skew
+    (they finished their particle kernel earlier).  No cross-GPU clock synchronisation is needed: every difference is
+    taken on one GPU's clock."""
+    last = min(r[1] for r in rows)
+    eps = [e for e in range(last - nepochs + 1, last + 1) if e > 0]
+    d = np.array([[rows[r][0][e % cap][2] - rows[r][0][e % cap][0] for r in range(len(rows))] for e in eps], dtype=np.float64)
+    gap = np.array([[rows[r][0][e % cap][1] - rows[r][0][e % cap][0] for r in range(len(rows))] for e in eps], dtype=np.float64)
+    spin = np.array([[rows[r][0][e % cap][2] - rows[r][0][e % cap][1] for r in range(len(rows))] for e in eps], dtype=np.float64)
+    floor = d.min(axis=1)
+    skew = d - floor[:, None]
+    q = lambda a, p: float(np.percentile(a, p)) / 1e3
+    return {"allreduces": len(eps), "ranks": len(rows), "unit": "us",
+            "publish_to_wait_exit": {"median": q(d, 50), "p95": q(d, 95), "max": q(d, 100)},
+            "exchange_floor_min_over_ranks": {"median": q(floor, 50), "p95": q(floor, 95)},
+            "kernel_boundary_publish_to_wait_entry": {"median": q(gap, 50), "p95": q(gap, 95)},
+            "spin_wait_entry_to_exit": {"median": q(spin, 50), "mean": float(spin.mean()) / 1e3, "p95": q(spin, 95)},
+            "arrival_skew_wait": {"mean": float(skew.mean()) / 1e3, "median": q(skew, 50), "p95": q(skew, 95),
+                                  "mean_of_worst_rank": float(skew.max(axis=1).mean()) / 1e3},
+            "per_step_cost_us": {"exchange_floor": 2 * float(floor.mean()) / 1e3,
+                                 "skew_mean_rank": 2 * float(skew.mean()) / 1e3,
+                                 "skew_worst_rank": 2 * float(skew.max(axis=1).mean()) / 1e3},
+            "note": "d = wait_exit - publish per rank and all-reduce; floor = min over ranks (the last arrival); skew = d - floor"}
+
+
 def parity_preflight(P, dist, torch, args, rank, world, local):
     """tests/mgpu_worker.py's comparison inside the bench run, so that every multi-GPU line carries its own parity
     evidence: 4e5 markers split by the PETSC_DECIDE rule over the N ranks, 5 steps through the same all-reduce path the
@@ -419,14 +452,19 @@ def main():
     g.collect_charge()
     g.solve_field()
     g.step(args.warmup)
+    tracing = args.p2p_trace and world > 1 and g.counters().p2p_allreduces > 0
+    if tracing:
+        g.p2p_trace(4 * args.steps + 16)
+        g.step(1)   # re-captures the step graph with the trace buffer
     barrier()
     c0 = g.counters()
     t0 = time.time()
-    g.launch_timing_start()   # event pair around every fused particle-kernel launch of the timed region
+    if not args.no_launch_timing:
+        g.launch_timing_start()   # event pair around every fused particle-kernel launch of the timed region
     g.timer_start()
     g.step(args.steps)
     ms = g.timer_stop()
-    lt = g.launch_timing_stop()
+    lt = g.launch_timing_stop() if not args.no_launch_timing else [(0.0, 0), (0.0, 0)]
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
@@ -434,6 +472,15 @@ def main():
     ms = max_over_ranks(ms)
     value = ntotal * args.steps / (ms * 1e-3)
     energy = g.field_energy()
+    p2p_trace = None
+    if tracing:
+        cap = 4 * args.steps + 16
+        stamps, last = g.p2p_trace_read(cap)
+        g.p2p_trace(0)
+        rows = [None] * world
+        dist.all_gather_object(rows, (stamps.astype(np.int64), int(last)))
+        if rank == 0:
+            p2p_trace = analyse_trace(rows, 2 * args.steps, cap)
 
     # ---- sustained: the same loop for >= 500 further steps (graph replay, no per-launch events) ----
     sustained = None
@@ -476,7 +523,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_push<bump-on-tail, irk=2, fused push+wrap+deposit>",
                 "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "ms_per_launch": float(prof[3]), "launches_timed": int(lt[1][1]),
-                "timing": "CUDA events around each launch of this kernel inside the timed region, on the library's stream",
+                "timing": ("CUDA events around each launch of this kernel inside the timed region, on the library's stream"
+                           if lt[1][1] > 0 else "CUDA events around this kernel in 4 separately profiled steps (graph-replay run)"),
                 "algorithmic_bytes_per_launch": n * BYTES_IRK2}
     roofline_detail = {
         "irk1": {"achieved": ach1, "frac": ach1 / peak, "ms_per_launch": float(prof[0]), "bytes": n * BYTES_IRK1},
@@ -574,7 +622,7 @@ def main():
             "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
             "nccl_calls": int(c1.nccl_calls - c0.nccl_calls),
             "p2p_allreduces": int(c1.p2p_allreduces - c0.p2p_allreduces), "p2p_timeouts": int(c1.p2p_timeouts),
-            "parity_check": parity,
+            "parity_check": parity, "p2p_trace": p2p_trace,
             "roofline": roofline, "roofline_detail": roofline_detail, "cpu_baseline": cpu,
             "deposit_mode": int(c1.deposit_mode), "grid_ctas": int(c1.grid_ctas), "cta_threads": int(c1.cta_threads),
             "smem_bytes": int(c1.smem_bytes), "oob_markers": int(c1.oob_markers), "field_energy": energy,

@@ -26,6 +26,16 @@
 #ifndef PIC1DP_PV_MASK
 #define PIC1DP_PV_MASK 4
 #endif
+// which CAS depositors deposit the two markers of a thread with overlapped round trips (Depositor::add2): bit 0 the
+// fp64 pair grid, bit 1 the fixed-point pair grid.  Measured on B200 (profiles/r02_ab_experiments.md): the overlap hides
+// the CAS latency but the extra live registers spill at 64 registers per thread and the kernels get slower.
+#ifndef PIC1DP_ADD2
+#define PIC1DP_ADD2 0
+#endif
+// fixed-point conversion: 1 = F2I.S64.F64, 0 = magic-number add + integer subtract
+#ifndef PIC1DP_FIXED_F2I
+#define PIC1DP_FIXED_F2I 1
+#endif
 
 namespace pic1dp {
 
@@ -752,30 +762,45 @@ struct Depositor<DEP_FIXED> {
   __device__ __forceinline__ bool is_full(unsigned long long e0, unsigned long long e1) const {
     return ((unsigned)(e0 >> 32) + sp.th >= 2 * sp.th) | ((unsigned)(e1 >> 32) + sp.th >= 2 * sp.th);
   }
-  // one CAS attempt at adding (ia, ib) to the slot whose content was last seen as (e0, e1); a full slot is swapped to
-  // zero instead (its old content then belongs to the winner, who spills it).  Returns true when the add went in.
-  __device__ __forceinline__ bool attempt(unsigned addr, int ix, unsigned long long &e0, unsigned long long &e1, long long ia,
-                                          long long ib) {
-    const bool full = is_full(e0, e1);
+  // slow path of attempt(): the slot is full -- swap it to zero; the winner owns the old content and adds it to the
+  // slot's 128-bit accumulator.  Afterwards (e0, e1) hold the slot's current content again.
+  __device__ __noinline__ void spill_slot(unsigned addr, int ix, unsigned long long &e0, unsigned long long &e1) {
     unsigned long long f0, f1;
-    cas128(addr, e0, e1, full ? 0ULL : e0 + (unsigned long long)ia, full ? 0ULL : e1 + (unsigned long long)ib, f0, f1);
-    const bool won = (f0 == e0) & (f1 == e1);
-    if (__builtin_expect(won & full, 0)) {   // this thread emptied the slot: it owns the old content
+    cas128(addr, e0, e1, 0ULL, 0ULL, f0, f1);
+    if (f0 == e0 && f1 == e1) {
       fixed_spill_add(sp.acc + 4 * (size_t)ix, (long long)e0);
       fixed_spill_add(sp.acc + 4 * (size_t)ix + 2, (long long)e1);
       *sp.flag = 1;
       e0 = 0;
       e1 = 0;
+    } else {
+      e0 = f0;
+      e1 = f1;
+    }
+  }
+  // one CAS attempt at adding (ia, ib) to the slot whose content was last seen as (e0, e1).  Returns true when the add
+  // went in; otherwise (e0, e1) hold the content to retry with.
+  __device__ __forceinline__ bool attempt(unsigned addr, int ix, unsigned long long &e0, unsigned long long &e1, long long ia,
+                                          long long ib) {
+    if (__builtin_expect(is_full(e0, e1), 0)) {
+      spill_slot(addr, ix, e0, e1);
       return false;
     }
+    unsigned long long f0, f1;
+    cas128(addr, e0, e1, e0 + (unsigned long long)ia, e1 + (unsigned long long)ib, f0, f1);
+    const bool won = (f0 == e0) & (f1 == e1);
     e0 = f0;
     e1 = f1;
     return won;
   }
   // double -> int64, round to nearest: the integer lands in the low mantissa bits of x + 1.5 * 2^52
   static __device__ __forceinline__ long long to_fixed(double x) {
+#if PIC1DP_FIXED_F2I
+    return __double2ll_rn(x);
+#else
     const double magic = 6755399441055744.0;
     return __double_as_longlong(dadd(x, magic)) - __double_as_longlong(magic);
+#endif
   }
   // a, b = weight * prescaled source: RN(weight * source) * 2^e exactly, then rounded to the nearest integer
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
@@ -960,8 +985,14 @@ __device__ __forceinline__ bool push_pair_fast(const ParticleArgs &a, const doub
   if (FUSED) {
     // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
     const double q0 = dep.prescale(deltaf ? awo[0] : p.x), q1 = dep.prescale(deltaf ? awo[1] : p.y);
-    dep.add2(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0),       // :110, :113
-             sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
+    constexpr bool OVERLAP = (DEP == DEP_SMEM_ATOMIC && (PIC1DP_ADD2 & 1)) || (DEP == DEP_FIXED && (PIC1DP_ADD2 & 2));
+    if constexpr (OVERLAP) {
+      dep.add2(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0),       // :110, :113
+               sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
+    } else {
+      dep.add(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0), !rare);  // :110, :113
+      dep.add(sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
+    }
     noob += (!rare && od[0]) + (!rare && od[1]);
   }
   return rare;
