@@ -117,8 +117,41 @@ __global__ void __launch_bounds__(512) k_diag(const DiagArgs a) {
 // = 6 atomics per marker instead of the 8 of the round-1 kernel.  Both divisions use the exact-reciprocal form of the
 // push kernels (div_const: bit-identical to IEEE division, IEEE fallback inside).  The grid is flushed to one of the
 // ncopies L2-resident grids with RED.ADD.F64.
+// K pair-slot additions of one thread with overlapped round trips: all slot loads, then all CAS, then the checks; a
+// failed attempt re-reads its slot and retries alone.  The serial form is bound by the latency of 6 dependent
+// LDS -> DADD -> CAS -> compare chains per marker (ncu: 52 % short-scoreboard stalls, 28 % issue utilisation).
+template <int K>
+__device__ __forceinline__ void cas_add_batch(double *grid0, double *grid1, const int (&slot)[K], const double (&ax)[K],
+                                              const double (&ay)[K], const int nfirst) {
+  unsigned addr[K];
+  double2 old[K];
+  unsigned long long f0[K], f1[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double2 *p = reinterpret_cast<double2 *>(k < nfirst ? grid0 : grid1) + slot[k];
+    addr[k] = (unsigned)__cvta_generic_to_shared(p);
+    old[k] = *p;
+  }
+#pragma unroll
+  for (int k = 0; k < K; k++)
+    cas128(addr[k], __double_as_longlong(old[k].x), __double_as_longlong(old[k].y),
+           __double_as_longlong(dadd(old[k].x, ax[k])), __double_as_longlong(dadd(old[k].y, ay[k])), f0[k], f1[k]);
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    unsigned long long e0 = __double_as_longlong(old[k].x), e1 = __double_as_longlong(old[k].y);
+    while (!(f0[k] == e0 && f1[k] == e1)) {
+      double2 o;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o.x), "=d"(o.y) : "r"(addr[k]) : "memory");
+      e0 = __double_as_longlong(o.x);
+      e1 = __double_as_longlong(o.y);
+      cas128(addr[k], e0, e1, __double_as_longlong(dadd(o.x, ax[k])), __double_as_longlong(dadd(o.y, ay[k])), f0[k], f1[k]);
+    }
+  }
+}
+
+#define PIC1DP_DIAG_THREADS 512
 template <bool SUMS>
-__global__ void __launch_bounds__(1024, 1) k_diag_fused(const DiagArgs a) {
+__global__ void __launch_bounds__(PIC1DP_DIAG_THREADS, 1) k_diag_fused(const DiagArgs a) {
   extern __shared__ __align__(16) double sh[];
   __shared__ double s_red[3][32];
   const int nxo = a.nx_opd, ncell = nxo * a.nv_opd, ncell1 = nxo * (a.nv_opd + 1);
@@ -128,9 +161,6 @@ __global__ void __launch_bounds__(1024, 1) k_diag_fused(const DiagArgs a) {
   __syncthreads();
   const double rnx = (double)nxo, rnv = (double)(a.nv_opd - 1), two_vmax = dmul(a.v_max, 2.0);
   const double rlx = 1.0 / a.lx, r2v = 1.0 / two_vmax;
-  Depositor<DEP_SMEM_ATOMIC> gf, pp;
-  gf.g = s_mt;
-  pp.g = s_pp;
   double s_vv = 0.0, s_vvp = 0.0, s_vvw = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.np; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = __ldcs(a.v + i), p = __ldcs(a.p + i);
@@ -158,13 +188,15 @@ __global__ void __launch_bounds__(1024, 1) k_diag_fused(const DiagArgs a) {
     const double sx2 = dsub(1.0, sx), sv2 = dsub(1.0, sv);  // :273
     const int r0 = iv * nxo, r1 = r0 + nxo;
     const double w00 = dmul(sx, sv), w10 = dmul(sx, sv2), w01 = dmul(sx2, sv), w11 = dmul(sx2, sv2);
-    gf.add(r0 + ix, 0, w00, dmul(w00, p), true);
-    gf.add(r1 + ix, 0, w10, dmul(w10, p), true);
-    gf.add(r0 + ix2, 0, w01, dmul(w01, p), true);
-    gf.add(r1 + ix2, 0, w11, dmul(w11, p), true);
+    const int slot[6] = {r0 + ix, r1 + ix, r0 + ix2, r1 + ix2, r0 + ix, r1 + ix};
+    const double ax[6] = {w00, w10, w01, w11, dmul(w00, w), dmul(w10, w)};
+    const double ay[6] = {dmul(w00, p), dmul(w10, p), dmul(w01, p), dmul(w11, p), dmul(w01, w), dmul(w11, w)};
     if (a.deltaf) {
-      pp.add(r0 + ix, 0, dmul(w00, w), dmul(w01, w), true);
-      pp.add(r1 + ix, 0, dmul(w10, w), dmul(w11, w), true);
+      cas_add_batch<6>(s_mt, s_pp, slot, ax, ay, 4);
+    } else {
+      const int slot4[4] = {slot[0], slot[1], slot[2], slot[3]};
+      const double ax4[4] = {ax[0], ax[1], ax[2], ax[3]}, ay4[4] = {ay[0], ay[1], ay[2], ay[3]};
+      cas_add_batch<4>(s_mt, s_pp, slot4, ax4, ay4, 4);
     }
   }
   __syncthreads();

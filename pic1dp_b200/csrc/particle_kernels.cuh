@@ -100,10 +100,8 @@ __device__ __forceinline__ double div_pos(double a, double b) {
   const unsigned ea = (unsigned)(__double2hiint(a) & 0x7ff00000) - (523u << 20);
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));  // MUFU.RCP64H: ~20 good bits
-  double e = fma(-b, y, 1.0);
-  e = fma(e, e, e);
-  y = fma(y, e, y);
-  e = fma(-b, y, 1.0);
+  double e = fma(-b, y, 1.0);   // 2^-20; y (1 + e + e^2) is 1/b to ~2^-60: one cubic step reaches working precision,
+  e = fma(e, e, e);             // and q1 below only needs y to an ulp (error of q1 ~ eps(q0) * eps(y) = 2^-104)
   y = fma(y, e, y);
   const double q0 = a * y;
   const double r = fma(-q0, b, a);
@@ -336,8 +334,6 @@ __device__ __forceinline__ void div_pos_n(const double (&a)[N], const double (&b
     double e = fma(-b[k], y, 1.0);
     e = fma(e, e, e);
     y = fma(y, e, y);
-    e = fma(-b[k], y, 1.0);
-    y = fma(y, e, y);
     const double q0 = a[k] * y;
     const double r = fma(-q0, b[k], a[k]);
     q[k] = fma(r, y, q0);
@@ -464,7 +460,7 @@ __device__ __forceinline__ void dlnf0_impl_n(const SpeciesConst &c, const double
 #undef DIVC
 }
 
-// a / b without the correctly-rounded guarantee (<= ~1 ulp): reciprocal seed, two Newton steps, one residual correction.
+// a / b without the correctly-rounded guarantee (<= ~1 ulp): reciprocal seed, one cubic Newton step, one residual correction.
 // TOLERANCE arithmetic only; operands far outside the normal range still raise the flag.
 template <int N>
 __device__ __forceinline__ void div_fast_n(const double (&a)[N], const double (&b)[N], double (&q)[N], bool &rare) {
@@ -475,8 +471,6 @@ __device__ __forceinline__ void div_fast_n(const double (&a)[N], const double (&
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b[k]));
     double e = fma(-b[k], y, 1.0);
     e = fma(e, e, e);
-    y = fma(y, e, y);
-    e = fma(-b[k], y, 1.0);
     y = fma(y, e, y);
     const double q0 = a[k] * y;
     q[k] = fma(fma(-q0, b[k], a[k]), y, q0);
@@ -615,20 +609,14 @@ struct Depositor<DEP_SMEM_ATOMIC> {
     if (!valid) return;
     double2 *slot = reinterpret_cast<double2 *>(g) + ix;
     const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
-    double2 old = *slot;
+    // a failed attempt re-reads the slot instead of recycling the value the CAS returned: the returned registers are
+    // then only compared, which saves ptxas four register moves per attempt on the (common) success path
     for (;;) {
+      const double2 old = *slot;
       const unsigned long long e0 = __double_as_longlong(old.x), e1 = __double_as_longlong(old.y);
-      const unsigned long long d0 = __double_as_longlong(dadd(old.x, a)), d1 = __double_as_longlong(dadd(old.y, b));
       unsigned long long f0, f1;
-      asm volatile(
-          "{\n\t.reg .b128 c, d, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 d, {%4, %5};\n\t"
-          "atom.shared.cas.b128 o, [%6], c, d;\n\tmov.b128 {%0, %1}, o;\n\t}"
-          : "=l"(f0), "=l"(f1)
-          : "l"(e0), "l"(e1), "l"(d0), "l"(d1), "r"(addr)
-          : "memory");
+      cas128(addr, e0, e1, __double_as_longlong(dadd(old.x, a)), __double_as_longlong(dadd(old.y, b)), f0, f1);
       if (f0 == e0 && f1 == e1) break;
-      old.x = __longlong_as_double(f0);
-      old.y = __longlong_as_double(f1);
     }
   }
   // Both markers of a thread: the two slot loads, then the two CAS, are issued back to back so that their shared-memory
@@ -762,20 +750,16 @@ struct Depositor<DEP_FIXED> {
   __device__ __forceinline__ bool is_full(unsigned long long e0, unsigned long long e1) const {
     return ((unsigned)(e0 >> 32) + sp.th >= 2 * sp.th) | ((unsigned)(e1 >> 32) + sp.th >= 2 * sp.th);
   }
-  // slow path of attempt(): the slot is full -- swap it to zero; the winner owns the old content and adds it to the
-  // slot's 128-bit accumulator.  Afterwards (e0, e1) hold the slot's current content again.
-  __device__ __noinline__ void spill_slot(unsigned addr, int ix, unsigned long long &e0, unsigned long long &e1) {
+  // slow path: the slot is full -- swap it to zero; the winner owns the old content and adds it to the slot's 128-bit
+  // accumulator.  Everything by value (reference parameters of a noinline function would force the caller's slot
+  // registers through local memory on the hot path); the caller re-reads the slot afterwards.
+  __device__ __noinline__ void spill_slot(unsigned addr, int ix, unsigned long long e0, unsigned long long e1) const {
     unsigned long long f0, f1;
     cas128(addr, e0, e1, 0ULL, 0ULL, f0, f1);
     if (f0 == e0 && f1 == e1) {
       fixed_spill_add(sp.acc + 4 * (size_t)ix, (long long)e0);
       fixed_spill_add(sp.acc + 4 * (size_t)ix + 2, (long long)e1);
       *sp.flag = 1;
-      e0 = 0;
-      e1 = 0;
-    } else {
-      e0 = f0;
-      e1 = f1;
     }
   }
   // one CAS attempt at adding (ia, ib) to the slot whose content was last seen as (e0, e1).  Returns true when the add
@@ -784,6 +768,7 @@ struct Depositor<DEP_FIXED> {
                                           long long ib) {
     if (__builtin_expect(is_full(e0, e1), 0)) {
       spill_slot(addr, ix, e0, e1);
+      asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(e0), "=l"(e1) : "r"(addr) : "memory");
       return false;
     }
     unsigned long long f0, f1;
@@ -809,9 +794,16 @@ struct Depositor<DEP_FIXED> {
     const long long ia = to_fixed(a), ib = to_fixed(b);
     longlong2 *slot = reinterpret_cast<longlong2 *>(g) + ix;
     const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
-    const longlong2 old = *slot;
-    unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
-    while (!attempt(addr, ix, e0, e1, ia, ib)) {
+    for (;;) {   // a failed attempt re-reads the slot (see Depositor<DEP_SMEM_ATOMIC>::add)
+      const longlong2 old = *slot;
+      unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
+      if (__builtin_expect(is_full(e0, e1), 0)) {
+        spill_slot(addr, ix, e0, e1);
+        continue;
+      }
+      unsigned long long f0, f1;
+      cas128(addr, e0, e1, e0 + (unsigned long long)ia, e1 + (unsigned long long)ib, f0, f1);
+      if (f0 == e0 && f1 == e1) break;
     }
   }
   // both markers of a thread with overlapped round trips (see Depositor<DEP_SMEM_ATOMIC>::add2)

@@ -1534,9 +1534,9 @@ static int launch_hist(pic1dp_gpu_t *h, int isp, int nx_opd, int nv_opd, double 
       CK(cudaFuncSetAttribute(k_diag_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
       h->hist_smem_set = (int)hs;
     }
-    // one 1024-thread CTA per SM (at most diag_grid CTAs: the sum partials are sized for that)
-    if (with_sums) k_diag_fused<true><<<h->nsm, 1024, hs, h->stream>>>(a);
-    else k_diag_fused<false><<<h->nsm, 1024, hs, h->stream>>>(a);
+    // one CTA per SM (at most diag_grid CTAs: the sum partials are sized for that)
+    if (with_sums) k_diag_fused<true><<<h->nsm, PIC1DP_DIAG_THREADS, hs, h->stream>>>(a);
+    else k_diag_fused<false><<<h->nsm, PIC1DP_DIAG_THREADS, hs, h->stream>>>(a);
     CKL(h);
     if (with_sums) {
       k_diag_sums_final<<<1, 32, 0, h->stream>>>(h->d_diag_part, h->nsm, h->d_diag_sums + 3 * isp);

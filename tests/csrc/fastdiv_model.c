@@ -6,7 +6,7 @@
  * |fma(-q1, b, a)| <= b*ulp(q1)/2 passes; operands that fail it (or are out of range) are flagged and redone with the
  * IEEE division.  This program checks exactly that on the host, where fma() is exact and a/b is the IEEE quotient:
  * every NON-flagged case must equal a/b bit for bit, and the flag rate must stay small.  It models y either as
- * RN(1/b) (div_const) or as a ~20-bit approximation refined by the kernel's two Newton steps (div_pos, MUFU.RCP64H).
+ * RN(1/b) (div_const) or as a ~20-bit approximation refined by the kernel's cubic Newton step (div_pos, MUFU.RCP64H).
  *
  * usage: fastdiv_model <ncases> <seed>   -> prints "checked N flagged F mismatches M random_flagged R of K"
  * (R of K: flags among the plainly random operands, i.e. how often the hot loop would fall back on ordinary data)
@@ -45,15 +45,13 @@ static int div_const(double a, double b, double y, double *q) {
   return !(a >= 0x1p-800) || div_suspect(a, b, *q);
 }
 
-/* div_pos: y from a 20-bit reciprocal + the kernel's Newton steps */
+/* div_pos: y from a 20-bit reciprocal + the kernel's one cubic Newton step */
 static int div_pos(double a, double b, double *q) {
   const uint32_t eb = (uint32_t)((bits(b) >> 32) & 0x7ff00000u) - (523u << 20);
   const uint32_t ea = (uint32_t)((bits(a) >> 32) & 0x7ff00000u) - (523u << 20);
   double y = from_bits(bits(1.0 / b) & 0xffffffff00000000ULL); /* ~20 good bits like MUFU.RCP64H */
   double e = fma(-b, y, 1.0);
   e = fma(e, e, e);
-  y = fma(y, e, y);
-  e = fma(-b, y, 1.0);
   y = fma(y, e, y);
   const double q0 = a * y;
   const double r = fma(-q0, b, a);
