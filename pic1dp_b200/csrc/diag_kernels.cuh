@@ -117,39 +117,12 @@ __global__ void __launch_bounds__(512) k_diag(const DiagArgs a) {
 // = 6 atomics per marker instead of the 8 of the round-1 kernel.  Both divisions use the exact-reciprocal form of the
 // push kernels (div_const: bit-identical to IEEE division, IEEE fallback inside).  The grid is flushed to one of the
 // ncopies L2-resident grids with RED.ADD.F64.
-// K pair-slot additions of one thread with overlapped round trips: all slot loads, then all CAS, then the checks; a
-// failed attempt re-reads its slot and retries alone.  The serial form is bound by the latency of 6 dependent
-// LDS -> DADD -> CAS -> compare chains per marker (ncu: 52 % short-scoreboard stalls, 28 % issue utilisation).
-template <int K>
-__device__ __forceinline__ void cas_add_batch(double *grid0, double *grid1, const int (&slot)[K], const double (&ax)[K],
-                                              const double (&ay)[K], const int nfirst) {
-  unsigned addr[K];
-  double2 old[K];
-  unsigned long long f0[K], f1[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    double2 *p = reinterpret_cast<double2 *>(k < nfirst ? grid0 : grid1) + slot[k];
-    addr[k] = (unsigned)__cvta_generic_to_shared(p);
-    old[k] = *p;
-  }
-#pragma unroll
-  for (int k = 0; k < K; k++)
-    cas128(addr[k], __double_as_longlong(old[k].x), __double_as_longlong(old[k].y),
-           __double_as_longlong(dadd(old[k].x, ax[k])), __double_as_longlong(dadd(old[k].y, ay[k])), f0[k], f1[k]);
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    unsigned long long e0 = __double_as_longlong(old[k].x), e1 = __double_as_longlong(old[k].y);
-    while (!(f0[k] == e0 && f1[k] == e1)) {
-      double2 o;
-      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o.x), "=d"(o.y) : "r"(addr[k]) : "memory");
-      e0 = __double_as_longlong(o.x);
-      e1 = __double_as_longlong(o.y);
-      cas128(addr[k], e0, e1, __double_as_longlong(dadd(o.x, ax[k])), __double_as_longlong(dadd(o.y, ay[k])), f0[k], f1[k]);
-    }
-  }
-}
-
-#define PIC1DP_DIAG_THREADS 512
+// CTA size of the fused output kernel.  Measured on B200 at 1e8 markers (profiles/r02_ab_experiments.md): 1024 threads
+// with six serial CAS loops 2.83 ms; 512 threads 2.96 ms; issuing the six CAS of a marker as one overlapped batch is
+// slower (3.97 ms at 512 threads, 5.2 ms at 1024: the batch needs ~80 registers).
+#ifndef PIC1DP_DIAG_THREADS
+#define PIC1DP_DIAG_THREADS 1024
+#endif
 template <bool SUMS>
 __global__ void __launch_bounds__(PIC1DP_DIAG_THREADS, 1) k_diag_fused(const DiagArgs a) {
   extern __shared__ __align__(16) double sh[];
@@ -191,12 +164,14 @@ __global__ void __launch_bounds__(PIC1DP_DIAG_THREADS, 1) k_diag_fused(const Dia
     const int slot[6] = {r0 + ix, r1 + ix, r0 + ix2, r1 + ix2, r0 + ix, r1 + ix};
     const double ax[6] = {w00, w10, w01, w11, dmul(w00, w), dmul(w10, w)};
     const double ay[6] = {dmul(w00, p), dmul(w10, p), dmul(w01, p), dmul(w11, p), dmul(w01, w), dmul(w11, w)};
+    Depositor<DEP_SMEM_ATOMIC> gf, pp;
+    gf.g = s_mt;
+    pp.g = s_pp;
+#pragma unroll
+    for (int k = 0; k < 4; k++) gf.add(slot[k], 0, ax[k], ay[k], true);
     if (a.deltaf) {
-      cas_add_batch<6>(s_mt, s_pp, slot, ax, ay, 4);
-    } else {
-      const int slot4[4] = {slot[0], slot[1], slot[2], slot[3]};
-      const double ax4[4] = {ax[0], ax[1], ax[2], ax[3]}, ay4[4] = {ay[0], ay[1], ay[2], ay[3]};
-      cas_add_batch<4>(s_mt, s_pp, slot4, ax4, ay4, 4);
+      pp.add(slot[4], 0, ax[4], ay[4], true);
+      pp.add(slot[5], 0, ax[5], ay[5], true);
     }
   }
   __syncthreads();

@@ -26,15 +26,29 @@
 #ifndef PIC1DP_PV_MASK
 #define PIC1DP_PV_MASK 4
 #endif
-// which CAS depositors deposit the two markers of a thread with overlapped round trips (Depositor::add2): bit 0 the
-// fp64 pair grid, bit 1 the fixed-point pair grid.  Measured on B200 (profiles/r02_ab_experiments.md): the overlap hides
-// the CAS latency but the extra live registers spill at 64 registers per thread and the kernels get slower.
+// 1: the fp64 pair-grid depositor deposits the two markers of a thread with overlapped round trips (Depositor::add2).
+// Measured on B200 (profiles/r02_ab_experiments.md): the overlap hides the CAS latency but the extra live registers
+// spill at 64 registers per thread and the kernels get 2-4 % slower.
 #ifndef PIC1DP_ADD2
 #define PIC1DP_ADD2 0
 #endif
 // fixed-point conversion: 1 = F2I.S64.F64, 0 = magic-number add + integer subtract
 #ifndef PIC1DP_FIXED_F2I
 #define PIC1DP_FIXED_F2I 1
+#endif
+// experiment switches (profiles/r02_ab_experiments.md): CAS loops that re-read the slot on retry; second Newton step of
+// the reciprocal in the fast divisions (not needed for correctness: the residual test certifies the quotient)
+#ifndef PIC1DP_CAS_RELOAD
+#define PIC1DP_CAS_RELOAD 0
+#endif
+// work assignment of the fused kernel: 1 = every CTA owns one contiguous range of markers (balanced to one warp's 64
+// markers; the next tile step is a constant 16 KB ahead, so the L2 prefetch needs no address arithmetic),
+// 0 = tiles dealt round-robin over the CTAs (round 1)
+#ifndef PIC1DP_CHUNKED
+#define PIC1DP_CHUNKED 1
+#endif
+#ifndef PIC1DP_NEWTON2
+#define PIC1DP_NEWTON2 0
 #endif
 
 namespace pic1dp {
@@ -188,8 +202,6 @@ struct ParticleArgs {
   // that a captured step graph can be replayed; raised with atomicMax by the kernels), and the overflow counter
   unsigned *dep_wmax_hi;
   unsigned long long *dep_overflow;
-  unsigned long long *dep_spill;   // [gridDim.x][2 * nx][2]: 128-bit spill accumulators of the int64 slots (all zero between launches)
-  unsigned dep_spill_th;           // spill threshold in units of 2^32 (0x40000000 = 2^62)
 };
 
 // ---- periodic wrap: px = mod(px, lx); if (px < 0) px = px + lx  (src/pic1dp_interaction.F90:102-104) ----
@@ -334,6 +346,10 @@ __device__ __forceinline__ void div_pos_n(const double (&a)[N], const double (&b
     double e = fma(-b[k], y, 1.0);
     e = fma(e, e, e);
     y = fma(y, e, y);
+#if PIC1DP_NEWTON2
+    e = fma(-b[k], y, 1.0);
+    y = fma(y, e, y);
+#endif
     const double q0 = a[k] * y;
     const double r = fma(-q0, b[k], a[k]);
     q[k] = fma(r, y, q0);
@@ -472,6 +488,10 @@ __device__ __forceinline__ void div_fast_n(const double (&a)[N], const double (&
     double e = fma(-b[k], y, 1.0);
     e = fma(e, e, e);
     y = fma(y, e, y);
+#if PIC1DP_NEWTON2
+    e = fma(-b[k], y, 1.0);
+    y = fma(y, e, y);
+#endif
     const double q0 = a[k] * y;
     q[k] = fma(fma(-q0, b[k], a[k]), y, q0);
     rare = rare | (eb >= (1000u << 20)) | !(b[k] > 0.0);
@@ -609,8 +629,9 @@ struct Depositor<DEP_SMEM_ATOMIC> {
     if (!valid) return;
     double2 *slot = reinterpret_cast<double2 *>(g) + ix;
     const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
-    // a failed attempt re-reads the slot instead of recycling the value the CAS returned: the returned registers are
-    // then only compared, which saves ptxas four register moves per attempt on the (common) success path
+#if PIC1DP_CAS_RELOAD
+    // a failed attempt re-reads the slot instead of recycling the value the CAS returned (saves four register moves per
+    // attempt, but the slot load can no longer be hoisted above the weight arithmetic: measured 35 % SLOWER)
     for (;;) {
       const double2 old = *slot;
       const unsigned long long e0 = __double_as_longlong(old.x), e1 = __double_as_longlong(old.y);
@@ -618,6 +639,17 @@ struct Depositor<DEP_SMEM_ATOMIC> {
       cas128(addr, e0, e1, __double_as_longlong(dadd(old.x, a)), __double_as_longlong(dadd(old.y, b)), f0, f1);
       if (f0 == e0 && f1 == e1) break;
     }
+#else
+    double2 old = *slot;   // outside the loop: ptxas hoists this load above the weight arithmetic
+    for (;;) {
+      const unsigned long long e0 = __double_as_longlong(old.x), e1 = __double_as_longlong(old.y);
+      unsigned long long f0, f1;
+      cas128(addr, e0, e1, __double_as_longlong(dadd(old.x, a)), __double_as_longlong(dadd(old.y, b)), f0, f1);
+      if (f0 == e0 && f1 == e1) break;
+      old.x = __longlong_as_double(f0);
+      old.y = __longlong_as_double(f1);
+    }
+#endif
   }
   // Both markers of a thread: the two slot loads, then the two CAS, are issued back to back so that their shared-memory
   // round trips overlap (the serial form exposes LDS -> DADD -> CAS -> compare twice: 22 % of the stall samples of the
@@ -704,86 +736,38 @@ struct Depositor<DEP_WARP_PRIVATE> {
 // (value * 2^e, round to nearest) and added as integers inside the CAS loop: integer addition is associative, so the
 // slot sums do not depend on the order in which the warps arrive.  The reference's own deposit is sequential, hence
 // deterministic (src/pic1dp_interaction.F90:96-114); this is the order-independent counterpart.
-//   scale   : 2^e with e chosen per launch from the running maximum of |deposit source| (max|w| so far, kept on the
-//             device) so that a contribution is below 2^50 with >= 4x headroom for growth within the substep;
-//             quantum = 2^-e <= 2^-47 max|w|: the rounding of one contribution is ~7e-15 max|w|, far below the
-//             summation-order noise of fp64 accumulation and 1e-12 of max|rho|.
-//   spill   : an int64 slot could overflow only if one cell of one CTA received > 2^12 maximal contributions.  Instead
-//             of bounding that with periodic CTA-wide flushes (barriers inside the persistent loop cost 30 % of the
-//             kernel: the warps drift many iterations apart and the laggards then run alone), every CAS attempt
-//             checks |old| < 2^62; a thread that sees a slot beyond it swaps the slot to zero and adds the old value
-//             to a 128-bit integer accumulator of that slot in global memory (two native 64-bit atomic adds with
-//             carry).  Integer all the way, so the total is exact and independent of when spills happen.  The final
-//             flush adds the accumulators of a CTA that spilled.  (Never taken with physical marker distributions;
-//             tests lower the threshold to exercise it.)
-//   overflow: |source| >= 2^51 / 2^e (growth by > 64x inside one substep) cannot be converted; it is counted in
-//             dep_overflow and reported by the next synchronising call.
+//   scale   : 2^e, chosen per launch so that NO slot can overflow whatever the marker distribution: a contribution is
+//             below B = 2^(62 - ceil(log2(n_cta))) (n_cta = markers this CTA handles; capped at 2^50), hence a slot sum
+//             stays below 2^62 even if every marker of the CTA hit the same cell; and sources up to 2^(E+3) map below
+//             B, E = exponent of the running maximum of |source| (max |w| so far, kept on the device), i.e. >= 4x
+//             headroom for growth within the substep.  (Two's-complement partial sums may even wrap: only the final
+//             sum has to be representable.)  No overflow checks, spills or barriers in the persistent loop -- an earlier
+//             version flushed the integer grid every 32 tile steps and lost 30 % to the CTA-wide barriers (the warps
+//             drift many iterations apart and the laggards then run alone).
+//   quantum : 2^-e <= 8 max|w| / B: 2^-39 max|w| at 1e8 markers per GPU (6.8e5 per CTA), 2^-47 max|w| below 4096
+//             markers per CTA.  The rounding error of a cell sum of n contributions is ~sqrt(n / 12) quanta: for the
+//             bench state (2e5 contributions per cell) 2e-10 max|w| against cell sums of ~3e4 max|w|, i.e. 1e-14 of
+//             max|rho|; it stays below 1e-12 of max|rho| unless the density is pure noise at > 2e8 markers per GPU.
+//   overflow: |source| >= 2^(E+4) (growth by more than 8x .. 16x inside one substep) is outside the planned headroom; it
+//             is counted in dep_overflow and reported by the next synchronising call.
 // ------------------------------------------------------------------------------------------------------------
-struct FixedSpill {
-  unsigned long long *acc;   // this CTA's accumulators: [2 * nx][2] = {low word, high word} of a 128-bit integer
-  int *flag;                 // shared-memory flag: this CTA has spilled
-  unsigned th;               // spill when |slot| >= th * 2^32 (2^62 unless a test lowers it)
-};
-
-// adds the signed 64-bit v to the 128-bit accumulator at acc[0..1]; order-independent
-static __device__ __noinline__ void fixed_spill_add(unsigned long long *acc, long long v) {
-  const unsigned long long u = (unsigned long long)v;
-  const unsigned long long old = atomicAdd(acc, u);
-  const unsigned long long carry = (old + u < old) ? 1ULL : 0ULL;
-  const unsigned long long hi = (v < 0 ? ~0ULL : 0ULL) + carry;
-  if (hi) atomicAdd(acc + 1, hi);
-}
-
 template <>
 struct Depositor<DEP_FIXED> {
   double *g;      // pair grid, 2*nx int64 viewed as doubles by dep_setup
   double scale;   // 2^e
   double inv;     // 2^-e
-  unsigned bound_hi;  // high word of 2^51 / 2^e: sources at or above it overflow the conversion
+  unsigned bound_hi;  // high word of the largest admissible |source|: at or above it the headroom is exhausted
   unsigned seen_hi;   // high word of the largest |source| this thread has deposited
-  FixedSpill sp;
   __device__ __forceinline__ double prescale(double q) {
     seen_hi = max(seen_hi, (unsigned)__double2hiint(q) & 0x7fffffffu);
     return dmul(q, scale);  // exact (power of two)
   }
-  // |content| >= th * 2^32 in either component of a slot
-  __device__ __forceinline__ bool is_full(unsigned long long e0, unsigned long long e1) const {
-    return ((unsigned)(e0 >> 32) + sp.th >= 2 * sp.th) | ((unsigned)(e1 >> 32) + sp.th >= 2 * sp.th);
-  }
-  // slow path: the slot is full -- swap it to zero; the winner owns the old content and adds it to the slot's 128-bit
-  // accumulator.  Everything by value (reference parameters of a noinline function would force the caller's slot
-  // registers through local memory on the hot path); the caller re-reads the slot afterwards.
-  __device__ __noinline__ void spill_slot(unsigned addr, int ix, unsigned long long e0, unsigned long long e1) const {
-    unsigned long long f0, f1;
-    cas128(addr, e0, e1, 0ULL, 0ULL, f0, f1);
-    if (f0 == e0 && f1 == e1) {
-      fixed_spill_add(sp.acc + 4 * (size_t)ix, (long long)e0);
-      fixed_spill_add(sp.acc + 4 * (size_t)ix + 2, (long long)e1);
-      *sp.flag = 1;
-    }
-  }
-  // one CAS attempt at adding (ia, ib) to the slot whose content was last seen as (e0, e1).  Returns true when the add
-  // went in; otherwise (e0, e1) hold the content to retry with.
-  __device__ __forceinline__ bool attempt(unsigned addr, int ix, unsigned long long &e0, unsigned long long &e1, long long ia,
-                                          long long ib) {
-    if (__builtin_expect(is_full(e0, e1), 0)) {
-      spill_slot(addr, ix, e0, e1);
-      asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(e0), "=l"(e1) : "r"(addr) : "memory");
-      return false;
-    }
-    unsigned long long f0, f1;
-    cas128(addr, e0, e1, e0 + (unsigned long long)ia, e1 + (unsigned long long)ib, f0, f1);
-    const bool won = (f0 == e0) & (f1 == e1);
-    e0 = f0;
-    e1 = f1;
-    return won;
-  }
-  // double -> int64, round to nearest: the integer lands in the low mantissa bits of x + 1.5 * 2^52
+  // double -> int64, round to nearest
   static __device__ __forceinline__ long long to_fixed(double x) {
 #if PIC1DP_FIXED_F2I
     return __double2ll_rn(x);
 #else
-    const double magic = 6755399441055744.0;
+    const double magic = 6755399441055744.0;   // the integer lands in the low mantissa bits of x + 1.5 * 2^52
     return __double_as_longlong(dadd(x, magic)) - __double_as_longlong(magic);
 #endif
   }
@@ -791,53 +775,36 @@ struct Depositor<DEP_FIXED> {
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     (void)ixr;
     if (!valid) return;
-    const long long ia = to_fixed(a), ib = to_fixed(b);
+    const unsigned long long ia = (unsigned long long)to_fixed(a), ib = (unsigned long long)to_fixed(b);
     longlong2 *slot = reinterpret_cast<longlong2 *>(g) + ix;
     const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
-    for (;;) {   // a failed attempt re-reads the slot (see Depositor<DEP_SMEM_ATOMIC>::add)
-      const longlong2 old = *slot;
-      unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
-      if (__builtin_expect(is_full(e0, e1), 0)) {
-        spill_slot(addr, ix, e0, e1);
-        continue;
-      }
+    const longlong2 old = *slot;   // outside the loop: hoisted above the weight arithmetic
+    unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
+    for (;;) {
       unsigned long long f0, f1;
-      cas128(addr, e0, e1, e0 + (unsigned long long)ia, e1 + (unsigned long long)ib, f0, f1);
+      cas128(addr, e0, e1, e0 + ia, e1 + ib, f0, f1);
       if (f0 == e0 && f1 == e1) break;
+      e0 = f0;
+      e1 = f1;
     }
   }
-  // both markers of a thread with overlapped round trips (see Depositor<DEP_SMEM_ATOMIC>::add2)
-  __device__ __forceinline__ void add2(int ix0, int ixr0, double a0, double b0, int ix1, int ixr1, double a1, double b1,
-                                       bool valid) {
-    (void)ixr0;
-    (void)ixr1;
-    if (!valid) return;
-    const long long ia0 = to_fixed(a0), ib0 = to_fixed(b0), ia1 = to_fixed(a1), ib1 = to_fixed(b1);
-    longlong2 *s0 = reinterpret_cast<longlong2 *>(g) + ix0, *s1 = reinterpret_cast<longlong2 *>(g) + ix1;
-    const unsigned ad0 = (unsigned)__cvta_generic_to_shared(s0), ad1 = (unsigned)__cvta_generic_to_shared(s1);
-    const longlong2 o0 = *s0, o1 = *s1;
-    unsigned long long e00 = (unsigned long long)o0.x, e01 = (unsigned long long)o0.y;
-    unsigned long long e10 = (unsigned long long)o1.x, e11 = (unsigned long long)o1.y;
-    bool ok0 = attempt(ad0, ix0, e00, e01, ia0, ib0);
-    bool ok1 = attempt(ad1, ix1, e10, e11, ia1, ib1);
-    while (!ok0) ok0 = attempt(ad0, ix0, e00, e01, ia0, ib0);
-    while (!ok1) ok1 = attempt(ad1, ix1, e10, e11, ia1, ib1);
-  }
+  PIC1DP_DEP_ADD2_SERIAL
 };
 
-// scale of this launch from the running maximum (high word of max|source|): source bound 2^(E+3) with E the unbiased
-// exponent of the maximum (>= 4x headroom), contribution * 2^e < 2^50
-__device__ __forceinline__ void fixed_scale(Depositor<DEP_FIXED> &dep, const unsigned wmax_hi) {
+// scale of this launch: wmax_hi = high word of the running max |source|, ncap = markers this CTA handles
+__device__ __forceinline__ void fixed_scale(Depositor<DEP_FIXED> &dep, const unsigned wmax_hi, const long long ncap) {
   int ex = (int)((wmax_hi >> 20) & 0x7ff);   // biased exponent of the maximum
   if (ex < 100) ex = 100;                     // all-zero / denormal sources: any scale works, keep 2^e finite
-  const int se = 2093 - ex;                   // biased exponent of 2^e, e = 50 - (ex - 1023 + 3)
+  int lb = 62 - (64 - __clzll(ncap > 1 ? ncap - 1 : 1));   // log2 B = 62 - ceil(log2 ncap)
+  if (lb > 50) lb = 50;
+  const int se = 1023 + lb - (ex - 1023 + 3);   // biased exponent of 2^e: sources below 2^(E+3) map below B
   dep.seen_hi = 0;
   dep.scale = __hiloint2double(se << 20, 0);
   dep.inv = __hiloint2double((2046 - se) << 20, 0);
-  dep.bound_hi = (unsigned)((2097 - se) << 20);
+  dep.bound_hi = (unsigned)((ex + 4) << 20);        // sources at or above 2 * 2^(E+3): beyond the planned bound
 }
 
-// end of the kernel: publish the largest source seen (the next launch scales by it) and count conversion overflows
+// end of the kernel: publish the largest source seen (the next launch scales by it) and count headroom violations
 __device__ __forceinline__ void fixed_finish(const Depositor<DEP_FIXED> &dep, unsigned *wmax_hi, unsigned long long *overflow) {
   const unsigned m = __reduce_max_sync(0xffffffffu, dep.seen_hi);
   if ((threadIdx.x & 31) == 0) {
@@ -846,49 +813,14 @@ __device__ __forceinline__ void fixed_finish(const Depositor<DEP_FIXED> &dep, un
   }
 }
 
-// (high : low) 128-bit two's-complement integer -> double through its magnitude: for |value| < 2^64 this is the
-// correctly rounded value, i.e. exactly what (double)(int64) gives when the value fits in 64 bits
-__device__ __forceinline__ double int128_to_double(unsigned long long lo, long long hi) {
-  const bool neg = hi < 0;
-  if (neg) {
-    lo = ~lo + 1ULL;
-    hi = ~hi + (lo == 0ULL ? 1 : 0);
-  }
-  const double m = dadd(dmul((double)(unsigned long long)hi, 18446744073709551616.0), (double)lo);
-  return neg ? -m : m;
-}
-
 // flush of the integer pair grid into the CTA's global grid; called by every thread of the CTA after the marker loop.
-// rho[j] = left[j] + right[j-1], summed as integers and converted once; a CTA that spilled adds the 128-bit
-// accumulators first.  Both branches round the same exact integer, so the result does not depend on whether (or when)
-// a slot was spilled.
-__device__ __forceinline__ void fixed_flush(double *pairs, int nx, double *my_partial, const double inv, const FixedSpill &sp) {
+// rho[j] = left[j] + right[j-1], summed as integers (exact) and converted once.
+__device__ __forceinline__ void fixed_flush(double *pairs, int nx, double *my_partial, const double inv) {
   __syncthreads();
   const longlong2 *sl = reinterpret_cast<const longlong2 *>(pairs);
-  const bool spilled = *sp.flag != 0;   // CTA-uniform after the barrier
   for (int j = threadIdx.x; j < nx; j += blockDim.x) {
     const int jl = (j == 0) ? nx - 1 : j - 1;  // right weights of the cell to the left (periodic, :111-112)
-    const long long L = sl[j].x, R = sl[jl].y;
-    if (!spilled) {
-      my_partial[j] = dmul((double)(L + R), inv);   // exact sum (|L|, |R| < 2^62), one rounding
-    } else {
-      const unsigned long long *aL = sp.acc + 4 * (size_t)j, *aR = sp.acc + 4 * (size_t)jl + 2;
-      unsigned long long lo = aL[0];
-      long long hi = (long long)aL[1];
-      const unsigned long long add[3] = {(unsigned long long)L, aR[0], (unsigned long long)R};
-      const long long addh[3] = {L < 0 ? -1LL : 0LL, (long long)aR[1], R < 0 ? -1LL : 0LL};
-#pragma unroll
-      for (int q = 0; q < 3; q++) {   // 128-bit additions
-        const unsigned long long t = lo + add[q];
-        hi += addh[q] + (t < lo ? 1 : 0);
-        lo = t;
-      }
-      my_partial[j] = dmul(int128_to_double(lo, hi), inv);
-    }
-  }
-  if (spilled) {   // the accumulators are all zero between launches
-    __syncthreads();
-    for (int j = threadIdx.x; j < 4 * nx; j += blockDim.x) sp.acc[j] = 0ULL;
+    my_partial[j] = dmul((double)(sl[j].x + sl[jl].y), inv);
   }
 }
 
@@ -977,7 +909,7 @@ __device__ __forceinline__ bool push_pair_fast(const ParticleArgs &a, const doub
   if (FUSED) {
     // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
     const double q0 = dep.prescale(deltaf ? awo[0] : p.x), q1 = dep.prescale(deltaf ? awo[1] : p.y);
-    constexpr bool OVERLAP = (DEP == DEP_SMEM_ATOMIC && (PIC1DP_ADD2 & 1)) || (DEP == DEP_FIXED && (PIC1DP_ADD2 & 2));
+    constexpr bool OVERLAP = DEP == DEP_SMEM_ATOMIC && (PIC1DP_ADD2 & 1);
     if constexpr (OVERLAP) {
       dep.add2(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0),       // :110, :113
                sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
@@ -992,11 +924,11 @@ __device__ __forceinline__ bool push_pair_fast(const ParticleArgs &a, const doub
 
 template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
 __device__ __forceinline__ void push_pair_slow(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep, const int64_t i,
-                                            unsigned long long &noob, const bool ok) {
+                                            unsigned long long &noob, const bool ok, const int64_t end) {
   typedef Cfg<CFG> F;
   const bool deltaf = F::deltaf(a.deltaf), linear = F::linear(a.linear), right_frac = F::right_frac(a.right_frac);
   const bool need_p = deltaf || FUSED;  // full-f deposits p (src/pic1dp_interaction.F90:88-90)
-  const bool v0ok = ok && i < a.np, v1ok = ok && i + 1 < a.np;
+  const bool v0ok = ok && i < end, v1ok = ok && i + 1 < end;   // end: one past this CTA's last marker (<= np)
   double2 x = {0.0, 0.0}, v = {0.0, 0.0}, w = {0.0, 0.0}, p = {0.0, 0.0};
   double2 xb = {0.0, 0.0}, vb = {0.0, 0.0}, wb = {0.0, 0.0};
   if (v1ok) {
@@ -1076,9 +1008,9 @@ __device__ __forceinline__ void load_pair(const ParticleArgs &a, const int64_t i
 // run the scalar code; the warp-private depositor needs all 32 lanes present
 template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
 __device__ __forceinline__ void push_pair_redo(const ParticleArgs &a, const double *sE, Depositor<DEP> &dep,
-                                               const int64_t i, unsigned long long &noob, const bool redo) {
+                                               const int64_t i, unsigned long long &noob, const bool redo, const int64_t end) {
   const bool enter = (FUSED && DEP == DEP_WARP_PRIVATE) ? __any_sync(0xffffffffu, redo) : redo;
-  if (__builtin_expect(enter, 0)) push_pair_slow<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, redo);
+  if (__builtin_expect(enter, 0)) push_pair_slow<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, redo, end);
 }
 
 template <int DIST, bool IRK2, int DEP, bool FUSED, int CFG>
@@ -1089,14 +1021,6 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   double *my_partial = FUSED ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
   Depositor<DEP> dep;
   dep.g = FUSED ? dep_setup<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial) : nullptr;
-  __shared__ int s_spill;
-  if constexpr (DEP == DEP_FIXED) {
-    fixed_scale(dep, FUSED ? *a.dep_wmax_hi : 0u);
-    dep.sp.acc = a.dep_spill + (size_t)blockIdx.x * 4 * a.nx;
-    dep.sp.flag = &s_spill;
-    dep.sp.th = a.dep_spill_th;
-    if (threadIdx.x == 0) s_spill = 0;
-  }
   __syncthreads();
 
   const int64_t tile = (int64_t)blockDim.x * 2;
@@ -1106,45 +1030,81 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   // the one load whose latency nothing hides; it is issued one iteration ahead (4 registers)
   constexpr bool PV = (PIC1DP_PV_MASK & ((DEP == DEP_WARP_PRIVATE ? 4 : 1) << (IRK2 ? 1 : 0))) != 0;
   double2 v_next = make_double2(0.0, 0.0);
+#if PIC1DP_CHUNKED
+  // this CTA's contiguous range [start, end): the markers are cut into granules of 64 (one warp's share of a tile step)
+  // and the granules are dealt out evenly, so every CTA runs the same number of tile steps (+-1 warp in the last one)
+  const int64_t ngran = (a.np + 63) >> 6;
+  const int64_t start = ((ngran * blockIdx.x) / gridDim.x) << 6;
+  const int64_t end_g = ((ngran * (blockIdx.x + 1)) / gridDim.x) << 6;
+  const int64_t end = end_g < a.np ? end_g : a.np;
+  const int64_t stride = tile;
+#else
+  const int64_t start = (int64_t)blockIdx.x * tile, end = a.np, stride = (int64_t)gridDim.x * tile;
+#endif
+  if constexpr (DEP == DEP_FIXED) fixed_scale(dep, FUSED ? *a.dep_wmax_hi : 0u, (end - start) / stride * tile + tile);
   if (PV) {
-    const int64_t b0 = (int64_t)blockIdx.x * tile;
-    if (b0 + tile <= a.np) v_next = ld2(a.v_cur + b0 + (int64_t)threadIdx.x * 2);
+    if (start + tile <= end) v_next = ld2(a.v_cur + start + (int64_t)threadIdx.x * 2);
   }
-  for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
+  for (int64_t base = start; base < end; base += stride) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
+    const double *px = a.x_cur + i, *pv = a.v_cur + i, *pw = a.w_cur + i, *pp = a.p + i;   // shared by prefetch and loads
     // L2 prefetch of this thread's markers of the next tile step: the loads then hit L2 instead of HBM.
     // Measured on B200 at 1e8 markers (profiles/r01_ab_experiments.md), enabled per variant: it helps the warp-private
     // deposit in both substeps and the atomic deposit at irk=1 (1.060 -> 1.040 ms: with the rare-path-free body the
     // first use of the streamed v is the top stall) and hurts the HBM-bound atomic irk=2 kernel (1.24 -> 1.54 ms).
+    // With contiguous CTA ranges the next tile step sits a constant 2 * blockDim * 8 bytes ahead of this one.
     if (PIC1DP_PF_MASK & ((DEP == DEP_WARP_PRIVATE ? 4 : 1) << (IRK2 ? 1 : 0))) {
-      const int64_t inext = i + (int64_t)gridDim.x * tile;
-      if (inext + 1 < a.np) {
-        prefetch_l2(a.x_cur + inext);
-        prefetch_l2(a.v_cur + inext);
-        if (deltaf_pf) prefetch_l2(a.w_cur + inext);
-        if (deltaf_pf || FUSED) prefetch_l2(a.p + inext);
+#if PIC1DP_CHUNKED
+      // a compile-time distance (2048 markers = one tile step of a 1024-thread CTA): the prefetch addresses are the
+      // load addresses plus an immediate offset
+      constexpr int64_t ahead = 2048;
+#else
+      const int64_t ahead = stride;
+#endif
+      if (i + ahead + 1 < end) {
+        prefetch_l2(px + ahead);
+        prefetch_l2(pv + ahead);
+        if (deltaf_pf) prefetch_l2(pw + ahead);
+        if (deltaf_pf || FUSED) prefetch_l2(pp + ahead);
         if (IRK2) {
-          prefetch_l2(a.x_bak + inext);
-          prefetch_l2(a.v_bak + inext);
-          if (deltaf_pf) prefetch_l2(a.w_bak + inext);
+          prefetch_l2(a.x_bak + i + ahead);
+          prefetch_l2(a.v_bak + i + ahead);
+          if (deltaf_pf) prefetch_l2(a.w_bak + i + ahead);
         }
       }
     }
+#if PIC1DP_CHUNKED
+    // range ends fall on warp boundaries (64 markers) except the ragged end of the arrays: a warp is either wholly inside
+    // (2-wide fast path), wholly outside, or the one warp that holds the last markers (scalar path, validity per marker)
+    const bool full = i + 2 <= end;
+    bool redo = !full && i < end;
+#else
+    const bool full = base + tile <= end;
     bool redo = true;  // partial tile: every thread takes the scalar path (validity per marker)
-    if (base + tile <= a.np) {
+#endif
+    if (full) {
       double2 x, v, w, p, xb, vb, wb;
-      load_pair<IRK2, FUSED, CFG>(a, i, x, v, w, p, xb, vb, wb);
+      x = ld2(px);
+      v = ld2(pv);
+      w = p = xb = vb = wb = make_double2(0.0, 0.0);
+      if (deltaf_pf) w = ld2(pw);
+      if (deltaf_pf || FUSED) p = ld2(pp);
+      if (IRK2) {
+        xb = ld2(a.x_bak + i);
+        vb = ld2(a.v_bak + i);
+        if (deltaf_pf) wb = ld2(a.w_bak + i);
+      }
       if (PV) {
         v = v_next;
-        const int64_t nb = base + (int64_t)gridDim.x * tile;
-        if (nb + tile <= a.np) v_next = ld2(a.v_cur + nb + (int64_t)threadIdx.x * 2);
+        const int64_t nb = base + stride;
+        if (nb + tile <= end) v_next = ld2(a.v_cur + nb + (int64_t)threadIdx.x * 2);
       }
       redo = push_pair_fast<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
     }
-    push_pair_redo<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, redo);
+    push_pair_redo<DIST, IRK2, DEP, FUSED, CFG>(a, sE, dep, i, noob, redo, end);
   }
   if constexpr (DEP == DEP_FIXED && FUSED) {
-    fixed_flush(smem + ((a.nx + 1) & ~1), a.nx, my_partial, dep.inv, dep.sp);
+    fixed_flush(smem + ((a.nx + 1) & ~1), a.nx, my_partial, dep.inv);
     fixed_finish(dep, a.dep_wmax_hi, a.dep_overflow);
   } else if (FUSED) {
     dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
@@ -1221,7 +1181,7 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push_cpa(const Particl
       }
       redo = push_pair_fast<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, x, v, w, p, xb, vb, wb);
     }
-    push_pair_redo<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, redo);
+    push_pair_redo<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, redo, a.np);
     cur_staged = next_staged;
   }
   dep_flush<DEP>(dep_base, a.nx, my_partial);
@@ -1337,7 +1297,7 @@ __global__ void __launch_bounds__(1024, 1) k_push_tma(const ParticleArgs a) {
     bool redo = true;  // partial tile: scalar path with per-marker validity (reads global memory itself)
     if (m0 + TILE <= a.np)
       redo = push_pair_fast<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, in.x, in.v, in.w, in.p, in.xb, in.vb, in.wb);
-    push_pair_redo<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, redo);
+    push_pair_redo<DIST, IRK2, DEP, true, CFG>(a, sE, dep, i, noob, redo, a.np);
   }
   dep_flush<DEP>(dep_base, a.nx, my_partial);
   if (noob) atomicAdd(a.noob, noob);
@@ -1354,16 +1314,10 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
   double *my_partial = DEPOSIT ? a.partial + (size_t)blockIdx.x * a.nx : nullptr;
   Depositor<DEP> dep;
   dep.g = DEPOSIT ? dep_setup<DEP>(smem, a.nx, my_partial) : nullptr;
-  __shared__ int s_spill;
-  if constexpr (DEP == DEP_FIXED) {
-    fixed_scale(dep, DEPOSIT ? *a.dep_wmax_hi : 0u);  // set by k_absmax_hi before this launch
-    dep.sp.acc = a.dep_spill + (size_t)blockIdx.x * 4 * a.nx;
-    dep.sp.flag = &s_spill;
-    dep.sp.th = a.dep_spill_th;
-    if (threadIdx.x == 0) s_spill = 0;
-  }
-  __syncthreads();
   const int64_t tile = (int64_t)blockDim.x * 2;
+  if constexpr (DEP == DEP_FIXED)   // wmax set by k_absmax_hi before this launch; this CTA handles <= ceil(tiles / grid) tiles
+    fixed_scale(dep, DEPOSIT ? *a.dep_wmax_hi : 0u, ((a.np + tile - 1) / tile + gridDim.x - 1) / gridDim.x * tile);
+  __syncthreads();
   unsigned long long noob = 0;
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
     const int64_t i = base + (int64_t)threadIdx.x * 2;
@@ -1394,7 +1348,7 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
     }
   }
   if constexpr (DEP == DEP_FIXED && DEPOSIT) {
-    fixed_flush(smem, a.nx, my_partial, dep.inv, dep.sp);
+    fixed_flush(smem, a.nx, my_partial, dep.inv);
     fixed_finish(dep, a.dep_wmax_hi, a.dep_overflow);
   } else if (DEPOSIT) {
     dep_flush<DEP>(smem, a.nx, my_partial);

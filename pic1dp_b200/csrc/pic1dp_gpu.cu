@@ -121,8 +121,7 @@ struct pic1dp_gpu {
   unsigned long long *d_noob = nullptr;
   unsigned *d_wmax_hi = nullptr;              // [species] running max |deposit source| (high words), DEP_FIXED
   unsigned long long *d_dep_overflow = nullptr, *h_dep_overflow = nullptr;  // conversion overflows (+ pinned mirror)
-  unsigned long long *d_dep_spill = nullptr;  // 128-bit spill accumulators of the fixed-point slots, [species][grid][2 nx][2]
-  unsigned dep_spill_th = 0x40000000u;
+
   std::vector<double> h_Fre, h_Fim, h_ginv;
   // diagnostics scratch (allocated on first use)
   double *d_diag_part = nullptr, *d_diag_sums = nullptr, *d_hist = nullptr, *d_hist_out = nullptr;
@@ -364,7 +363,7 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
   if (h->d_kiss_tab) cudaFree(h->d_kiss_tab);
   if (h->d_wmax_hi) cudaFree(h->d_wmax_hi);
   if (h->d_dep_overflow) cudaFree(h->d_dep_overflow);
-  if (h->d_dep_spill) cudaFree(h->d_dep_spill);
+
   if (h->h_dep_overflow) cudaFreeHost(h->h_dep_overflow);
   for (int r = 0; r < 8; r++)
     if (h->peer_base[r] && h->peer_base[r] != h->d_xchg) cudaIpcCloseMemHandle(h->peer_base[r]);
@@ -568,22 +567,6 @@ static int create_impl(pic1dp_gpu_t *h) {
   CK(cudaMemsetAsync(h->d_dep_overflow, 0, 8, h->stream));
   CK(cudaMallocHost(&h->h_dep_overflow, 8));
   *h->h_dep_overflow = 0;
-  if (dep == DEP_FIXED) {
-    const size_t sb = (size_t)p.nspecies * h->grid * 4 * nx * 8;
-    CK(cudaMalloc(&h->d_dep_spill, sb));
-    CK(cudaMemsetAsync(h->d_dep_spill, 0, sb, h->stream));
-    if (const char *e = getenv("PIC1DP_EXP_SPILL_BITS")) {  // test hook: spill at 2^bits instead of 2^62
-      const int bits = atoi(e);
-      if (bits >= 33 && bits <= 62) h->dep_spill_th = 1u << (bits - 32);
-    }
-  }
-  CK(cudaMemsetAsync(h->d_E, 0, (size_t)nx * 8, h->stream));
-  CK(cudaMemsetAsync(h->d_rho, 0, (size_t)nx * 8, h->stream));
-  CK(cudaMemsetAsync(h->d_mre, 0, (size_t)M * 8, h->stream));
-  CK(cudaMemsetAsync(h->d_mim, 0, (size_t)M * 8, h->stream));
-  CK(cudaMemsetAsync(h->d_partial, 0, (size_t)p.nspecies * h->grid * nx * 8, h->stream));
-  CK(cudaMemsetAsync(h->d_red, 0, (size_t)h->nred * nx * 8, h->stream));
-  CK(cudaMemsetAsync(h->d_noob, 0, 8, h->stream));
 
   // ---- field operators (src/pic1dp_field.F90:158-210), evaluated on the host with libm exactly as written ----
   const double PETSC_PI = 3.14159265358979323846264338327950288419716939937510582;
@@ -706,9 +689,9 @@ static void p2p_queue_timeout_read(pic1dp_gpu_t *h) {
 }
 static int p2p_check_timeouts(pic1dp_gpu_t *h, const char *who) {
   if (h->dep == DEP_FIXED && *h->h_dep_overflow != 0) {
-    h->err = std::string(who) + ": fixed-point deposit overflow -- the deposit source grew by more than 64x within one "
-             "substep (" + std::to_string(*h->h_dep_overflow) + " warps); rho is invalid.  Use another deposit_mode for "
-             "this input";
+    h->err = std::string(who) + ": fixed-point deposit overflow -- the deposit source grew by more than 8x within one "
+             "substep (" + std::to_string(*h->h_dep_overflow) + " warps): the headroom of the integer slots is exhausted "
+             "and rho may be invalid.  Use another deposit_mode for this input";
     return PIC1DP_ESTATE;
   }
   if (h->p2p_ready && h->h_p2p_timeouts && *h->h_p2p_timeouts != 0) {
@@ -1006,8 +989,6 @@ static void fill_particle_args(pic1dp_gpu_t *h, int s, ParticleArgs &a) {
   a.noob = h->d_noob;
   a.dep_wmax_hi = h->d_wmax_hi + s;
   a.dep_overflow = h->d_dep_overflow;
-  a.dep_spill = h->d_dep_spill ? h->d_dep_spill + (size_t)s * h->grid * 4 * p.nx : nullptr;
-  a.dep_spill_th = h->dep_spill_th;
   a.np = S.np;
   a.nx = p.nx;
   a.lx = p.lx;
