@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libpic1dp_b200.so")
 UNITS = [("pic1dp_gpu", "pic1dp_gpu.cu", [])] + \
         [("push_dist%d" % d, "push_dist.cu", ["-DPIC1DP_DIST=%d" % d]) for d in range(4)]
 HEADERS = ["particle_kernels.cuh", "field_kernels.cuh", "diag_kernels.cuh", "optimize_kernels.cuh", "optimize_host.hpp",
-           "push_tables.hpp", "loader_kernels.cuh", "rng_kernels.cuh", "kiss_jump_tables.h"]
+           "push_tables.hpp", "fp_strict.cuh", "grid_device.cuh", "loader_kernels.cuh", "rng_kernels.cuh", "kiss_jump_tables.h"]
 OBJDIR = os.path.join(HERE, "build")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

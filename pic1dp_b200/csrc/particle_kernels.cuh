@@ -13,6 +13,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "grid_device.cuh"
+#include "fp_strict.cuh"
+
 // Resident threads per SM the particle kernels are compiled for: 1024 -> 64 registers/thread, 768 -> 85, 512 -> 128.
 #ifndef PIC1DP_MAXTHREADS
 #define PIC1DP_MAXTHREADS 1024
@@ -41,22 +44,12 @@
 #ifndef PIC1DP_CAS_RELOAD
 #define PIC1DP_CAS_RELOAD 0
 #endif
-// work assignment of the fused kernel: 1 = every CTA owns one contiguous range of markers (balanced to one warp's 64
-// markers; the next tile step is a constant 16 KB ahead, so the L2 prefetch needs no address arithmetic),
-// 0 = tiles dealt round-robin over the CTAs (round 1)
-#ifndef PIC1DP_CHUNKED
-#define PIC1DP_CHUNKED 1
-#endif
 #ifndef PIC1DP_NEWTON2
 #define PIC1DP_NEWTON2 0
 #endif
 
 namespace pic1dp {
 
-__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
 // ---- exp() with its polynomial in the constant bank ------------------------------------------------------
 // exp(a) = 2^n * (1 + r + r^2 q(r)), n = rint(a log2 e), r = a - n ln2 (two-term Cody-Waite with FMA),
@@ -202,6 +195,11 @@ struct ParticleArgs {
   // that a captured step graph can be replayed; raised with atomicMax by the kernels), and the overflow counter
   unsigned *dep_wmax_hi;
   unsigned long long *dep_overflow;
+  // single-GPU step(): the CTA that finishes last also reduces the private grids and solves the field (grid_tail in
+  // field_kernels.cuh), so a substep is ONE launch.  tail == nullptr: off (individual calls, multi-GPU exchange)
+  const GridArgs *tail;
+  unsigned *tail_counter;
+  int tail_seq;   // PIC1DP_FIELD_SEQUENTIAL
 };
 
 // ---- periodic wrap: px = mod(px, lx); if (px < 0) px = px + lx  (src/pic1dp_interaction.F90:102-104) ----
@@ -1030,17 +1028,10 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   // the one load whose latency nothing hides; it is issued one iteration ahead (4 registers)
   constexpr bool PV = (PIC1DP_PV_MASK & ((DEP == DEP_WARP_PRIVATE ? 4 : 1) << (IRK2 ? 1 : 0))) != 0;
   double2 v_next = make_double2(0.0, 0.0);
-#if PIC1DP_CHUNKED
-  // this CTA's contiguous range [start, end): the markers are cut into granules of 64 (one warp's share of a tile step)
-  // and the granules are dealt out evenly, so every CTA runs the same number of tile steps (+-1 warp in the last one)
-  const int64_t ngran = (a.np + 63) >> 6;
-  const int64_t start = ((ngran * blockIdx.x) / gridDim.x) << 6;
-  const int64_t end_g = ((ngran * (blockIdx.x + 1)) / gridDim.x) << 6;
-  const int64_t end = end_g < a.np ? end_g : a.np;
-  const int64_t stride = tile;
-#else
+  // tiles of 2 * blockDim markers are dealt round-robin over the persistent CTAs.  (Contiguous per-CTA ranges with a
+  // constant-offset prefetch were measured slower on B200 -- 2.31 vs 2.25 ms per step in TOLERANCE mode, 2.84 vs 2.41 ms
+  // with the warp-private deposit: 148 separate streams per array instead of one front moving through HBM.)
   const int64_t start = (int64_t)blockIdx.x * tile, end = a.np, stride = (int64_t)gridDim.x * tile;
-#endif
   if constexpr (DEP == DEP_FIXED) fixed_scale(dep, FUSED ? *a.dep_wmax_hi : 0u, (end - start) / stride * tile + tile);
   if (PV) {
     if (start + tile <= end) v_next = ld2(a.v_cur + start + (int64_t)threadIdx.x * 2);
@@ -1052,15 +1043,8 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
     // Measured on B200 at 1e8 markers (profiles/r01_ab_experiments.md), enabled per variant: it helps the warp-private
     // deposit in both substeps and the atomic deposit at irk=1 (1.060 -> 1.040 ms: with the rare-path-free body the
     // first use of the streamed v is the top stall) and hurts the HBM-bound atomic irk=2 kernel (1.24 -> 1.54 ms).
-    // With contiguous CTA ranges the next tile step sits a constant 2 * blockDim * 8 bytes ahead of this one.
     if (PIC1DP_PF_MASK & ((DEP == DEP_WARP_PRIVATE ? 4 : 1) << (IRK2 ? 1 : 0))) {
-#if PIC1DP_CHUNKED
-      // a compile-time distance (2048 markers = one tile step of a 1024-thread CTA): the prefetch addresses are the
-      // load addresses plus an immediate offset
-      constexpr int64_t ahead = 2048;
-#else
       const int64_t ahead = stride;
-#endif
       if (i + ahead + 1 < end) {
         prefetch_l2(px + ahead);
         prefetch_l2(pv + ahead);
@@ -1073,15 +1057,8 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
         }
       }
     }
-#if PIC1DP_CHUNKED
-    // range ends fall on warp boundaries (64 markers) except the ragged end of the arrays: a warp is either wholly inside
-    // (2-wide fast path), wholly outside, or the one warp that holds the last markers (scalar path, validity per marker)
-    const bool full = i + 2 <= end;
-    bool redo = !full && i < end;
-#else
     const bool full = base + tile <= end;
     bool redo = true;  // partial tile: every thread takes the scalar path (validity per marker)
-#endif
     if (full) {
       double2 x, v, w, p, xb, vb, wb;
       x = ld2(px);
@@ -1110,6 +1087,23 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
     dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
   }
   if (FUSED && noob) atomicAdd(a.noob, noob);
+#ifndef PIC1DP_NO_TAIL_CODE
+  if (FUSED && a.tail) {   // uniform over the grid
+    __shared__ int s_last;
+    __threadfence();       // this CTA's private grid is visible before it is counted
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned prev = atomicAdd(a.tail_counter, 1u);
+      s_last = prev == gridDim.x - 1;
+      if (s_last) *a.tail_counter = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      grid_tail(*a.tail, smem, a.tail_seq != 0);
+    }
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
