@@ -101,6 +101,30 @@ interface
     real(c_double), intent(in) :: gauss_v(*), rand_x(*), init_mode_cos(*), init_mode_sin(*)
     integer(c_int32_t), intent(in) :: init_mode(*)
   end function
+  integer(c_int) function pic1dp_gpu_load_markers_kiss64(handle, isp, np, nparticle_init, seeds, offset_v, offset_x, &
+      v_max, init_nmode, init_mode, init_mode_cos, init_mode_sin) bind(c, name = 'pic1dp_gpu_load_markers_kiss64')
+    import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: isp, init_nmode
+    integer(c_int64_t), value :: np, nparticle_init, offset_v, offset_x
+    integer(c_int64_t), intent(in) :: seeds(4)   ! multirand_seeds(0:3), same bits as the C uint64_t
+    real(c_double), value :: v_max
+    real(c_double), intent(in) :: init_mode_cos(*), init_mode_sin(*)
+    integer(c_int32_t), intent(in) :: init_mode(*)
+  end function
+  integer(c_int) function pic1dp_host_kiss64_jump(seeds, n) bind(c, name = 'pic1dp_host_kiss64_jump')
+    import :: c_int, c_int64_t
+    integer(c_int64_t), intent(inout) :: seeds(4)
+    integer(c_int64_t), value :: n
+  end function
+  integer(c_int) function pic1dp_gpu_output_all(handle, nx_opd, nv_opd, v_max, scalars, dist) &
+      bind(c, name = 'pic1dp_gpu_output_all')
+    import :: c_ptr, c_int, c_int32_t, c_double
+    type(c_ptr), value :: handle
+    integer(c_int32_t), value :: nx_opd, nv_opd
+    real(c_double), value :: v_max
+    real(c_double), intent(out) :: scalars(*), dist(*)
+  end function
   integer(c_int) function pic1dp_gpu_get_markers(handle, isp, x, v, p, w, np) bind(c, name = 'pic1dp_gpu_get_markers')
     import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
     type(c_ptr), value :: handle
@@ -211,6 +235,7 @@ public :: pic1dp_gpu_get_field, pic1dp_gpu_set_field, pic1dp_gpu_sync
 public :: pic1dp_gpu_p2p_export, pic1dp_gpu_p2p_import, pic1dp_gpu_output_field, pic1dp_gpu_output_ptcldist
 public :: pic1dp_gpu_compute_dist_pertb_abs_v, pic1dp_gpu_particle_merge, pic1dp_gpu_particle_remove
 public :: pic1dp_gpu_particle_split
+public :: pic1dp_gpu_load_markers_kiss64, pic1dp_host_kiss64_jump, pic1dp_gpu_output_all
 
 end module pic1dp_gpu
 
@@ -331,6 +356,28 @@ global_ierr = pic1dp_gpu_load_markers(gpu_handle, int(ispecies - 1, c_int32_t), 
   real(input_init_mode_sin, c_double))
 CHKERRQ(global_ierr)
 end subroutine gpu_particle_load
+
+! particle_load with input_multirand_al_int = 1 (KISS64): no marker-sized host-to-device copy.  Call in place of the two
+! multirand_real_array calls (src/pic1dp_particle.F90:180, :222) AFTER multirand_init (:159-160): the device generates
+! exactly the numbers those calls would have produced, and the host generator is advanced past them so that later draws
+! (particle_remove, particle_split) continue the same stream.  nlocal = particle_ip_high - particle_ip_low.
+subroutine gpu_particle_load_kiss64(ispecies, np, nlocal)
+use multirand, only : multirand_seeds
+implicit none
+#include "finclude/petsc.h90"
+PetscInt, intent(in) :: ispecies, np, nlocal
+integer(c_int64_t) :: seeds(4), off_v
+seeds(1 : 4) = multirand_seeds(0 : 3)
+off_v = 0_c_int64_t                          ! multirand_seeds already stands at this species' first draw
+global_ierr = pic1dp_gpu_load_markers_kiss64(gpu_handle, int(ispecies - 1, c_int32_t), int(np, c_int64_t), &
+  int(input_species_nparticle_init(ispecies), c_int64_t), seeds, off_v, off_v + int(nlocal, c_int64_t), &
+  real(input_v_max, c_double), int(input_init_nmode, c_int32_t), int(input_init_mode, c_int32_t), &
+  real(input_init_mode_cos, c_double), real(input_init_mode_sin, c_double))
+CHKERRQ(global_ierr)
+global_ierr = pic1dp_host_kiss64_jump(seeds, 2_c_int64_t * int(nlocal, c_int64_t))
+CHKERRQ(global_ierr)
+multirand_seeds(0 : 3) = seeds(1 : 4)
+end subroutine gpu_particle_load_kiss64
 
 ! before output_all / particle_optimize (src/pic1dp_output.F90:128-150, :228-237): device -> host Vecs
 subroutine gpu_particle_refresh_host(ispecies, vx, vv, vp, vw)
