@@ -1,6 +1,6 @@
 // grid_device.cuh -- device-side building blocks of the grid (density / field) work: the argument block, the peer-memory
-// all-reduce helpers, rho finalisation, the partial-DFT field solve and the single-CTA "tail" (reduce + solve) that the
-// fused particle kernel runs in its last CTA.  The __global__ kernels built from them are in field_kernels.cuh.
+// all-reduce helpers, rho finalisation and the partial-DFT field solve.  The __global__ kernels built from them are in
+// field_kernels.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -219,55 +219,9 @@ __device__ __forceinline__ void field_solve_body(const GridArgs &g, double *smem
   }
 }
 
-// ---- reduce + finalize + solve by ONE CTA: the tail of the fused particle kernel in single-GPU step() ----
-// Same summation trees as k_reduce_charge (8 interleaved partial sums per cell, added in order) and k_field_solve, so
-// step() gives bit for bit what the individual collect_charge / solve_field calls give.  Runs in the CTA that finished
-// its markers last; the grids of the other CTAs are read through L2 (__ldcg).
-__device__ __forceinline__ void tail_reduce(const GridArgs &g) {
-  __shared__ double s_part[4][8][33];
-  const int grp = threadIdx.x >> 8, ngrp = blockDim.x >> 8;   // groups of 256 threads = one k_reduce_charge CTA each
-  const int t = threadIdx.x & 255, lane = t & 31, wq = t >> 5;
-  const int nvb = (g.nx + 31) >> 5;
-  for (int vb0 = 0; vb0 < nvb; vb0 += ngrp) {
-    const int j = (vb0 + grp) * 32 + lane;
-    const bool act = grp < ngrp && j < g.nx;
-    double c2 = 0.0;
-    for (int s = 0; s < g.nspecies; s++) {
-      double c1 = 0.0;
-      if (act) {
-        double *ps = g.partial + (size_t)s * g.ngrids * g.nx + j;
-        int k = wq;
-        for (; k + 24 < g.ngrids; k += 32) {
-          const double t0 = __ldcg(ps + (size_t)k * g.nx), t1 = __ldcg(ps + (size_t)(k + 8) * g.nx);
-          const double t2 = __ldcg(ps + (size_t)(k + 16) * g.nx), t3 = __ldcg(ps + (size_t)(k + 24) * g.nx);
-          c1 = dadd(dadd(dadd(dadd(c1, t0), t1), t2), t3);
-        }
-        for (; k < g.ngrids; k += 8) c1 = dadd(c1, __ldcg(ps + (size_t)k * g.nx));
-        if (g.zero_partials)
-          for (k = wq; k < g.ngrids; k += 8) ps[(size_t)k * g.nx] = 0.0;
-      }
-      if (grp < 4) s_part[grp][wq][lane] = c1;
-      __syncthreads();
-      if (act && wq == 0) {
-        double tt = s_part[grp][0][lane];
-#pragma unroll
-        for (int q = 1; q < 8; q++) tt = dadd(tt, s_part[grp][q][lane]);
-        if (g.matrix_path) g.red[(size_t)s * g.nx + j] = tt;   // field_tmp = S^T w per species (:52-59)
-        else c2 = dadd(c2, dmul(tt, g.Z[s]));                   // charge2 += charge1 * Z (:126-127)
-      }
-      __syncthreads();
-    }
-    if (act && wq == 0 && !g.matrix_path) g.red[j] = c2;
-  }
-  __syncthreads();   // g.red written by this CTA is read by all its threads below
-}
-
-// noinline: the tail runs once per launch; inlined, its registers raise the pressure in the marker loop (spills)
-static __device__ __noinline__ void grid_tail(const GridArgs &g, double *smem, const bool seq) {
-  tail_reduce(g);
-  if (seq) field_solve_body<true, true>(g, smem);
-  else field_solve_body<false, true>(g, smem);
-}
-
+// (A single-CTA "tail" -- reduce + solve run by the last CTA of the fused particle kernel, one launch per substep -- was
+// built and measured in round 2: slower at every size (6.4e6 markers, nx = 192: 0.200 vs 0.177 ms per step; nx = 4096:
+// 0.45 vs 0.25 ms): one CTA reading 148 private grids is slower than the 6 .. 128 CTAs of k_reduce_charge plus two
+// launch boundaries inside a replayed graph, and its registers spilled in the marker loop.)
 
 }  // namespace pic1dp

@@ -13,7 +13,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "grid_device.cuh"
 #include "fp_strict.cuh"
 
 // Resident threads per SM the particle kernels are compiled for: 1024 -> 64 registers/thread, 768 -> 85, 512 -> 128.
@@ -195,11 +194,6 @@ struct ParticleArgs {
   // that a captured step graph can be replayed; raised with atomicMax by the kernels), and the overflow counter
   unsigned *dep_wmax_hi;
   unsigned long long *dep_overflow;
-  // single-GPU step(): the CTA that finishes last also reduces the private grids and solves the field (grid_tail in
-  // field_kernels.cuh), so a substep is ONE launch.  tail == nullptr: off (individual calls, multi-GPU exchange)
-  const GridArgs *tail;
-  unsigned *tail_counter;
-  int tail_seq;   // PIC1DP_FIELD_SEQUENTIAL
 };
 
 // ---- periodic wrap: px = mod(px, lx); if (px < 0) px = px + lx  (src/pic1dp_interaction.F90:102-104) ----
@@ -1087,23 +1081,6 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
     dep_flush<DEP>(smem + ((a.nx + 1) & ~1), a.nx, my_partial);
   }
   if (FUSED && noob) atomicAdd(a.noob, noob);
-#ifndef PIC1DP_NO_TAIL_CODE
-  if (FUSED && a.tail) {   // uniform over the grid
-    __shared__ int s_last;
-    __threadfence();       // this CTA's private grid is visible before it is counted
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned prev = atomicAdd(a.tail_counter, 1u);
-      s_last = prev == gridDim.x - 1;
-      if (s_last) *a.tail_counter = 0;
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      grid_tail(*a.tail, smem, a.tail_seq != 0);
-    }
-  }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -117,9 +117,6 @@ struct pic1dp_gpu {
   double *d_E = nullptr, *d_rho = nullptr, *d_mre = nullptr, *d_mim = nullptr;
   double *d_Fre = nullptr, *d_Fim = nullptr, *d_ginv = nullptr;
   double *d_partial = nullptr, *d_red = nullptr, *d_energy = nullptr;
-  GridArgs *d_grid_args = nullptr;   // device copy of the (single-rank) grid arguments for the tail of the fused kernel
-  unsigned *d_tail_counter = nullptr;
-  bool tail_now = false;             // set by step(): the next fused push of the last species also reduces and solves
   void *d_kiss_tab = nullptr;   // KissTables: jump-ahead tables of the device KISS64 (allocated on first use)
   unsigned long long *d_noob = nullptr;
   unsigned *d_wmax_hi = nullptr;              // [species] running max |deposit source| (high words), DEP_FIXED
@@ -164,7 +161,7 @@ struct pic1dp_gpu {
   // buffer rotation it was captured with
   cudaGraphExec_t step_graph = nullptr;
   bool graph_enabled = true;
-  bool no_tail = false;              // PIC1DP_NO_TAIL: keep reduce and solve as separate launches inside step()
+
   int graph_cur[PIC1DP_MAX_SPECIES] = {};
   int64_t graph_np[PIC1DP_MAX_SPECIES] = {};
   int64_t graph_launches = 0, graph_nccl = 0, graph_p2p = 0, graph_replays = 0;
@@ -365,8 +362,6 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
     }
   if (h->d_noob) cudaFree(h->d_noob);
   if (h->d_kiss_tab) cudaFree(h->d_kiss_tab);
-  if (h->d_grid_args) cudaFree(h->d_grid_args);
-  if (h->d_tail_counter) cudaFree(h->d_tail_counter);
   if (h->d_wmax_hi) cudaFree(h->d_wmax_hi);
   if (h->d_dep_overflow) cudaFree(h->d_dep_overflow);
 
@@ -390,8 +385,6 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
   return PIC1DP_OK;
 }
 
-static void fill_grid_args(pic1dp_gpu_t *h, GridArgs &g);
-
 static int create_impl(pic1dp_gpu_t *h) {
   const pic1dp_params &p = h->p;
   int ndev = 0;
@@ -409,10 +402,7 @@ static int create_impl(pic1dp_gpu_t *h) {
   CK(cudaGetDeviceProperties(&prop, p.device));
   h->nsm = prop.multiProcessorCount;
   h->graph_enabled = p.no_step_graph == 0 && !getenv("PIC1DP_NO_GRAPH");
-  h->no_tail = getenv("PIC1DP_NO_TAIL") != nullptr;
-#ifdef PIC1DP_NO_TAIL_CODE
-  h->no_tail = true;
-#endif
+
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
@@ -426,13 +416,7 @@ static int create_impl(pic1dp_gpu_t *h) {
   // 32 warps.  Shared/global-atomic deposits run 2 CTAs x 512 threads; the warp-private deposit needs one grid
   // per warp in shared memory, so its CTA is as large as fits (multiple of 4 warps, <= 32).
   int dep = p.deposit_mode;
-  // E copy + deposit grids; the tail of step() (reduce + field solve in the last CTA) reuses the front of it as
-  // rho[nx] + 2 * nmode mode values, which the RED deposit (no grid in shared memory) must leave room for
-  auto smem_need = [&](int d, int thr) {
-    const size_t main = (size_t)8 * (((nx + 1) & ~1) + (size_t)nx * dep_grids(d, thr));
-    const size_t tail = (size_t)8 * (nx + 2 * M);
-    return main > tail ? main : tail;
-  };
+  auto smem_need = [&](int d, int thr) { return (size_t)8 * (((nx + 1) & ~1) + (size_t)nx * dep_grids(d, thr)); };
   auto warp_private_threads = [&]() {
     int w = (int)((max_smem - 8) / ((size_t)nx * 8)) - 1;
     if (w > PIC1DP_MAXTHREADS / 32) w = PIC1DP_MAXTHREADS / 32;
@@ -601,14 +585,6 @@ static int create_impl(pic1dp_gpu_t *h) {
   CK(cudaMemcpyAsync(h->d_Fre, h->h_Fre.data(), (size_t)nx * M * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_Fim, h->h_Fim.data(), (size_t)nx * M * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_ginv, h->h_ginv.data(), (size_t)M * 8, cudaMemcpyHostToDevice, h->stream));
-  if (p.nranks == 1) {   // grid arguments of the fused kernel's tail (no exchange: single rank only)
-    GridArgs g;
-    fill_grid_args(h, g);
-    CK(cudaMalloc(&h->d_grid_args, sizeof(GridArgs)));
-    CK(cudaMemcpyAsync(h->d_grid_args, &g, sizeof(GridArgs), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMalloc(&h->d_tail_counter, 4));
-    CK(cudaMemsetAsync(h->d_tail_counter, 0, 4, h->stream));
-  }
   CK(cudaStreamSynchronize(h->stream));
   return PIC1DP_OK;
 }
@@ -1207,11 +1183,7 @@ int pic1dp_gpu_push(pic1dp_gpu_t *h, int32_t irk) {
     a.x_out = S.x[out];
     a.v_out = S.v[out];
     a.w_out = S.w[out];
-    if (h->tail_now && s == p.nspecies - 1) {   // step(): reduce + field solve in this launch's last CTA
-      a.tail = h->d_grid_args;
-      a.tail_counter = h->d_tail_counter;
-      a.tail_seq = p.field_mode == PIC1DP_FIELD_SEQUENTIAL;
-    }
+
     int cfg = (h->cfg == 1) ? (S.c.unit ? 25 : S.c.pow2 ? 9 : 1) : -1;
     if (cfg > 0 && fused && p.arith_mode == PIC1DP_ARITH_TOLERANCE && (p.iptcldist == 2 || p.iptcldist == 3))
       cfg = (S.c.unit ? 25 : 1) + 32;   // the tolerance form has no constant divisors left, so pow2 needs no variant
@@ -1273,19 +1245,9 @@ int pic1dp_gpu_launch_timing_stop(pic1dp_gpu_t *h, double ms_sum[2], int64_t lau
 
 // one timestep with individual launches: src/pic1dp.F90:79-90
 static int step_direct(pic1dp_gpu_t *h) {
-  // single rank, fused deposit, direct-load kernels: the last CTA of the push kernel also reduces the private grids and
-  // solves the field, so a substep is one launch instead of three (same summation trees: same bits)
-  const bool tail = h->d_grid_args && h->p.fuse != 0 && !h->use_tma[0] && !h->use_tma[1] && !h->use_cpa[0] &&
-                    !h->use_cpa[1] && !h->no_tail;
   for (int irk = 1; irk <= 2; irk++) {
-    h->tail_now = tail;
     int rc = pic1dp_gpu_push(h, irk);
-    h->tail_now = false;
     if (rc) return rc;
-    if (tail) {
-      h->partial_valid = false;   // collected by the tail
-      continue;
-    }
     if (h->p.iptclshape < 4) {
       rc = pic1dp_gpu_compute_shape_x(h);
       if (rc) return rc;

@@ -282,49 +282,3 @@ def test_tolerance_arithmetic_ten_steps_within_north_star_bar(dep):
         out = g.get_markers(0)
     for k in ("x", "v", "w"):
         assert rel_err(out[k], ref.st[0][0][k]) < 1e-12, k
-
-
-# ---- single-launch substeps: reduce + field solve in the last CTA of the fused kernel ----
-
-@pytest.mark.parametrize("dep,nx,nsp,fmode", [(P.DEPOSIT_WARP_PRIVATE, 192, 1, P.FIELD_TREE), (P.DEPOSIT_FIXED, 1000, 1, P.FIELD_TREE),
-                                              (P.DEPOSIT_FIXED, 4096, 2, P.FIELD_SEQUENTIAL), (P.DEPOSIT_FIXED, 33, 1, P.FIELD_TREE),
-                                              (P.DEPOSIT_GLOBAL_RED, 256, 1, P.FIELD_TREE), (P.DEPOSIT_SMEM_ATOMIC, 512, 2, P.FIELD_TREE)])
-def test_step_tail_equals_individual_calls(dep, nx, nsp, fmode):
-    """Inside step() on one GPU the last CTA of the fused kernel also reduces the private grids and solves the field
-    (same summation trees as k_reduce_charge / k_field_solve).  With a deterministic deposit the result must equal the
-    individual push / collect_charge / solve_field calls bit for bit; with atomic deposits within summation tolerance."""
-    kw = dict(nx=nx, capacity=150_001, deposit_mode=dep, field_mode=fmode, nmode=2, modes=[1, 3])
-    if nsp == 2:
-        kw.update(nspecies=2, charge=[-1.0, 1.0], mass=[1.0, 4.0], temperature=[1.0, 0.5], temperature2=[1.0, 0.5],
-                  density=[0.9, 1.0], v0=[5.0, 0.0])
-    op, gp = make_params(**kw)
-    sts = [synth_markers(op, 150_001 - 7 * s, seed=30 + s, isp=s) for s in range(nsp)]
-    outs = []
-    for use_step in (True, False):
-        with P.Pic1dGpu(gp) as g:
-            for s, st in enumerate(sts):
-                g.set_markers(s, st["x"], st["v"], st["p"], st["w"])
-            g.collect_charge()
-            g.solve_field()
-            if use_step:
-                g.step(3)
-            else:
-                for _ in range(3):
-                    for irk in (1, 2):
-                        g.push(irk)
-                        g.collect_charge()
-                        g.solve_field()
-            outs.append((g.get_field(), [g.get_markers(s) for s in range(nsp)], g.counters().kernel_launches))
-    assert outs[0][2] < outs[1][2]          # fewer launches: one per species and substep
-    exact = dep in (P.DEPOSIT_WARP_PRIVATE, P.DEPOSIT_FIXED)
-    for k in ("electric", "chargeden", "mode_re", "mode_im"):
-        if exact:
-            assert np.array_equal(outs[0][0][k], outs[1][0][k]), k
-        else:
-            assert rel_err(outs[0][0][k], outs[1][0][k], np.abs(outs[1][0][k]).max() + 1e-300) < 1e-11, k
-    for s in range(nsp):
-        for k in ("x", "v", "w"):
-            if exact:
-                assert np.array_equal(outs[0][1][s][k], outs[1][1][s][k]), (s, k)
-            else:
-                assert rel_err(outs[0][1][s][k], outs[1][1][s][k]) < 1e-11, (s, k)
