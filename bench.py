@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--sustained-steps", type=int, default=500, help="steps of the additional sustained region (0 = off)")
     ap.add_argument("--e2e-extras", action="store_true", help="also time the host-stream and host-refresh e2e variants")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-alt-arith", action="store_true",
+                    help="skip the second timed region in the other arithmetic mode (reported as 'alt_arith')")
     ap.add_argument("--p2p-trace", action="store_true",
                     help="stamp %%globaltimer at publish / wait entry / wait exit of every peer-memory all-reduce of the "
                          "timed region and report arrival skew vs exchange latency (adds 'p2p_trace' to the JSON line)")
@@ -601,6 +603,37 @@ def main():
         e2e["output_step_ms"] = {"output_all": t_oa}
         e2e["particle_load_ms"] = t_ld
 
+    # ---- the other arithmetic mode, same workload, same box, same run (device-timed like `value`) ----
+    alt = None
+    if not args.no_alt_arith and args.scaling == "weak":
+        other = "tolerance" if args.arith == "strict" else "strict"
+        g.close()
+        gp2 = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit,
+                               load_path=args.load_path, arith_mode=1 if other == "tolerance" else 0,
+                               no_step_graph=1 if args.no_graph else 0)
+        g = P.Pic1dGpu(gp2)
+        if world > 1:
+            setup_comm(P, dist, g, args, rank, world)
+        load_from_host()
+        g.collect_charge()
+        g.solve_field()
+        g.step(args.warmup)
+        barrier()
+        g.launch_timing_start()
+        g.timer_start()
+        g.step(args.steps)
+        ms2 = max_over_ranks(g.timer_stop())
+        lt2 = g.launch_timing_stop()
+        barrier()
+        t_i1, t_i2 = lt2[0][0] / max(lt2[0][1], 1), lt2[1][0] / max(lt2[1][1], 1)
+        alt = {"arith_mode": other, "value": ntotal * args.steps / (ms2 * 1e-3), "unit": "particle-steps/s",
+               "ms_per_step": ms2 / args.steps, "step_roofline_frac": n * BYTES_STEP / (ms2 / args.steps * 1e-3) / 1e9 / peak,
+               "irk1": {"ms_per_launch": t_i1, "frac": n * BYTES_IRK1 / (t_i1 * 1e-3) / 1e9 / peak},
+               "irk2": {"ms_per_launch": t_i2, "frac": n * BYTES_IRK2 / (t_i2 * 1e-3) / 1e9 / peak},
+               "note": "STRICT = the reference's operation order everywhere (the parity target of the tests); TOLERANCE = "
+                       "-d ln f0/dv with one exponential instead of two: x, v, cell index still bit-exact, w within "
+                       "1e-14 of max|w| per substep (tests/test_gpu_round2.py)"}
+
     # ---- CPU baseline beside it (rank 0, bounded sample) ----
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
@@ -622,7 +655,7 @@ def main():
             "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(c1.kernel_launches - c0.kernel_launches),
             "nccl_calls": int(c1.nccl_calls - c0.nccl_calls),
             "p2p_allreduces": int(c1.p2p_allreduces - c0.p2p_allreduces), "p2p_timeouts": int(c1.p2p_timeouts),
-            "parity_check": parity, "p2p_trace": p2p_trace,
+            "parity_check": parity, "p2p_trace": p2p_trace, "alt_arith": alt,
             "roofline": roofline, "roofline_detail": roofline_detail, "cpu_baseline": cpu,
             "deposit_mode": int(c1.deposit_mode), "grid_ctas": int(c1.grid_ctas), "cta_threads": int(c1.cta_threads),
             "smem_bytes": int(c1.smem_bytes), "oob_markers": int(c1.oob_markers), "field_energy": energy,

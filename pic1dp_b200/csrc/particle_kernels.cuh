@@ -633,13 +633,16 @@ struct Depositor<DEP_SMEM_ATOMIC> {
     }
 #else
     double2 old = *slot;   // outside the loop: ptxas hoists this load above the weight arithmetic
-    for (;;) {
-      const unsigned long long e0 = __double_as_longlong(old.x), e1 = __double_as_longlong(old.y);
-      unsigned long long f0, f1;
-      cas128(addr, e0, e1, __double_as_longlong(dadd(old.x, a)), __double_as_longlong(dadd(old.y, b)), f0, f1);
-      if (f0 == e0 && f1 == e1) break;
-      old.x = __longlong_as_double(f0);
-      old.y = __longlong_as_double(f1);
+    unsigned long long e0 = __double_as_longlong(old.x), e1 = __double_as_longlong(old.y), f0, f1;
+    // first attempt peeled by hand (see Depositor<DEP_FIXED>::add: no YIELD on the success path)
+    cas128(addr, e0, e1, __double_as_longlong(dadd(old.x, a)), __double_as_longlong(dadd(old.y, b)), f0, f1);
+    if (__builtin_expect(!(f0 == e0 && f1 == e1), 0)) {
+      do {
+        e0 = f0;
+        e1 = f1;
+        cas128(addr, e0, e1, __double_as_longlong(dadd(__longlong_as_double(e0), a)),
+               __double_as_longlong(dadd(__longlong_as_double(e1), b)), f0, f1);
+      } while (!(f0 == e0 && f1 == e1));
     }
 #endif
   }
@@ -771,13 +774,17 @@ struct Depositor<DEP_FIXED> {
     longlong2 *slot = reinterpret_cast<longlong2 *>(g) + ix;
     const unsigned addr = (unsigned)__cvta_generic_to_shared(slot);
     const longlong2 old = *slot;   // outside the loop: hoisted above the weight arithmetic
-    unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y;
-    for (;;) {
-      unsigned long long f0, f1;
-      cas128(addr, e0, e1, e0 + ia, e1 + ib, f0, f1);
-      if (f0 == e0 && f1 == e1) break;
-      e0 = f0;
-      e1 = f1;
+    unsigned long long e0 = (unsigned long long)old.x, e1 = (unsigned long long)old.y, f0, f1;
+    // first attempt peeled by hand: ptxas puts a YIELD into every spin-loop body, and with the attempt inside the loop
+    // the warp yields its issue slot on EVERY deposit -- measured: 30 % of the kernel spent at the end-of-loop barrier
+    // (warps drift apart), 4.0 instead of 2.3 ms per step.  Only genuine retries may spin.
+    cas128(addr, e0, e1, e0 + ia, e1 + ib, f0, f1);
+    if (__builtin_expect(!(f0 == e0 && f1 == e1), 0)) {
+      do {
+        e0 = f0;
+        e1 = f1;
+        cas128(addr, e0, e1, e0 + ia, e1 + ib, f0, f1);
+      } while (!(f0 == e0 && f1 == e1));
     }
   }
   PIC1DP_DEP_ADD2_SERIAL
