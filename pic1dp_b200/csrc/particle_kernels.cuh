@@ -8,7 +8,9 @@
 //
 // Arithmetic is "strict": every fp64 operation is an explicit round-to-nearest intrinsic in the reference's
 // left-to-right order, so nvcc cannot contract to FMA.  Given identical inputs the cell index, weights, x and v
-// are bit-identical to the x86-64 reference build; w differs only through exp() (<= 1 ulp vs glibc).
+// equal the x86-64 reference build's bit for bit -- proven for every division the fast path does not hand to the IEEE
+// routine except one corner (quotient an exact power of two AND within 2^-104 of the midpoint below it: probability
+// below 2^-150 per division, see div_suspect); w differs only through exp() (<= 1 ulp vs glibc).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -49,7 +49,7 @@ def test_energy_trace_matches_oracle_200_steps():
     assert np.max(np.abs(e_gpu / e_ref - 1.0)) < 1e-9
 
 
-@pytest.mark.parametrize("dep", [P.DEPOSIT_SMEM_ATOMIC, P.DEPOSIT_WARP_PRIVATE])
+@pytest.mark.parametrize("dep", [P.DEPOSIT_SMEM_ATOMIC, P.DEPOSIT_WARP_PRIVATE, P.DEPOSIT_FIXED])
 def test_bump_on_tail_growth_rate(dep):
     """4e6 quiet-start markers, t = 0..60: gamma from the energy fit on [20, 50] within 2% of the analytic root."""
     op, gp = make_params(nx=192, capacity=4_000_000, deposit_mode=dep)

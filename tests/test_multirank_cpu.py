@@ -132,3 +132,39 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "particle-steps/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_trace_analysis_separates_skew_from_exchange_floor():
+    """bench.py --p2p-trace: per all-reduce and rank d = wait_exit - publish on that rank's own clock; the last
+    arrival's d is the exchange floor, the rest is arrival skew.  Synthetic stamps with known skew and unsynchronised
+    clocks must come back out."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    cap, nep, ranks = 64, 40, 4
+    rng = np.random.default_rng(0)
+    clock_offset = [0, 5_000_000, -3_000_000, 123]          # ns: the GPUs' %globaltimer are not synchronised
+    rows = []
+    arrive = np.cumsum(rng.integers(900_000, 1_100_000, size=nep + 1))   # true time the LAST rank publishes
+    skews = rng.integers(0, 30_000, size=(nep + 1, ranks))
+    skews[:, 2] = 0                                                      # rank 2 always arrives last
+    for r in range(ranks):
+        st = np.zeros((cap, 3), dtype=np.int64)
+        for e in range(1, nep + 1):
+            pub = arrive[e] - skews[e, r] + clock_offset[r]
+            st[e % cap] = (pub, pub + 3_000, arrive[e] + 4_500 + clock_offset[r])    # boundary 3 us, floor 4.5 us
+        rows.append((st, nep))
+    t = bench.analyse_trace(rows, nep, cap)
+    assert t["allreduces"] == nep and t["ranks"] == ranks
+    assert abs(t["exchange_floor_min_over_ranks"]["median"] - 4.5) < 1e-9
+    assert abs(t["kernel_boundary_publish_to_wait_entry"]["median"] - 3.0) < 1e-9
+    assert abs(t["arrival_skew_wait"]["mean"] - skews[1:].mean() / 1e3) < 1e-9
+    assert abs(t["per_step_cost_us"]["skew_worst_rank"] - 2 * skews[1:].max(axis=1).mean() / 1e3) < 1e-9
+
+
+def test_bench_rank_seeds_are_valid_kiss64_states_and_rank_dependent():
+    sys.path.insert(0, ROOT)
+    import bench
+    a, b, a2 = bench.rank_seeds(0), bench.rank_seeds(1), bench.rank_seeds(0)
+    assert a == a2 and a != b and len(a) == 4
+    assert a[1] != 0 and a[3] < (1 << 58) + 1      # xorshift word non-zero, carry in range after the warm-up
