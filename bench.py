@@ -305,10 +305,13 @@ def analyse_trace(rows, nepochs, cap):
             "spin_wait_entry_to_exit": {"median": q(spin, 50), "mean": float(spin.mean()) / 1e3, "p95": q(spin, 95)},
             "arrival_skew_wait": {"mean": float(skew.mean()) / 1e3, "median": q(skew, 50), "p95": q(skew, 95),
                                   "mean_of_worst_rank": float(skew.max(axis=1).mean()) / 1e3},
+            "per_rank_mean_skew_wait": [float(v) / 1e3 for v in skew.mean(axis=0)],
+            "last_arrival_counts_per_rank": [int(v) for v in np.bincount(d.argmin(axis=1), minlength=len(rows))],
             "per_step_cost_us": {"exchange_floor": 2 * float(floor.mean()) / 1e3,
                                  "skew_mean_rank": 2 * float(skew.mean()) / 1e3,
                                  "skew_worst_rank": 2 * float(skew.max(axis=1).mean()) / 1e3},
-            "note": "d = wait_exit - publish per rank and all-reduce; floor = min over ranks (the last arrival); skew = d - floor"}
+            "note": "d = wait_exit - publish per rank and all-reduce; floor = min over ranks (the last arrival); skew = d - floor; "
+                    "per_rank_mean_skew_wait small / last_arrival_counts large for a rank = that GPU is systematically the slowest"}
 
 
 def parity_preflight(P, dist, torch, args, rank, world, local):
