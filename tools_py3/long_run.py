@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--tmax", type=float, default=60.0)
     ap.add_argument("--fit", type=float, nargs=2, default=[20.0, 50.0])
     ap.add_argument("--deposit", type=int, default=0)
+    ap.add_argument("--arith", default="strict", choices=["strict", "tolerance"])
+    ap.add_argument("--rng", default="host", choices=["host", "kiss64"],
+                    help="host: numpy markers uploaded with set_markers; kiss64: particle_load with the device KISS64 stream")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import torch
@@ -38,7 +41,8 @@ def main():
     if world > 1:
         dist.init_process_group("gloo")
     n = int(args.markers_per_gpu)
-    gp = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit)
+    gp = P.default_params(nx=args.nx, capacity=n, device=local, rank=rank, nranks=world, deposit_mode=args.deposit,
+                          arith_mode=1 if args.arith == "tolerance" else 0)
     g = P.Pic1dGpu(gp)
     if world > 1:
         uid = [g.comm_unique_id() if rank == 0 else None]
@@ -47,12 +51,16 @@ def main():
         handles = [None] * world
         dist.all_gather_object(handles, g.p2p_export())
         g.p2p_import(handles)
-    x, v, p, w = (np.empty(n) for _ in range(4))
-    fill_markers(x, v, p, w, gp.lx, seed=4321 + rank)
-    p *= 1.0 / world   # fill_markers normalises p for n markers; the plasma holds n * world of them
-    w *= 1.0 / world
-    g.set_markers(0, x, v, p, w)
-    del x, v, p, w
+    if args.rng == "kiss64":
+        from bench import rank_seeds
+        g.load_markers_kiss64(0, n, rank_seeds(rank), 0, n, n * world, v_max=8.0)
+    else:
+        x, v, p, w = (np.empty(n) for _ in range(4))
+        fill_markers(x, v, p, w, gp.lx, seed=4321 + rank)
+        p *= 1.0 / world   # fill_markers normalises p for n markers; the plasma holds n * world of them
+        w *= 1.0 / world
+        g.set_markers(0, x, v, p, w)
+        del x, v, p, w
     g.collect_charge()
     g.solve_field()
     nout = int(round(args.tmax / (10 * gp.dt)))
@@ -73,7 +81,8 @@ def main():
                "rel_dev": gamma / 0.0838311 - 1.0, "wall_s_incl_outputs": wall,
                "particle_steps_per_s_wall": n * world * nout * 10 / wall, "oob_markers": int(c.oob_markers),
                "p2p_allreduces": int(c.p2p_allreduces), "p2p_timeouts": int(c.p2p_timeouts), "nccl_calls": int(c.nccl_calls),
-               "deposit_mode": int(c.deposit_mode), "t": t, "energy": en}
+               "deposit_mode": int(c.deposit_mode), "arith_mode": args.arith, "rng": args.rng,
+               "graph_replays": int(c.graph_replays), "t": t, "energy": en}
         print(json.dumps({k: v for k, v in res.items() if k not in ("t", "energy")}))
         if args.out:
             json.dump(res, open(args.out, "w"))
