@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(256) k_load_markers(const LoadArgs a) {
     for (int im = 0; im < a.init_nmode; im++) {  // :226-232
       const double k = dmul(ddiv(dmul(2.0, PI), a.lx), (double)a.init_mode[im]);
       const double arg = dmul(k, px);
-      pw = dadd(dadd(pw, dmul(a.init_cos[im], cos(arg))), dmul(a.init_sin[im], sin(arg)));
+      double sn, cs;
+      sincos(arg, &sn, &cs);   // one argument reduction for both (same results as sin() and cos())
+      pw = dadd(dadd(pw, dmul(a.init_cos[im], cs)), dmul(a.init_sin[im], sn));
     }
     pw = dmul(dmul(pw, pp), 1.0);  // * p * input_pertb_shape (= 1.0), :235-236
     if (!a.linear) pp = dadd(pp, dmul(1.0, pw));  // VecAXPY(p, 1.0, w), :260-263

@@ -827,11 +827,11 @@ static int kiss64_fill_device(pic1dp_gpu_t *h, const uint64_t seeds[4], int64_t 
   if (rc) return rc;
   if (n == 0) return PIC1DP_OK;
   Kiss64 s0 = {seeds[0], seeds[1], seeds[2], seeds[3]};
-  const int chunk = 512;
+  const int chunk = 512;   // a multiple of 32 (the tile protocol of k_kiss64_fill)
   const int64_t nchunks = (n + chunk - 1) / chunk;
-  int blocks = (int)((nchunks + 255) / 256);
-  if (blocks > h->nsm * 8) blocks = h->nsm * 8;
-  k_kiss64_fill<<<blocks, 256, 0, h->stream>>>(s0, (uint64_t)offset, n, chunk, (const KissTables *)h->d_kiss_tab, d_out);
+  int blocks = (int)((nchunks + 127) / 128);
+  if (blocks > h->nsm * 16) blocks = h->nsm * 16;
+  k_kiss64_fill<<<blocks, 128, 0, h->stream>>>(s0, (uint64_t)offset, n, chunk, (const KissTables *)h->d_kiss_tab, d_out);
   CKL(h);
   return PIC1DP_OK;
 }
