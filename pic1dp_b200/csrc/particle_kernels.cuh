@@ -48,6 +48,11 @@
 #ifndef PIC1DP_NEWTON2
 #define PIC1DP_NEWTON2 0
 #endif
+// CAS retries written as straight-line code before the spin loop (whose body carries ptxas's YIELD): with ~2 retrying
+// warp-instructions per tile step at nx = 1024 the loop's YIELD is still executed about as often as a deposit
+#ifndef PIC1DP_CAS_UNROLL
+#define PIC1DP_CAS_UNROLL 2
+#endif
 
 namespace pic1dp {
 
@@ -638,6 +643,14 @@ struct Depositor<DEP_SMEM_ATOMIC> {
     unsigned long long e0 = __double_as_longlong(old.x), e1 = __double_as_longlong(old.y), f0, f1;
     // first attempt peeled by hand (see Depositor<DEP_FIXED>::add: no YIELD on the success path)
     cas128(addr, e0, e1, __double_as_longlong(dadd(old.x, a)), __double_as_longlong(dadd(old.y, b)), f0, f1);
+#pragma unroll
+    for (int r = 0; r < PIC1DP_CAS_UNROLL; r++) {   // straight-line retries (no YIELD)
+      if (f0 == e0 && f1 == e1) return;
+      e0 = f0;
+      e1 = f1;
+      cas128(addr, e0, e1, __double_as_longlong(dadd(__longlong_as_double(e0), a)),
+             __double_as_longlong(dadd(__longlong_as_double(e1), b)), f0, f1);
+    }
     if (__builtin_expect(!(f0 == e0 && f1 == e1), 0)) {
       do {
         e0 = f0;
@@ -781,6 +794,13 @@ struct Depositor<DEP_FIXED> {
     // the warp yields its issue slot on EVERY deposit -- measured: 30 % of the kernel spent at the end-of-loop barrier
     // (warps drift apart), 4.0 instead of 2.3 ms per step.  Only genuine retries may spin.
     cas128(addr, e0, e1, e0 + ia, e1 + ib, f0, f1);
+#pragma unroll
+    for (int r = 0; r < PIC1DP_CAS_UNROLL; r++) {   // straight-line retries (no YIELD)
+      if (f0 == e0 && f1 == e1) return;
+      e0 = f0;
+      e1 = f1;
+      cas128(addr, e0, e1, e0 + ia, e1 + ib, f0, f1);
+    }
     if (__builtin_expect(!(f0 == e0 && f1 == e1), 0)) {
       do {
         e0 = f0;
