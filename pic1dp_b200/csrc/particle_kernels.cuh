@@ -51,7 +51,7 @@
 // CAS retries written as straight-line code before the spin loop (whose body carries ptxas's YIELD): with ~2 retrying
 // warp-instructions per tile step at nx = 1024 the loop's YIELD is still executed about as often as a deposit
 #ifndef PIC1DP_CAS_UNROLL
-#define PIC1DP_CAS_UNROLL 2
+#define PIC1DP_CAS_UNROLL 4
 #endif
 
 namespace pic1dp {
