@@ -101,6 +101,7 @@ struct Species {
   int64_t np = 0;
   bool loaded = false;
   bool wmax_valid = false;   // d_wmax_hi[s] covers the current deposit source (fixed-point deposit)
+  bool pmax_valid = false;   // d_diag_max[2 s] holds max |p| of the current markers (limb histograms)
   SpeciesConst c;
 };
 
@@ -127,6 +128,10 @@ struct pic1dp_gpu {
   double *d_diag_part = nullptr, *d_diag_sums = nullptr, *d_hist = nullptr, *d_hist_out = nullptr;
   int diag_grid = 0, hist_cells = 0, hist_copies = 16, hist_smem_set = -1;
   double *d_hist_all = nullptr;   // output_all: reduced histograms of all species
+  __int128 *d_hist_tab = nullptr;   // limb histograms: one 128-bit integer table per CTA, [nsm][3][ncell]
+  unsigned *d_diag_max = nullptr;   // [species][2] high words of max |p|, max |w|
+  int hist_tab_cells = 0, limb_smem_set = -1;
+  bool limb_enabled = true;         // PIC1DP_DIAG_CAS=1: the round-2 CAS.128 histogram kernel instead
   size_t hist_all_cap = 0;
   // marker optimisation (allocated on first use): device scratch of compute_dist_pertb_abs_v, its host copy
   // particle_dist_pertb_abs_v(ispecies, 0:nv-1), and the pinned staging arrays of merge / remove / split
@@ -364,6 +369,8 @@ int pic1dp_gpu_destroy(pic1dp_gpu_t *h) {
   if (h->d_kiss_tab) cudaFree(h->d_kiss_tab);
   if (h->d_wmax_hi) cudaFree(h->d_wmax_hi);
   if (h->d_dep_overflow) cudaFree(h->d_dep_overflow);
+  if (h->d_hist_tab) cudaFree(h->d_hist_tab);
+  if (h->d_diag_max) cudaFree(h->d_diag_max);
 
   if (h->h_dep_overflow) cudaFreeHost(h->h_dep_overflow);
   for (int r = 0; r < 8; r++)
@@ -402,6 +409,7 @@ static int create_impl(pic1dp_gpu_t *h) {
   CK(cudaGetDeviceProperties(&prop, p.device));
   h->nsm = prop.multiProcessorCount;
   h->graph_enabled = p.no_step_graph == 0 && !getenv("PIC1DP_NO_GRAPH");
+  h->limb_enabled = !getenv("PIC1DP_DIAG_CAS");
 
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
@@ -730,6 +738,7 @@ static int upload_species(pic1dp_gpu_t *h, int isp, int64_t np, const double *x,
   h->h2d += 4 * (int64_t)b;
   S.loaded = true;
   S.wmax_valid = false;
+  S.pmax_valid = false;
   return invalidate_partials(h);
 }
 
@@ -789,6 +798,7 @@ static int load_markers_finish(pic1dp_gpu_t *h, int32_t isp, int64_t np, int64_t
   CK(cudaStreamSynchronize(h->stream));  // host buffers are only borrowed for the call
   S.loaded = true;
   S.wmax_valid = false;
+  S.pmax_valid = false;
   return invalidate_partials(h);
 }
 
@@ -1512,6 +1522,52 @@ static int launch_hist(pic1dp_gpu_t *h, int isp, int nx_opd, int nv_opd, double 
   a.nv_opd = nv_opd;
   a.v_max = v_max;
   const size_t hs = (size_t)4 * nx_opd * (nv_opd + 1) * 8;
+  const size_t ls = (size_t)PIC1DP_LIMB_W * nx_opd * (nv_opd + 1) * 4;   // limb counters: [cells + spare row][PIC1DP_LIMB_W words]
+  Species &S = h->sp[isp];
+  if (h->limb_enabled && ls <= h->max_smem && S.np > 0) {
+    // exact fixed-point histograms with native 32-bit shared-memory adds (k_diag_limb)
+    if (!h->d_diag_max) {
+      CK(cudaMalloc(&h->d_diag_max, (size_t)2 * PIC1DP_MAX_SPECIES * 4));
+      CK(cudaMemsetAsync(h->d_diag_max, 0, (size_t)2 * PIC1DP_MAX_SPECIES * 4, h->stream));
+    }
+    if (ncell > h->hist_tab_cells) {
+      if (h->d_hist_tab) cudaFree(h->d_hist_tab);
+      h->d_hist_tab = nullptr;
+      CK(cudaMalloc(&h->d_hist_tab, (size_t)h->nsm * 3 * ncell * 16));
+      h->hist_tab_cells = ncell;
+    }
+    if (h->limb_smem_set != (int)ls) {
+      CK(cudaFuncSetAttribute(k_diag_limb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls));
+      CK(cudaFuncSetAttribute(k_diag_limb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ls));
+      h->limb_smem_set = (int)ls;
+    }
+    // the tables are laid out with stride 3 * ncell of THIS call
+    CK(cudaMemsetAsync(h->d_hist_tab, 0, (size_t)h->nsm * 3 * ncell * 16, h->stream));
+    unsigned *mx = h->d_diag_max + 2 * isp;
+    if (!S.pmax_valid) {   // p does not change between marker replacements
+      CK(cudaMemsetAsync(mx, 0, 4, h->stream));
+      k_absmax_hi<<<h->nsm * 8, 256, 0, h->stream>>>(S.p, S.np, mx);
+      CKL(h);
+      S.pmax_valid = true;
+    }
+    CK(cudaMemsetAsync(mx + 1, 0, 4, h->stream));
+    if (h->p.deltaf) {
+      k_absmax_hi<<<h->nsm * 8, 256, 0, h->stream>>>(S.w[S.cur], S.np, mx + 1);
+      CKL(h);
+    }
+    a.tab = h->d_hist_tab;
+    a.max_hi = mx;
+    if (with_sums) k_diag_limb<true><<<h->nsm, 1024, ls, h->stream>>>(a);
+    else k_diag_limb<false><<<h->nsm, 1024, ls, h->stream>>>(a);
+    CKL(h);
+    if (with_sums) {
+      k_diag_sums_final<<<1, 32, 0, h->stream>>>(h->d_diag_part, h->nsm, h->d_diag_sums + 3 * isp);
+      CKL(h);
+    }
+    k_diag_limb_final<<<(3 * ncell + 63) / 64, 256, 0, h->stream>>>(h->d_hist_tab, h->nsm, ncell, mx, d_out);
+    CKL(h);
+    return PIC1DP_OK;
+  }
   if (hs <= h->max_smem) {
     if (h->hist_smem_set != (int)hs) {
       CK(cudaFuncSetAttribute(k_diag_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));

@@ -160,3 +160,97 @@ def test_output_all_odd_histogram_grids():
             dr = ref.o.output_ptcldist(ref.st, 0, nxo, nvo, vm)
             for k in dr:
                 assert rel_err(dists[0][k], dr[k]) < 1e-11, (nxo, nvo, k)
+
+
+def _hist_all(gp, st, nxo=64, nvo=64, vm=8.0):
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        a = g.output_all(nxo, nvo, vm)
+        b = g.output_all(nxo, nvo, vm)
+        c = g.output_ptcldist(0, nxo, nvo, vm)
+    return a, b, c
+
+
+def test_limb_histograms_are_bitwise_reproducible_and_match_the_cas_kernel(monkeypatch):
+    """The default histogram kernel (k_diag_limb) accumulates exact fixed-point integers with native 32-bit shared-memory
+    adds: the result does not depend on the arrival order, so repeated calls and a second handle agree bit for bit;
+    against the round-2 CAS.128 kernel (PIC1DP_DIAG_CAS=1, fp64 sums in arrival order) it agrees to 1e-12 of the maximum."""
+    op, gp = make_params(nx=192, capacity=300000)
+    st = synth_markers(op, 300000, seed=72)
+    st["w"][::7] *= -1.0
+    (sc1, d1), (sc2, d2), sep1 = _hist_all(gp, st)
+    (sc3, d3), _, _ = _hist_all(gp, st)
+    for k in d1[0]:
+        assert np.array_equal(d1[0][k], d2[0][k]), k      # same handle, second call
+        assert np.array_equal(d1[0][k], d3[0][k]), k      # another handle
+        assert np.array_equal(d1[0][k], sep1[k]), k       # output_ptcldist runs the same kernel without the sums
+    monkeypatch.setenv("PIC1DP_DIAG_CAS", "1")
+    (sc4, d4), _, _ = _hist_all(gp, st)
+    monkeypatch.delenv("PIC1DP_DIAG_CAS")
+    assert np.array_equal(sc1, sc4)                       # the output_field sums do not go through the histogram
+    for k in d1[0]:
+        assert rel_err(d1[0][k], d4[0][k]) < 1e-12, k
+
+
+@pytest.mark.parametrize("case", ["outlier", "zero_w", "tiny", "huge", "one_cell"])
+def test_limb_histograms_dynamic_range(case):
+    """The fixed-point scale comes from the largest |p| and |w| of the species: one huge outlier costs the other markers
+    resolution (2^-42 of the outlier), all-zero and very small / very large weights must not break the scaling, and the
+    worst case of the counter bounds (every marker in one cell, same sign) stays exact."""
+    op, gp = make_params(nx=192, capacity=200000)
+    st = synth_markers(op, 200000, seed=73)
+    if case == "outlier":
+        st["w"][1234] = 1.0e3 * np.max(np.abs(st["w"]))
+        st["p"][4321] = 1.0e3 * np.max(np.abs(st["p"]))
+    elif case == "zero_w":
+        st["w"][:] = 0.0
+    elif case == "tiny":
+        st["w"] *= 1e-200
+        st["p"] *= 1e-100
+    elif case == "huge":
+        st["w"] *= 1e250
+        st["p"] *= 1e200
+    elif case == "one_cell":
+        st["x"][:] = 0.4321 * op.lx / 64 + 10 * op.lx / 64
+        st["v"][:] = 0.7
+        st["w"][:] = np.abs(st["w"]).max()
+        st["p"][:] = np.abs(st["p"]).max()
+    ref = OracleRun(op, [[copy_state(st)]])
+    (sc, d), _, _ = _hist_all(gp, st)
+    dr = ref.o.output_ptcldist(ref.st, 0, 64, 64, 8.0)
+    # one_cell: the oracle's own sequential fp64 sum of 2e5 equal terms is only good to ~1e-11; the integer sum is exact
+    tol = 1e-10 if case == "one_cell" else 1e-11
+    for k in dr:
+        scale = np.max(np.abs(dr[k]))
+        if scale == 0.0:
+            assert not np.any(d[0][k]), (case, k)
+        else:
+            assert rel_err(d[0][k], dr[k], scale) < tol, (case, k)
+    if case == "one_cell":
+        cell = (op.lx / 64) * (16.0 / 63)
+        assert abs(np.sum(d[0]["markr_xv"]) * cell / st["x"].size - 1.0) < 1e-12
+        assert abs(np.sum(d[0]["pertb_xv"]) * cell / (st["x"].size * st["w"][0]) - 1.0) < 1e-12
+
+
+def test_limb_histograms_counter_flush_at_scale():
+    """2.2e7 markers: every CTA runs more than PIC1DP_LIMB_FLUSH = 128 tile steps, so its 32-bit counters are folded into
+    the 64-bit table in mid-kernel; conservation (sum of the g histogram = markers inside |v| < v_max, sum of f / delta f
+    = sum of p / w over them) holds to rounding and the oracle agrees on a strided sample of the same markers."""
+    n = 22_000_000
+    op, gp = make_params(nx=1024, capacity=n)
+    st = synth_markers(op, n, seed=74)
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        sc, d = g.output_all(64, 64, 8.0)
+        sc2, d2 = g.output_all(64, 64, 8.0)
+    inside = np.abs(st["v"]) < 8.0
+    cell = (op.lx / 64) * (16.0 / 63)      # the reference scales the x-v histograms by 1 / (delx delv)
+    assert abs(np.sum(d[0]["markr_xv"]) * cell / np.count_nonzero(inside) - 1.0) < 1e-12
+    assert abs(np.sum(d[0]["total_xv"]) * cell / np.sum(st["p"][inside]) - 1.0) < 1e-12
+    assert abs(np.sum(d[0]["pertb_xv"]) * cell - np.sum(st["w"][inside])) < 1e-12 * np.sum(np.abs(st["w"][inside]))
+    for k in d[0]:
+        assert np.array_equal(d[0][k], d2[0][k]), k
+    ref = OracleRun(op, [[{k: st[k].copy() for k in ("x", "v", "p", "w")}]])
+    dr = ref.o.output_ptcldist(ref.st, 0, 64, 64, 8.0)
+    for k in dr:
+        assert rel_err(d[0][k], dr[k]) < 1e-11, k
