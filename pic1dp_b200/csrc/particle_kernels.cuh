@@ -30,11 +30,13 @@
 #ifndef PIC1DP_PV_MASK
 #define PIC1DP_PV_MASK 4
 #endif
-// 1: the fp64 pair-grid depositor deposits the two markers of a thread with overlapped round trips (Depositor::add2).
+// bit 0: the fp64 pair-grid depositor deposits the two markers of a thread with overlapped round trips (Depositor::add2).
 // Measured on B200 (profiles/r02_ab_experiments.md): the overlap hides the CAS latency but the extra live registers
 // spill at 64 registers per thread and the kernels get 2-4 % slower.
+// bit 1: the same for the fixed-point depositor with native adds (four returning adds, then the four carries): no spill,
+// 2.161-2.185 -> 2.134-2.136 ms per step at 1e8 markers (strict arithmetic).
 #ifndef PIC1DP_ADD2
-#define PIC1DP_ADD2 0
+#define PIC1DP_ADD2 2
 #endif
 // fixed-point conversion: 1 = F2I.S64.F64, 0 = magic-number add + integer subtract
 #ifndef PIC1DP_FIXED_F2I
@@ -44,6 +46,11 @@
 // the reciprocal in the fast divisions (not needed for correctness: the residual test certifies the quotient)
 #ifndef PIC1DP_CAS_RELOAD
 #define PIC1DP_CAS_RELOAD 0
+#endif
+// fixed-point deposit: 1 = 64-bit integer adds as two native 32-bit ATOMS.ADD (low word returning, high word + carry),
+// 0 = the round-2 ATOMS.CAS.128 loop on {left, right} int64 pairs
+#ifndef PIC1DP_FIXED_NATIVE
+#define PIC1DP_FIXED_NATIVE 1
 #endif
 #ifndef PIC1DP_NEWTON2
 #define PIC1DP_NEWTON2 0
@@ -782,6 +789,48 @@ struct Depositor<DEP_FIXED> {
 #endif
   }
   // a, b = weight * prescaled source: RN(weight * source) * 2^e exactly, then rounded to the nearest integer
+#if PIC1DP_FIXED_NATIVE
+  // The grid is four planes of nx 32-bit words {low left, high left, low right, high right}: a 64-bit integer add is the
+  // native ATOMS.ADD of the low word (returning the old value) plus the add of (high word + carry), the carry being
+  // known to exactly the thread whose add wrapped the low word.  Four native adds, no compare-and-swap loop, no retry
+  // path: on B200 the native 32-bit shared-memory add retires ~9 lane-operations per clock per SM at random banks, the
+  // LDS.128 + CAS.128 pair 0.7 (tools_py3/dev/smem_scatter_bench.cu).  Word planes instead of 16-byte slots so that the
+  // lanes of one ATOMS spread over all 32 banks (slot-major words would use 8).
+  int nx;
+  __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
+    (void)ixr;
+    if (!valid) return;
+    const double magic = 6755399441055744.0;   // the integer lands in the low mantissa bits of x + 1.5 * 2^52
+    const double ta = dadd(a, magic), tb = dadd(b, magic);
+    const unsigned la = (unsigned)__double2loint(ta), lb = (unsigned)__double2loint(tb);
+    const unsigned ha = (unsigned)(__double2hiint(ta) - 0x43380000), hb = (unsigned)(__double2hiint(tb) - 0x43380000);
+    unsigned *w = reinterpret_cast<unsigned *>(g) + ix;
+    const unsigned oa = atomicAdd(w, la), ob = atomicAdd(w + 2 * nx, lb);
+    atomicAdd(w + nx, ha + ((oa + la) < la ? 1u : 0u));        // results unused: fire-and-forget
+    atomicAdd(w + 3 * nx, hb + ((ob + lb) < lb ? 1u : 0u));
+  }
+  // both markers of a thread: the four returning adds are issued before the four carries wait for them
+  __device__ __forceinline__ void add2(int ix0, int ixr0, double a0, double b0, int ix1, int ixr1, double a1, double b1,
+                                       bool valid) {
+    (void)ixr0;
+    (void)ixr1;
+    if (!valid) return;
+    const double magic = 6755399441055744.0;
+    const double t[4] = {dadd(a0, magic), dadd(b0, magic), dadd(a1, magic), dadd(b1, magic)};
+    unsigned *w0 = reinterpret_cast<unsigned *>(g) + ix0, *w1 = reinterpret_cast<unsigned *>(g) + ix1;
+    unsigned *lo[4] = {w0, w0 + 2 * nx, w1, w1 + 2 * nx};
+    unsigned l[4], o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      l[k] = (unsigned)__double2loint(t[k]);
+      o[k] = atomicAdd(lo[k], l[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      atomicAdd(lo[k] + nx, (unsigned)(__double2hiint(t[k]) - 0x43380000) + ((o[k] + l[k]) < l[k] ? 1u : 0u));
+  }
+#define PIC1DP_FIXED_HAS_ADD2 1
+#else
   __device__ __forceinline__ void add(int ix, int ixr, double a, double b, bool valid) {
     (void)ixr;
     if (!valid) return;
@@ -809,11 +858,19 @@ struct Depositor<DEP_FIXED> {
       } while (!(f0 == e0 && f1 == e1));
     }
   }
+#endif
+#ifndef PIC1DP_FIXED_HAS_ADD2
   PIC1DP_DEP_ADD2_SERIAL
+#endif
 };
 
 // scale of this launch: wmax_hi = high word of the running max |source|, ncap = markers this CTA handles
-__device__ __forceinline__ void fixed_scale(Depositor<DEP_FIXED> &dep, const unsigned wmax_hi, const long long ncap) {
+__device__ __forceinline__ void fixed_scale(Depositor<DEP_FIXED> &dep, const unsigned wmax_hi, const long long ncap, const int nx) {
+#if PIC1DP_FIXED_NATIVE
+  dep.nx = nx;
+#else
+  (void)nx;
+#endif
   int ex = (int)((wmax_hi >> 20) & 0x7ff);   // biased exponent of the maximum
   if (ex < 100) ex = 100;                     // all-zero / denormal sources: any scale works, keep 2^e finite
   int lb = 62 - (64 - __clzll(ncap > 1 ? ncap - 1 : 1));   // log2 B = 62 - ceil(log2 ncap)
@@ -838,11 +895,21 @@ __device__ __forceinline__ void fixed_finish(const Depositor<DEP_FIXED> &dep, un
 // rho[j] = left[j] + right[j-1], summed as integers (exact) and converted once.
 __device__ __forceinline__ void fixed_flush(double *pairs, int nx, double *my_partial, const double inv) {
   __syncthreads();
+#if PIC1DP_FIXED_NATIVE
+  const unsigned *w = reinterpret_cast<const unsigned *>(pairs);   // planes: low left, high left, low right, high right
+  for (int j = threadIdx.x; j < nx; j += blockDim.x) {
+    const int jl = (j == 0) ? nx - 1 : j - 1;  // right weights of the cell to the left (periodic, :111-112)
+    const long long left = (long long)(((unsigned long long)w[nx + j] << 32) | w[j]);
+    const long long right = (long long)(((unsigned long long)w[3 * nx + jl] << 32) | w[2 * nx + jl]);
+    my_partial[j] = dmul((double)(left + right), inv);
+  }
+#else
   const longlong2 *sl = reinterpret_cast<const longlong2 *>(pairs);
   for (int j = threadIdx.x; j < nx; j += blockDim.x) {
     const int jl = (j == 0) ? nx - 1 : j - 1;  // right weights of the cell to the left (periodic, :111-112)
     my_partial[j] = dmul((double)(sl[j].x + sl[jl].y), inv);
   }
+#endif
 }
 
 // Marker arrays are touched once per substep.  Measured on B200 (profiles/r01_ab_experiments.md): the default cache
@@ -930,7 +997,7 @@ __device__ __forceinline__ bool push_pair_fast(const ParticleArgs &a, const doub
   if (FUSED) {
     // deposit source: w (delta-f) or p (full-f)  (src/pic1dp_interaction.F90:84-91)
     const double q0 = dep.prescale(deltaf ? awo[0] : p.x), q1 = dep.prescale(deltaf ? awo[1] : p.y);
-    constexpr bool OVERLAP = DEP == DEP_SMEM_ATOMIC && (PIC1DP_ADD2 & 1);
+    constexpr bool OVERLAP = (DEP == DEP_SMEM_ATOMIC && (PIC1DP_ADD2 & 1)) || (DEP == DEP_FIXED && (PIC1DP_ADD2 & 2));
     if constexpr (OVERLAP) {
       dep.add2(sd[0].ix, sd[0].ixr, dmul(sd[0].sl, q0), dmul(sd[0].sr, q0),       // :110, :113
                sd[1].ix, sd[1].ixr, dmul(sd[1].sl, q1), dmul(sd[1].sr, q1), !rare);
@@ -1055,7 +1122,7 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
   // constant-offset prefetch were measured slower on B200 -- 2.31 vs 2.25 ms per step in TOLERANCE mode, 2.84 vs 2.41 ms
   // with the warp-private deposit: 148 separate streams per array instead of one front moving through HBM.)
   const int64_t start = (int64_t)blockIdx.x * tile, end = a.np, stride = (int64_t)gridDim.x * tile;
-  if constexpr (DEP == DEP_FIXED) fixed_scale(dep, FUSED ? *a.dep_wmax_hi : 0u, (end - start) / stride * tile + tile);
+  if constexpr (DEP == DEP_FIXED) fixed_scale(dep, FUSED ? *a.dep_wmax_hi : 0u, (end - start) / stride * tile + tile, a.nx);
   if (PV) {
     if (start + tile <= end) v_next = ld2(a.v_cur + start + (int64_t)threadIdx.x * 2);
   }
@@ -1316,7 +1383,7 @@ __global__ void __launch_bounds__(1024, 1) k_deposit(const ParticleArgs a) {
   dep.g = DEPOSIT ? dep_setup<DEP>(smem, a.nx, my_partial) : nullptr;
   const int64_t tile = (int64_t)blockDim.x * 2;
   if constexpr (DEP == DEP_FIXED)   // wmax set by k_absmax_hi before this launch; this CTA handles <= ceil(tiles / grid) tiles
-    fixed_scale(dep, DEPOSIT ? *a.dep_wmax_hi : 0u, ((a.np + tile - 1) / tile + gridDim.x - 1) / gridDim.x * tile);
+    fixed_scale(dep, DEPOSIT ? *a.dep_wmax_hi : 0u, ((a.np + tile - 1) / tile + gridDim.x - 1) / gridDim.x * tile, a.nx);
   __syncthreads();
   unsigned long long noob = 0;
   for (int64_t base = (int64_t)blockIdx.x * tile; base < a.np; base += (int64_t)gridDim.x * tile) {
