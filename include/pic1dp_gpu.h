@@ -51,17 +51,20 @@ enum {
 
 /* deposit (S^T w) strategies; all give the same sum up to fp64 summation order */
 enum {
-  PIC1DP_DEPOSIT_AUTO = 0,       /* fastest strategy that fits: WARP_PRIVATE for nx <= 256, SMEM_ATOMIC, else GLOBAL_RED */
+  PIC1DP_DEPOSIT_AUTO = 0,       /* fastest strategy that fits: FIXED (native 32-bit shared-memory adds; strict arithmetic at
+                                    any nx, tolerance arithmetic for nx <= 512; <= 2^20 markers per CTA), else
+                                    WARP_PRIVATE for nx <= 256, SMEM_ATOMIC, else GLOBAL_RED */
   PIC1DP_DEPOSIT_SMEM_ATOMIC = 1,/* per-CTA shared-memory grid of {left,right} pairs, 128-bit CAS; CTA partials reduced
                                     in fixed order */
   PIC1DP_DEPOSIT_GLOBAL_RED = 2, /* RED.ADD.F64 into an L2-resident per-CTA private grid */
   PIC1DP_DEPOSIT_WARP_PRIVATE = 3,/* per-warp private shared-memory grid, lane-ordered duplicate merge: bitwise
                                     run-to-run deterministic ("deterministic deposition"); needs >= 8 nx-sized grids in
                                     shared memory (nx <~ 2900) and degrades to FIXED beyond that */
-  PIC1DP_DEPOSIT_FIXED = 4       /* per-CTA {left,right} pair grid of 64-bit FIXED-POINT sums (value * 2^e, e from the
-                                    running max |w|): integer adds are order-independent, so the density is bitwise
-                                    reproducible for any nx the pair grid fits (<~ 9600), within ~1e-14 max|w| per
-                                    contribution of the fp64 sum */
+  PIC1DP_DEPOSIT_FIXED = 4       /* per-CTA grid of 64-bit FIXED-POINT left / right sums (value * 2^e, e from the running
+                                    max |w|), each add = two native 32-bit shared-memory adds (low word, high word +
+                                    carry): integer adds are order-independent, so the density is bitwise reproducible
+                                    for any nx the grid fits (<~ 9600), within ~1e-14 max|w| per contribution of the
+                                    fp64 sum */
 };
 
 /* how the fused kernel reads marker arrays */
