@@ -629,7 +629,8 @@ def main():
         lt2 = g.launch_timing_stop()
         barrier()
         t_i1, t_i2 = lt2[0][0] / max(lt2[0][1], 1), lt2[1][0] / max(lt2[1][1], 1)
-        alt = {"arith_mode": other, "value": ntotal * args.steps / (ms2 * 1e-3), "unit": "particle-steps/s",
+        alt = {"arith_mode": other, "deposit_mode": int(g.counters().deposit_mode),
+               "value": ntotal * args.steps / (ms2 * 1e-3), "unit": "particle-steps/s",
                "ms_per_step": ms2 / args.steps, "step_roofline_frac": n * BYTES_STEP / (ms2 / args.steps * 1e-3) / 1e9 / peak,
                "irk1": {"ms_per_launch": t_i1, "frac": n * BYTES_IRK1 / (t_i1 * 1e-3) / 1e9 / peak},
                "irk2": {"ms_per_launch": t_i2, "frac": n * BYTES_IRK2 / (t_i2 * 1e-3) / 1e9 / peak},

@@ -51,9 +51,8 @@ enum {
 
 /* deposit (S^T w) strategies; all give the same sum up to fp64 summation order */
 enum {
-  PIC1DP_DEPOSIT_AUTO = 0,       /* fastest strategy that fits: FIXED (native 32-bit shared-memory adds; strict arithmetic at
-                                    any nx, tolerance arithmetic for nx <= 512; <= 2^20 markers per CTA), else
-                                    WARP_PRIVATE for nx <= 256, SMEM_ATOMIC, else GLOBAL_RED */
+  PIC1DP_DEPOSIT_AUTO = 0,       /* fastest strategy that fits: FIXED (native 32-bit shared-memory adds; up to 2^20 markers
+                                    per CTA), else WARP_PRIVATE for nx <= 256, SMEM_ATOMIC, else GLOBAL_RED */
   PIC1DP_DEPOSIT_SMEM_ATOMIC = 1,/* per-CTA shared-memory grid of {left,right} pairs, 128-bit CAS; CTA partials reduced
                                     in fixed order */
   PIC1DP_DEPOSIT_GLOBAL_RED = 2, /* RED.ADD.F64 into an L2-resident per-CTA private grid */

@@ -435,16 +435,16 @@ static int create_impl(pic1dp_gpu_t *h) {
     // measured on B200 (profiles/r01_config_sweep.md): the warp-private deposit wins on small grids (nx <= 256: more
     // intra-CTA contention for the CAS loop, and 32 private grids still fit), the 128-bit-CAS deposit elsewhere;
     // RED.ADD.F64 to L2 only when the pair grid does not fit in shared memory.
-    // Round 2 (profiles/r02_ab_experiments.md, calls r02x / r02y): with strict arithmetic the fixed-point deposit with
-    // native 32-bit adds beats the CAS deposit (2.135 vs 2.25 ms per step at 1e8 markers, nx = 1024) and, on small
-    // grids, the warp-private one (6.4e6 markers, nx = 192: 0.162 vs 0.177 ms; the native add resolves collisions in
-    // the unit instead of in a retry loop), and it is bitwise reproducible; with the tolerance arithmetic the CAS
-    // deposit stays ahead at nx = 1024 (2.17 vs 2.24 ms).  The fixed-point quantum grows with the markers a CTA
-    // handles, so AUTO keeps it to <= 2^20 markers per CTA (1.5e8 per GPU).
-    // Tolerance arithmetic on small grids (call r02z): 6.4e6 markers, nx = 192: 0.160 (fixed point) vs 0.180 ms
-    // (warp-private); 1e7, nx = 256: 0.240 vs 0.263 ms.
-    const bool fixed_ok = (p.arith_mode == PIC1DP_ARITH_STRICT || nx <= 512) && smem_need(DEP_FIXED, 512) <= max_smem &&
-                          p.capacity <= ((int64_t)1 << 20) * h->nsm && !getenv("PIC1DP_AUTO_NO_FIXED");
+    // Round 2 (profiles/r02_ab_experiments.md, calls r02x / r02y / r02z / r02h): the fixed-point deposit with native
+    // 32-bit adds beats the CAS deposit (strict arithmetic, 1e8 markers, nx = 1024: 2.135 vs 2.25 ms per step) and, on
+    // small grids, the warp-private one (6.4e6 markers, nx = 192: 0.162 vs 0.177 ms; the native add resolves collisions
+    // in the unit instead of in a retry loop), and it is bitwise reproducible.  With the tolerance arithmetic the CAS
+    // deposit is 2 % ahead in a 20-step burst at nx = 1024 (2.18 vs 2.22 ms) but 8 % behind once the part runs under
+    // its power cap, which is where a real run lives (500 steps: 2.27 vs 2.47 ms): fewer instructions win there.
+    // The fixed-point quantum grows with the markers a CTA handles, so AUTO keeps it to <= 2^20 markers per CTA
+    // (1.5e8 per GPU).
+    const bool fixed_ok = smem_need(DEP_FIXED, 512) <= max_smem && p.capacity <= ((int64_t)1 << 20) * h->nsm &&
+                          !getenv("PIC1DP_AUTO_NO_FIXED");
     if (fixed_ok)
       dep = DEP_FIXED;
     else if (nx <= 256 && warp_private_threads() >= 1024)
