@@ -282,3 +282,29 @@ def test_tolerance_arithmetic_ten_steps_within_north_star_bar(dep):
         out = g.get_markers(0)
     for k in ("x", "v", "w"):
         assert rel_err(out[k], ref.st[0][0][k]) < 1e-12, k
+
+
+@pytest.mark.parametrize("nx,arith", [(192, 0), (256, 0), (1024, 0), (1024, 1), (4096, 0)])
+def test_default_deposit_is_the_reproducible_fixed_point_one(nx, arith):
+    """PIC1DP_DEPOSIT_AUTO selects the fixed-point deposit with native 32-bit shared-memory adds (the fastest one on
+    B200 at every grid size): two runs of the DEFAULT configuration agree bit for bit in rho, E, x, w, and match the
+    oracle; the CAS deposit (fp64 sums in arrival order) agrees with it to the summation tolerance."""
+    n = 300_007
+    op, gp = make_params(nx=nx, capacity=n, arith_mode=arith)
+    st = synth_markers(op, n, seed=27, spread=0.2)
+    ref = OracleRun(op, [[copy_state(st)]])
+    ref.init_field()
+    for _ in range(3):
+        ref.step()
+    a, b = _run(gp, st, 3), _run(gp, st, 3)
+    assert a[2].deposit_mode == P.DEPOSIT_FIXED
+    assert np.array_equal(a[0]["chargeden"], b[0]["chargeden"]) and np.array_equal(a[0]["electric"], b[0]["electric"])
+    assert np.array_equal(a[1]["w"], b[1]["w"]) and np.array_equal(a[1]["x"], b[1]["x"])
+    assert rel_err(a[0]["chargeden"], ref.rho) < TOL_SUM and rel_err(a[0]["electric"], ref.E) < TOL_SUM
+    wtol = 1e-12
+    for k in ("x", "v", "w"):
+        assert rel_err(a[1][k], ref.st[0][0][k]) < wtol, k
+    _, gp_cas = make_params(nx=nx, capacity=n, arith_mode=arith, deposit_mode=P.DEPOSIT_SMEM_ATOMIC)
+    c = _run(gp_cas, st, 3)
+    assert c[2].deposit_mode == P.DEPOSIT_SMEM_ATOMIC
+    assert rel_err(c[0]["chargeden"], a[0]["chargeden"]) < TOL_SUM
