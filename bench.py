@@ -564,6 +564,8 @@ def main():
                     "h2d_bytes_per_step": (cc.h2d_bytes - cc0.h2d_bytes) / k,
                     "d2h_bytes_per_step": (cc.d2h_bytes - cc0.d2h_bytes) / k}
 
+        g.output_all(64, 64, 8.0)   # untimed warm-up of the output path (on N > 1 ranks the first ncclAllReduce of the
+        g.sync()                    # histograms sets up its channels: ~5 ms that are not part of a step)
         e2e = e2e_run(args.steps, load_from_host)
         e2e["definition"] = ("reference driver loop through the C ABI, host wall clock, max over ranks: particle_load as "
                              "pic1dp_gpu_load_markers_kiss64 (the host passes multirand's 32-byte KISS64 state, the device "
