@@ -487,9 +487,10 @@ def main():
         if rank == 0:
             p2p_trace = analyse_trace(rows, 2 * args.steps, cap)
 
-    # ---- sustained: the same loop for >= 500 further steps (graph replay, no per-launch events) ----
-    sustained = None
-    if args.sustained_steps > 0:
+    # ---- sustained: the same loop for >= 500 further steps (graph replay, no per-launch events).  Runs AFTER the
+    # driver-length e2e region below, so that `value` and `e2e` are both measured from the same (cool) state and
+    # `sustained` / `e2e.sustained` both under the power cap ----
+    def run_sustained():
         s2 = ClockSampler(local)
         s2.start()
         time.sleep(0.05)
@@ -501,10 +502,11 @@ def main():
         barrier()
         ts1 = time.time()
         ms_s = max_over_ranks(ms_s)
-        sustained = {"steps": args.sustained_steps, "value": ntotal * args.sustained_steps / (ms_s * 1e-3),
-                     "unit": "particle-steps/s", "ms_per_step": ms_s / args.sustained_steps,
-                     "step_roofline_frac": n * BYTES_STEP / (ms_s / args.sustained_steps * 1e-3) / 1e9 / measured_peak()[0],
-                     "clocks": s2.stop(ts0, ts1), "graph_replays": int(g.counters().graph_replays)}
+        return {"steps": args.sustained_steps, "value": ntotal * args.sustained_steps / (ms_s * 1e-3),
+                "unit": "particle-steps/s", "ms_per_step": ms_s / args.sustained_steps,
+                "step_roofline_frac": n * BYTES_STEP / (ms_s / args.sustained_steps * 1e-3) / 1e9 / measured_peak()[0],
+                "clocks": s2.stop(ts0, ts1), "graph_replays": int(g.counters().graph_replays)}
+    sustained = None
     g.output_all(64, 64, 8.0)            # one-time scratch allocations of the diagnostics happen here, untimed
 
     # ---- roofline of the dominant kernel, CUDA events around each launch ----
@@ -564,8 +566,6 @@ def main():
                     "h2d_bytes_per_step": (cc.h2d_bytes - cc0.h2d_bytes) / k,
                     "d2h_bytes_per_step": (cc.d2h_bytes - cc0.d2h_bytes) / k}
 
-        g.output_all(64, 64, 8.0)   # untimed warm-up of the output path (on N > 1 ranks the first ncclAllReduce of the
-        g.sync()                    # histograms sets up its channels: ~5 ms that are not part of a step)
         e2e = e2e_run(args.steps, load_from_host)
         e2e["definition"] = ("reference driver loop through the C ABI, host wall clock, max over ranks: particle_load as "
                              "pic1dp_gpu_load_markers_kiss64 (the host passes multirand's 32-byte KISS64 state, the device "
@@ -573,7 +573,8 @@ def main():
                              "get_field (E, rho, modes) to pinned host memory after every step, output_all every "
                              f"{OUTPUT_EVERY} steps and at the end (reference cadence, src/pic1dp.F90:98-108) as "
                              "pic1dp_gpu_output_all (one fused device pass, results to the host)")
-        if sustained is not None:   # the same loop at the sustained length: start-up costs amortised as in a real run
+        if args.sustained_steps > 0:   # the same loop at the sustained length: start-up costs amortised as in a real run
+            sustained = run_sustained()
             ks = min(args.sustained_steps, 200)
             e2e["sustained"] = e2e_run(ks, load_from_host)
         if args.e2e_extras and n <= 200_000_000:
@@ -607,6 +608,9 @@ def main():
         t_ld = g.timer_stop()
         e2e["output_step_ms"] = {"output_all": t_oa}
         e2e["particle_load_ms"] = t_ld
+
+    if sustained is None and args.sustained_steps > 0:   # --no-e2e
+        sustained = run_sustained()
 
     # ---- the other arithmetic mode, same workload, same box, same run (device-timed like `value`) ----
     alt = None
