@@ -27,7 +27,7 @@ struct DiagArgs {
   double *hist;         // [ncopies][3][nv_opd*nx_opd], accumulated with RED.ADD.F64 (L2 resident)
   // limb path (k_diag_limb): exact fixed-point accumulation with native 32-bit shared-memory adds
   __int128 *tab;                  // [gridDim.x][3][ncell] per-CTA integer histograms (L2 resident), zeroed before the launch
-  const unsigned *max_hi;         // [2] high words of max |p|, max |w| over this species (k_absmax_hi)
+  const unsigned *max_p_hi, *max_w_hi;   // high words of (a bound on) max |p| and max |w| over this species
 };
 
 template <bool SUMS, bool HIST>
@@ -226,8 +226,9 @@ __global__ void __launch_bounds__(PIC1DP_DIAG_THREADS, 1) k_diag_fused(const Dia
 // Integer addition is associative: the histograms are bitwise reproducible from run to run and independent of the
 // order in which markers, warps and CTAs arrive.  Accuracy: each contribution is rounded once to 2^-47 of the power of
 // two above the largest |p| (|w|) of the species (<= 7.2e-15 relative to it); the sums are exact.
-// The scales come from device-resident maxima (k_absmax_hi: p once per marker set, w before every output), so no
-// host synchronisation is needed between the passes.
+// The scales come from device-resident maxima (p: k_absmax_hi once per marker set; w: the running maximum that the
+// fixed-point deposit keeps anyway, else k_absmax_hi before the output), so no host synchronisation is needed between
+// the passes.
 #ifndef PIC1DP_LIMB_FLUSH
 #define PIC1DP_LIMB_FLUSH 64
 #endif
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(1024, 1) k_diag_limb(const DiagArgs a) {
   __syncthreads();
   __int128 *tab = a.tab + (size_t)blockIdx.x * 3 * ncell;
   const double sg = __hiloint2double((PIC1DP_LIMB_BITS + 1023) << 20, 0);   // weights <= 1
-  const double sf = limb_scale(a.max_hi[0], PIC1DP_LIMB_BITS), sw = limb_scale(a.max_hi[1], PIC1DP_LIMB_BITS);
+  const double sf = limb_scale(*a.max_p_hi, PIC1DP_LIMB_BITS), sw = limb_scale(*a.max_w_hi, PIC1DP_LIMB_BITS);
   const double rnx = (double)nxo, rnv = (double)(a.nv_opd - 1), two_vmax = dmul(a.v_max, 2.0);
   const double rlx = 1.0 / a.lx, r2v = 1.0 / two_vmax;
   double s_vv = 0.0, s_vvp = 0.0, s_vvw = 0.0;
@@ -390,8 +391,8 @@ __global__ void __launch_bounds__(1024, 1) k_diag_limb(const DiagArgs a) {
 }
 
 // out[3][ncell] = (sum over the CTA tables, exact in 128-bit integers) / scale.  CTA = 64 entries x 4 groups of tables.
-__global__ void __launch_bounds__(256) k_diag_limb_final(const __int128 *tab, int ntab, int ncell, const unsigned *max_hi,
-                                                         double *out) {
+__global__ void __launch_bounds__(256) k_diag_limb_final(const __int128 *tab, int ntab, int ncell, const unsigned *max_p_hi,
+                                                         const unsigned *max_w_hi, double *out) {
   __shared__ __int128 s_part[4][64];
   const int jl = threadIdx.x & 63, grp = threadIdx.x >> 6, j = blockIdx.x * 64 + jl;
   __int128 t = 0;
@@ -402,7 +403,8 @@ __global__ void __launch_bounds__(256) k_diag_limb_final(const __int128 *tab, in
   if (grp != 0 || j >= 3 * ncell) return;
   t = s_part[0][jl] + s_part[1][jl] + s_part[2][jl] + s_part[3][jl];
   const int q = j / ncell;
-  const double scale = q == 0 ? __hiloint2double((PIC1DP_LIMB_BITS + 1023) << 20, 0) : limb_scale(max_hi[q - 1], PIC1DP_LIMB_BITS);
+  const double scale = q == 0 ? __hiloint2double((PIC1DP_LIMB_BITS + 1023) << 20, 0)
+                              : limb_scale(q == 1 ? *max_p_hi : *max_w_hi, PIC1DP_LIMB_BITS);
   // two roundings when |t| >= 2^64 (more than 2^18 markers of the largest magnitude in one cell), one otherwise
   const bool neg = t < 0;
   const unsigned __int128 u = neg ? (unsigned __int128)(-t) : (unsigned __int128)t;

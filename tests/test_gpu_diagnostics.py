@@ -254,3 +254,41 @@ def test_limb_histograms_counter_flush_at_scale():
     dr = ref.o.output_ptcldist(ref.st, 0, 64, 64, 8.0)
     for k in dr:
         assert rel_err(d[0][k], dr[k]) < 1e-11, k
+
+
+@pytest.mark.parametrize("fuse", [1, 0])
+def test_limb_histogram_scale_follows_the_markers(fuse):
+    """The fixed-point scale of the delta-f histogram comes from a device-resident bound on max |w|: the running maximum
+    that the (default) fixed-point deposit keeps in fused runs, a fresh pass otherwise.  Whatever the call sequence, the
+    histograms must be those of the markers the device holds at that moment (oracle binning of get_markers())."""
+    op, gp = make_params(nx=256, capacity=150000, fuse=fuse)
+    st = synth_markers(op, 150000, seed=75)
+    ref = OracleRun(op, [[copy_state(st)]])
+
+    def check(g, what):
+        mk = g.get_markers(0)
+        d = g.output_ptcldist(0, 64, 64, 8.0)
+        dr = ref.o.output_ptcldist([[{k: mk[k] for k in ("x", "v", "p", "w")}]], 0, 64, 64, 8.0)
+        for k in dr:
+            assert rel_err(d[k], dr[k]) < 1e-11, (what, k)
+
+    with P.Pic1dGpu(gp) as g:
+        g.set_markers(0, st["x"], st["v"], st["p"], st["w"])
+        check(g, "fresh markers, nothing deposited yet")
+        g.collect_charge()
+        g.solve_field()
+        g.step(3)
+        check(g, "after three steps")
+        g.push(1)                                  # w has moved since the last output
+        if fuse:                                   # (unfused, x is not wrapped before collect_charge: nothing to bin yet)
+            check(g, "between push and collect_charge")
+        g.collect_charge()
+        g.solve_field()
+        big = {k: st[k].copy() for k in st}
+        big["w"] *= 1.0e4                          # replaced markers with a much larger |w| than any bound kept so far
+        g.set_markers(0, big["x"], big["v"], big["p"], big["w"])
+        check(g, "after set_markers with larger weights")
+        small = {k: st[k].copy() for k in st}
+        small["w"] *= 1.0e-6
+        g.set_markers(0, small["x"], small["v"], small["p"], small["w"])
+        check(g, "after set_markers with smaller weights")
