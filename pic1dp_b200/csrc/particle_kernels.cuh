@@ -27,6 +27,10 @@
 #endif
 // which fused-kernel variants stage the next tile step's v in registers (same bit layout as PIC1DP_PF_MASK).
 // Measured on B200 at 1e8 markers, nx = 1024: warp-private irk=1 1.264 -> 1.158 ms; atomic deposits +0.5 % slower.
+// how many tile steps ahead the L2 prefetch runs (2 measured 6 % slower than 1 in both arithmetic modes, call r02n)
+#ifndef PIC1DP_PF_DIST
+#define PIC1DP_PF_DIST 1
+#endif
 #ifndef PIC1DP_PV_MASK
 #define PIC1DP_PV_MASK 4
 #endif
@@ -1134,7 +1138,7 @@ __global__ void __launch_bounds__(PIC1DP_MAXTHREADS, 1) k_push(const ParticleArg
     // deposit in both substeps and the atomic deposit at irk=1 (1.060 -> 1.040 ms: with the rare-path-free body the
     // first use of the streamed v is the top stall) and hurts the HBM-bound atomic irk=2 kernel (1.24 -> 1.54 ms).
     if (PIC1DP_PF_MASK & ((DEP == DEP_WARP_PRIVATE ? 4 : 1) << (IRK2 ? 1 : 0))) {
-      const int64_t ahead = stride;
+      const int64_t ahead = PIC1DP_PF_DIST * stride;
       if (i + ahead + 1 < end) {
         prefetch_l2(px + ahead);
         prefetch_l2(pv + ahead);
