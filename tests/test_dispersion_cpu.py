@@ -42,3 +42,21 @@ def test_zero_of_a_cold_limit():
     """Sanity of the Z-function form: for k -> 0 the thermal root tends to the plasma frequency (omega_p = 1)."""
     om = D.solve_omega(0.05, D.THERMAL, (1.0 - 0.0j, 1.01 - 0.001j, 0.99 + 0.001j))
     assert abs(om.real - (1.0 + 1.5 * 0.05 ** 2)) < 1e-4 and abs(om.imag) < 1e-6  # Bohm-Gross: 1 + 3/2 k^2
+
+
+def test_traffic_json_is_what_the_converter_makes_of_the_committed_ncu_csv():
+    """profiles/r02_traffic.json (the source of bench.py's roofline.traffic) must be reproducible from the ncu CSV
+    committed beside it: measured DRAM bytes per marker at the bench size, within 1 % of the algorithmic 56 / 80 B."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = json.load(open(os.path.join(root, "profiles", "r02_traffic.json")))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools_py3", "traffic_json.py"),
+                          os.path.join(root, "profiles", "r02_traffic.csv"), str(want["markers"]), str(want["nx"]),
+                          str(want["deposit_mode"])], capture_output=True, text=True, check=True).stdout
+    got = json.loads(out)
+    for irk, alg in (("irk1", 56), ("irk2", 80)):
+        assert got[irk]["dram_bytes_per_marker"] == want[irk]["dram_bytes_per_marker"]
+        assert abs(got[irk]["dram_bytes_per_marker"] / alg - 1.0) < 0.01
